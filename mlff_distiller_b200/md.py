@@ -1,0 +1,102 @@
+"""Host-side NVE driver used by configs C1/C3/C4 when ASE is not installed.
+
+Restates what the reference's MD harness does around the calculator
+(src/mlff_distiller/testing/nve_harness.py:141-171 initial velocities, :214-235 VelocityVerlet,
+:329-331 drift metric; energy_metrics.py:74-80): Maxwell-Boltzmann velocities at T0 with the
+centre-of-mass translation (and optionally rotation) removed, textbook velocity-Verlet
+half-kick / drift / half-kick in ASE units (eV, Angstrom, amu; time unit
+``fs = 1e-15 s * sqrt(e/amu) / Angstrom``), and ``drift % = 100 (E_tot[-1] - E_tot[0]) / |E_tot[0]|``
+with E_tot = PE + KE sampled every step.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import numpy as np
+
+# CODATA-2014 constants as ASE uses them (ase/units.py): eV, Angstrom, amu base units.
+_E = 1.6021766208e-19
+_AMU = 1.660539040e-27
+KB = 8.6173303e-5  # eV / K
+FS = 1e-15 * np.sqrt(_E / _AMU) * 1e10  # = 0.09822694788...
+
+# Standard atomic weights (IUPAC abridged), index = atomic number.
+ATOMIC_MASSES = np.array([
+    1.0, 1.008, 4.002602, 6.94, 9.0121831, 10.81, 12.011, 14.007, 15.999, 18.998403163, 20.1797,
+    22.98976928, 24.305, 26.9815385, 28.085, 30.973761998, 32.06, 35.45, 39.948, 39.0983, 40.078,
+    44.955908, 47.867, 50.9415, 51.9961, 54.938044, 55.845, 58.933194, 58.6934, 63.546, 65.38,
+    69.723, 72.630, 74.921595, 78.971, 79.904, 83.798, 85.4678, 87.62, 88.90584, 91.224,
+    92.90637, 95.95, 97.90721, 101.07, 102.90550, 106.42, 107.8682, 112.414, 114.818, 118.710,
+    121.760, 127.60, 126.90447, 131.293, 132.90545196, 137.327, 138.90547, 140.116, 140.90766,
+    144.242, 144.91276, 150.36, 151.964, 157.25, 158.92535, 162.500, 164.93033, 167.259,
+    168.93422, 173.054, 174.9668, 178.49, 180.94788, 183.84, 186.207, 190.23, 192.217, 195.084,
+    196.966569, 200.592, 204.38, 207.2, 208.98040, 208.98243, 209.98715, 222.01758, 223.01974,
+    226.02541, 227.02775, 232.0377, 231.03588, 238.02891, 237.04817, 244.06421, 243.06138,
+    247.07035, 247.07031, 251.07959, 252.0830, 257.09511, 258.09843, 259.1010, 262.110, 267.122,
+    268.126, 271.134, 270.133, 269.1338, 278.156, 281.165, 281.166, 285.177, 286.182, 289.190,
+    289.194, 293.204, 293.208, 294.214])
+
+
+def maxwell_boltzmann(masses: np.ndarray, temperature_K: float, rng: np.random.Generator,
+                      positions: Optional[np.ndarray] = None, zero_rotation: bool = False
+                      ) -> np.ndarray:
+    """Velocities [N,3] (ASE units) drawn at T, COM momentum removed (nve_harness.py:158-165)."""
+    m = np.asarray(masses, dtype=np.float64)[:, None]
+    v = rng.normal(size=(len(m), 3)) * np.sqrt(KB * temperature_K / m)
+    v -= (m * v).sum(0) / m.sum()
+    if zero_rotation and positions is not None and len(m) > 2:
+        x = positions - (m * positions).sum(0) / m.sum()
+        L = (m * np.cross(x, v)).sum(0)
+        I = np.zeros((3, 3))
+        for a in range(len(m)):
+            r = x[a]
+            I += m[a, 0] * ((r @ r) * np.eye(3) - np.outer(r, r))
+        try:
+            omega = np.linalg.solve(I, L)
+            v -= np.cross(omega, x)
+        except np.linalg.LinAlgError:
+            pass
+    return v
+
+
+def kinetic_energy(masses: np.ndarray, velocities: np.ndarray) -> float:
+    return float(0.5 * np.sum(np.asarray(masses)[:, None] * velocities ** 2))
+
+
+def energy_drift_percent(e_total: np.ndarray) -> float:
+    """nve_harness.py:329-331."""
+    return float(100.0 * (e_total[-1] - e_total[0]) / abs(e_total[0]))
+
+
+def velocity_verlet(force_fn: Callable[[np.ndarray], Tuple[float, np.ndarray]],
+                    positions: np.ndarray, velocities: np.ndarray, masses: np.ndarray,
+                    steps: int, dt_fs: float = 0.5, record_every: int = 1) -> Dict[str, np.ndarray]:
+    """NVE trajectory; ``force_fn(positions) -> (potential energy, forces[N,3])``.
+
+    One force evaluation per step, float64 integrator on the host, like ASE's VelocityVerlet.
+    Returns positions/velocities at the end and the PE/KE/E_tot series (step 0 included).
+    """
+    dt = dt_fs * FS
+    x = np.array(positions, dtype=np.float64)
+    v = np.array(velocities, dtype=np.float64)
+    m = np.asarray(masses, dtype=np.float64)[:, None]
+    pe, f = force_fn(x)
+    f = np.asarray(f, dtype=np.float64)
+    pes, kes = [float(pe)], [kinetic_energy(m[:, 0], v)]
+    for step in range(1, steps + 1):
+        v += 0.5 * dt * f / m
+        x += dt * v
+        pe, f = force_fn(x)
+        f = np.asarray(f, dtype=np.float64)
+        v += 0.5 * dt * f / m
+        if step % record_every == 0 or step == steps:
+            pes.append(float(pe))
+            kes.append(kinetic_energy(m[:, 0], v))
+    pes_a, kes_a = np.asarray(pes), np.asarray(kes)
+    return {"positions": x, "velocities": v, "potential": pes_a, "kinetic": kes_a,
+            "total": pes_a + kes_a, "drift_percent": energy_drift_percent(pes_a + kes_a)}
+
+
+def ns_per_day(steps_per_second: float, dt_fs: float = 0.5) -> float:
+    """ns/day = steps/s * dt[fs] * 86400 * 1e-6."""
+    return steps_per_second * dt_fs * 86400.0 * 1e-6
