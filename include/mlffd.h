@@ -1,0 +1,187 @@
+/*
+ * mlffd.h -- C ABI of the B200-native PaiNN-student energy+force library (libmlffd.so).
+ *
+ * The reference (atfrank/MLFF-Distiller) is 100% Python and has no FFI boundary for this path;
+ * the entry points below are what a binding for its two hot-path classes needs.  Each export
+ * cites the reference interface it replaces (paths relative to /root/reference).  All pointers
+ * suffixed _d are DEVICE pointers (plain CUDA memory, e.g. torch.Tensor.data_ptr()); `stream`
+ * is a cudaStream_t passed as void*.  No torch / C++ types cross the boundary.
+ *
+ * Conventions: return 0 on success, a negative MLFFD_E* code on failure; never throws.  A
+ * context is bound to one device and is NOT thread-safe; distinct contexts are independent
+ * (multi-GPU = one context per GPU).  All work is enqueued asynchronously on `stream`; only
+ * mlffd_model_create, mlffd_workspace_reserve, mlffd_get_status and mlffd_debug_buffer
+ * synchronise.  There is no CPU fallback: every call fails with MLFFD_ECUDA without a GPU.
+ */
+#ifndef MLFFD_H
+#define MLFFD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLFFD_ABI_VERSION 1
+
+enum {
+    MLFFD_OK = 0,
+    MLFFD_EINVAL = -1,    /* bad argument (null pointer, unsupported hidden_dim, ...) */
+    MLFFD_ECUDA = -2,     /* CUDA runtime error; text in mlffd_last_error */
+    MLFFD_ECAPACITY = -3, /* workspace too small for the request (reserve more and retry) */
+    MLFFD_ENOMEM = -4
+};
+
+/* Arithmetic of the dense layers.  FP32 is the parity default (north-star tolerances 1e-5
+ * eV/atom, 1e-4 eV/A); the others trade accuracy for tensor-core speed with looser bounds. */
+enum {
+    MLFFD_PREC_FP32 = 0,
+    MLFFD_PREC_TF32X3 = 1,
+    MLFFD_PREC_TF32 = 2,
+    MLFFD_PREC_BF16 = 3
+};
+
+/* Hyper-parameters = the `config` dict of StudentForceField.save
+ * (src/mlff_distiller/models/student_model.py:1087-1094). */
+typedef struct mlffd_config {
+    int32_t hidden_dim;       /* H: 128 (Original), 64 (Tiny), 32 (Ultra-tiny) */
+    int32_t num_rbf;          /* K <= 32 */
+    int32_t num_interactions; /* L <= 8 */
+    int32_t max_z;            /* embedding has max_z + 1 rows */
+    float cutoff;             /* r_c in Angstrom */
+    int32_t precision;        /* MLFFD_PREC_* */
+} mlffd_config;
+
+/* Read back by mlffd_get_status (synchronises the stream of the last call). */
+typedef struct mlffd_status {
+    int64_t num_atoms;
+    int64_t num_edges;   /* directed edges found by the last neighbour build */
+    int64_t num_pairs;   /* undirected pairs = num_edges / 2 */
+    int64_t edge_capacity;
+    int32_t overflow;    /* 1: edges exceeded capacity, outputs invalid -> reserve and retry */
+    int32_t max_degree;
+} mlffd_status;
+
+typedef struct mlffd_ctx mlffd_ctx;
+
+int mlffd_version(void);
+
+/* Message of the last failure on `ctx` (or of the last failed create when ctx == NULL). */
+const char* mlffd_last_error(const mlffd_ctx* ctx);
+
+/*
+ * Replaces StudentForceField.__init__ + load_state_dict (student_model.py:566-616, 1164-1170).
+ * `weights_host`: every tensor of the reference state_dict, FP32 little-endian, row-major, torch
+ * [out,in] layout for Linear weights, concatenated in this order:
+ *   embedding.weight [max_z+1,H]; rbf.centers [K]; rbf.widths [K];
+ *   for l in 0..L-1: message.rbf_to_scalar.0.{weight [H,K], bias [H]},
+ *                    message.rbf_to_scalar.2.{weight [3H,H], bias [3H]},
+ *                    update.update_mlp.0.{weight [H,2H], bias [H]},
+ *                    update.update_mlp.2.{weight [3H,H], bias [3H]}, update.mixing_matrix [3,3];
+ *   energy_head.0.{weight [H/2,H], bias [H/2]}; energy_head.2.{weight [H/4,H/2], bias [H/4]};
+ *   energy_head.4.{weight [1,H/4], bias [1]}.
+ * The library copies and re-lays the weights out on `device`; the caller keeps the host blob.
+ */
+int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_config* config,
+                       const float* weights_host, size_t num_floats);
+void mlffd_model_destroy(mlffd_ctx* ctx);
+
+/* Pre-size every scratch buffer; nothing is allocated on the hot path afterwards.  Growing is
+ * allowed at any time (synchronises).  max_edges counts DIRECTED edges. */
+int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_t max_edges,
+                            int64_t max_structures);
+
+/*
+ * Replaces radius_graph / radius_graph_native (student_model.py:63-109, 165-191).
+ *   pos_d      [N,3] f32 positions
+ *   offsets_d  [B+1] i32 first atom of each structure (replaces the `batch` vector)
+ *   cells_d    [B,18] f32: row-major 3x3 cell followed by its row-major 3x3 inverse, or NULL
+ *   pbc_d      [B,3] u8 periodic flags, or NULL (open boundaries, the reference's behaviour)
+ * Builds destination-sorted CSR (sources ascending within a row) inside the context.
+ * Edge (i -> j) iff same structure, i != j and |x_i - x_j (minimum image)| <= cutoff in FP32.
+ */
+int mlffd_neighbor_list(mlffd_ctx* ctx, const float* pos_d, const int32_t* offsets_d,
+                        int32_t num_structures, int64_t num_atoms, const float* cells_d,
+                        const uint8_t* pbc_d, void* stream);
+
+/* Copy the last neighbour list out as the reference's edge_index [2,E] int64, row 0 = src,
+ * row 1 = dst, lexicographic (src,dst) order (student_model.py:106-107).  `capacity_edges` is
+ * the room in edge_index_d per row; fails with MLFFD_ECAPACITY if smaller than E (syncs). */
+int mlffd_export_edges(mlffd_ctx* ctx, int64_t* edge_index_d, int64_t capacity_edges,
+                       int64_t* num_edges_out, void* stream);
+
+/*
+ * Replaces StudentForceField.forward + predict_energy_and_forces (student_model.py:634-795) and
+ * the batched recipe of StudentForceFieldCalculator._batch_forward
+ * (src/mlff_distiller/inference/ase_calculator.py:708-770).
+ *   z_d        [N] i32 atomic numbers (0..max_z)
+ *   energy_d   [B] f32 out: total energy per structure (eV)
+ *   forces_d   [N,3] f32 out: -dE/dx (eV/A); NULL = energy only (no reverse pass)
+ * Runs neighbour build, filter tables, L x (message, update), readout and the analytical
+ * reverse pass, all on `stream`, no host synchronisation.  Check mlffd_get_status().overflow
+ * after synchronising: if set, the outputs are invalid; reserve more edges and call again.
+ */
+int mlffd_energy_forces(mlffd_ctx* ctx, const int32_t* z_d, const float* pos_d,
+                        const int32_t* offsets_d, int32_t num_structures, int64_t num_atoms,
+                        const float* cells_d, const uint8_t* pbc_d, float* energy_d,
+                        float* forces_d, void* stream);
+
+int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out);
+
+/*
+ * Stage entry point (parity tests, ncu): evaluate the per-layer radial filter and its
+ * d-derivative for `num_pairs` distances.  Restates PaiNNMessage.rbf_to_scalar applied to
+ * GaussianRBF * CosineCutoff (student_model.py:249-255, 285-292, 318-322, 350).
+ *   dist_d [P] f32 -> filter_d [P,3H] f32, dfilter_d [P,3H] f32 (d filter / d distance)
+ */
+int mlffd_filter_table(mlffd_ctx* ctx, int32_t layer, const float* dist_d, int64_t num_pairs,
+                       float* filter_d, float* dfilter_d, void* stream);
+
+/*
+ * Test hook: device pointer + element count of an internal buffer of the last call
+ * (synchronises).  Names: "rowptr","col","rev","pair","edge_dst","geo" (float4 ux,uy,uz,d),
+ * "pair_dist", "filter"/"dfilter" (layer), "s_in"/"v_in"/"s_msg"/"v_msg"/"y1"/"gates" (layer),
+ * "s_out", "atom_energy", "sbar"/"vbar" (adjoints of s_msg / v_msg of `layer`; all layers are
+ * kept only when the context was created with MLFFD_DEBUG_KEEP=1 in the environment, otherwise
+ * two sets ping-pong), "edge_adj" (float4 dE/du_x, dE/du_y, dE/du_z, dE/dd through the filters).
+ * elem_size_out: bytes per element.
+ */
+int mlffd_debug_buffer(mlffd_ctx* ctx, const char* name, int32_t layer, void** ptr_out,
+                       int64_t* count_out, int32_t* elem_size_out);
+
+/*
+ * Launch accounting and per-stage device timing (bench.py roofline / gpu_launches).  While
+ * enabled, a CUDA event is recorded on the step's stream after every kernel of a stage, so
+ * stage_ms is the device time of that stage's kernels inside the live step (the analogue of the
+ * reference's CUDATimer, src/mlff_distiller/cuda/benchmark_utils.py:147-193, moved inside the
+ * step).  enable resets the counters; read synchronises and accumulates.
+ */
+enum {
+    MLFFD_STAGE_NEIGHBOR = 0,
+    MLFFD_STAGE_EMBEDDING = 1,
+    MLFFD_STAGE_FILTER = 2,
+    MLFFD_STAGE_MESSAGE_FWD = 3,
+    MLFFD_STAGE_UPDATE_FWD = 4,
+    MLFFD_STAGE_READOUT = 5,
+    MLFFD_STAGE_ENERGY_SUM = 6,
+    MLFFD_STAGE_UPDATE_BWD = 7,
+    MLFFD_STAGE_MESSAGE_BWD = 8,
+    MLFFD_STAGE_FORCE = 9,
+    MLFFD_NUM_STAGES = 10
+};
+
+typedef struct mlffd_profile {
+    int64_t launches;                         /* kernels launched since enable */
+    int64_t stage_launches[MLFFD_NUM_STAGES];
+    double stage_ms[MLFFD_NUM_STAGES];        /* only filled while profiling is enabled */
+} mlffd_profile;
+
+int mlffd_profile_enable(mlffd_ctx* ctx, int32_t enable);
+int mlffd_profile_read(mlffd_ctx* ctx, mlffd_profile* out);
+const char* mlffd_stage_name(int32_t stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLFFD_H */

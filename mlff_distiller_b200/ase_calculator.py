@@ -1,0 +1,320 @@
+"""``StudentForceFieldCalculator`` on the B200 CUDA path.
+
+Mirrors the reference calculator (src/mlff_distiller/inference/ase_calculator.py:61-886, paths
+relative to /root/reference): constructor keywords (:105-120), ``calculate`` with ASE result
+caching (:279-412), input validation and its exception types/messages (:414-459),
+``calculate_batch`` (:590-817), ``reset`` / ``n_calls`` / ``avg_time`` / ``get_timing_stats``
+(:819-874) and ``__repr__`` (:876-883).  When ASE is installed the class derives from
+``ase.calculators.calculator.Calculator``; otherwise a small stand-in base provides the same
+caching contract so MD drivers and tests run without ASE.
+
+Everything numeric happens in libmlffd.so; the reference's optimisation switches
+(``use_compile``, ``use_fp16``, ``use_jit``, ``use_torch_cluster``, ``use_analytical_forces``,
+``batch_size``) are accepted for call-site compatibility and ignored with a log line.
+"""
+from __future__ import annotations
+
+import logging
+import time
+import warnings
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from .student_model import StudentForceField
+
+logger = logging.getLogger(__name__)
+
+try:  # pragma: no cover - ASE is optional
+    from ase.calculators.calculator import Calculator as _AseCalculator, all_changes
+    HAVE_ASE = True
+except Exception:  # ImportError or a broken install
+    HAVE_ASE = False
+    all_changes = ["positions", "numbers", "cell", "pbc", "initial_charges", "initial_magmoms"]
+
+    class _AseCalculator:  # minimal stand-in with ASE's caching contract
+        implemented_properties: List[str] = []
+
+        def __init__(self, **kwargs):
+            self.atoms = None
+            self.results: Dict[str, Any] = {}
+            self.parameters = dict(kwargs)
+
+        def reset(self):
+            self.atoms = None
+            self.results = {}
+
+        def calculate(self, atoms=None, properties=("energy",), system_changes=all_changes):
+            if atoms is not None:
+                self.atoms = atoms.copy()
+
+        def _changed(self, atoms) -> bool:
+            a = self.atoms
+            if a is None or len(a) != len(atoms):
+                return True
+            return not (np.array_equal(a.get_positions(), atoms.get_positions())
+                        and np.array_equal(a.get_atomic_numbers(), atoms.get_atomic_numbers())
+                        and np.array_equal(np.asarray(a.get_cell()), np.asarray(atoms.get_cell()))
+                        and np.array_equal(a.get_pbc(), atoms.get_pbc()))
+
+        def get_property(self, name, atoms=None):
+            if atoms is None:
+                atoms = self.atoms
+            if name not in self.results or self._changed(atoms):
+                self.calculate(atoms, [name], all_changes)
+            return self.results[name]
+
+        def get_potential_energy(self, atoms=None):
+            return self.get_property("energy", atoms)
+
+        def get_forces(self, atoms=None):
+            return self.get_property("forces", atoms)
+
+
+class StudentForceFieldCalculator(_AseCalculator):
+    """ASE-style calculator backed by the hand-written CUDA energy+force path."""
+
+    def __init__(self, checkpoint_path: Union[str, Path], device: str = "cuda",
+                 dtype: torch.dtype = torch.float32, enable_stress: bool = False,
+                 batch_size: Optional[int] = None, enable_timing: bool = False,
+                 use_compile: bool = False, use_fp16: bool = False, use_jit: bool = False,
+                 jit_path: Optional[Union[str, Path]] = None, use_torch_cluster: bool = True,
+                 use_analytical_forces: bool = False, *, precision: str = "fp32",
+                 pbc_mode: str = "ignore", **kwargs):
+        super().__init__(**kwargs)
+        self.checkpoint_path = Path(checkpoint_path)
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.enable_stress = enable_stress
+        self.batch_size = batch_size
+        self.enable_timing = enable_timing
+        self.use_compile = use_compile
+        self.use_fp16 = use_fp16
+        self.use_jit = use_jit
+        self.jit_path = Path(jit_path) if jit_path else None
+        self.use_torch_cluster = use_torch_cluster
+        self.use_analytical_forces = use_analytical_forces
+        self.precision = precision
+        self.pbc_mode = pbc_mode
+        self.implemented_properties = ["energy", "forces"]
+        if self.enable_stress:
+            self.implemented_properties.append("stress")
+        if dtype != torch.float32:
+            raise ValueError("the CUDA path computes in float32; use the reference for other dtypes")
+        ignored = [n for n, v in (("use_compile", use_compile), ("use_fp16", use_fp16),
+                                  ("use_jit", use_jit), ("batch_size", batch_size)) if v]
+        if ignored:
+            logger.info("StudentForceFieldCalculator: ignoring %s (superseded by the CUDA path)", ignored)
+        self.model = self._load_model()
+        self._n_calls = 0
+        self._total_time = 0.0
+        self._call_times: List[float] = []
+        self._numbers_cache = None  # (host numbers copy, device int32 tensor)
+        self._pin_pos = None
+        self._pin_out = None
+        logger.info("Initialized StudentForceFieldCalculator: device=%s, precision=%s, pbc_mode=%s",
+                    self.device, precision, pbc_mode)
+
+    # ---- model ----------------------------------------------------------------------------
+    def _load_model(self) -> StudentForceField:
+        if not self.checkpoint_path.exists():
+            raise FileNotFoundError(
+                f"Checkpoint not found: {self.checkpoint_path}\n"
+                f"Please ensure the model has been trained and checkpoint saved.")
+        try:
+            model = StudentForceField.load(self.checkpoint_path, device=str(self.device),
+                                           precision=self.precision, pbc_mode=self.pbc_mode)
+            model.eval()
+            model.engine()  # fail loudly now if the CUDA library / device is missing
+            return model
+        except FileNotFoundError:
+            raise
+        except Exception as e:
+            raise RuntimeError(f"Failed to load model from {self.checkpoint_path}: {e}") from e
+
+    # ---- single structure -----------------------------------------------------------------
+    def calculate(self, atoms=None, properties: Sequence[str] = ("energy", "forces"),
+                  system_changes: Sequence[str] = all_changes):
+        _AseCalculator.calculate(self, atoms, properties, system_changes)
+        start = time.perf_counter() if self.enable_timing else 0.0
+        try:
+            positions = atoms.get_positions()
+            numbers = atoms.get_atomic_numbers()
+            cell = np.asarray(atoms.get_cell(), dtype=np.float64)
+            pbc = np.asarray(atoms.get_pbc(), dtype=bool)
+            self._validate_inputs(positions, numbers, cell, pbc)
+            energy, forces = self._evaluate_single(positions, numbers, cell, pbc)
+            results: Dict[str, Any] = {"energy": energy, "forces": forces}
+            if "stress" in properties and self.enable_stress:
+                results["stress"] = np.zeros(6)  # the reference's stress path also yields zeros
+            self.results = results
+            self._n_calls += 1
+            if self.enable_timing:
+                elapsed = time.perf_counter() - start
+                self._total_time += elapsed
+                self._call_times.append(elapsed)
+        except ValueError:
+            raise
+        except Exception as e:
+            logger.error("Calculation failed: %s", e, exc_info=True)
+            raise RuntimeError(f"Failed to calculate properties for {len(atoms)} atoms: {e}") from e
+
+    def _validate_inputs(self, positions, numbers, cell, pbc):
+        """Same checks and messages as ase_calculator.py:434-459; Z is validated against the
+        embedding size (the reference checks 1-118 although trained tables stop at max_z)."""
+        if len(positions) == 0:
+            raise ValueError("Cannot calculate properties for empty structure")
+        if np.any(numbers < 1) or np.any(numbers > 118):
+            raise ValueError(f"Invalid atomic numbers: must be 1-118, got {numbers}")
+        if np.any(numbers > self.model.max_z):
+            raise ValueError(f"Invalid atomic numbers: model supports Z <= {self.model.max_z}, got {numbers}")
+        if not np.isfinite(positions).all():
+            raise ValueError("Positions contain NaN or Inf values")
+        if pbc.any():
+            if not np.isfinite(cell).all():
+                raise ValueError("Cell contains NaN or Inf values")
+            volume = abs(np.linalg.det(cell))
+            if volume < 1e-6:
+                warnings.warn(f"Cell volume very small ({volume:.2e} Å³), may indicate degenerate cell",
+                              stacklevel=3)
+            if self.pbc_mode == "minimum_image":
+                self._check_minimum_image(cell, pbc)
+
+    def _check_minimum_image(self, cell, pbc):
+        """Minimum image is unique only if every periodic cell height is >= 2 r_c."""
+        vol = abs(np.linalg.det(cell))
+        for k in range(3):
+            if pbc[k]:
+                a, b = cell[(k + 1) % 3], cell[(k + 2) % 3]
+                height = vol / np.linalg.norm(np.cross(a, b))
+                if height < 2.0 * self.model.cutoff:
+                    raise ValueError(
+                        f"pbc_mode='minimum_image' needs cell heights >= 2*cutoff "
+                        f"({2 * self.model.cutoff:.2f} Å); axis {k} has {height:.3f} Å")
+
+    def _evaluate_single(self, positions, numbers, cell, pbc):
+        dev = self.device
+        n = len(numbers)
+        if (self._numbers_cache is None or len(self._numbers_cache[0]) != n
+                or not np.array_equal(self._numbers_cache[0], numbers)):
+            z_d = torch.from_numpy(np.ascontiguousarray(numbers, dtype=np.int32)).to(dev)
+            off_d = torch.tensor([0, n], dtype=torch.int32, device=dev)
+            self._numbers_cache = (np.array(numbers), z_d, off_d)
+            self._pin_pos = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+            self._pin_out = torch.empty(3 * n + 1, dtype=torch.float32).pin_memory()
+        _, z_d, off_d = self._numbers_cache
+        self._pin_pos.copy_(torch.from_numpy(np.ascontiguousarray(positions, dtype=np.float64)))
+        pos_d = self._pin_pos.to(dev, non_blocking=True)
+        cells_d = pbc_d = None
+        if self.pbc_mode == "minimum_image" and pbc.any():
+            cells_d, pbc_d = StudentForceField.pack_cells(torch.from_numpy(cell), torch.from_numpy(pbc), 1, dev)
+        e_d, f_d = self.model.energy_and_forces_packed(z_d, pos_d, off_d, 1, cells_d, pbc_d)
+        out_d = torch.cat([e_d.reshape(1), f_d.reshape(-1)])
+        self._pin_out.copy_(out_d, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        out = self._pin_out.numpy()
+        return float(out[0]), out[1:].reshape(n, 3).copy()
+
+    # ---- batches --------------------------------------------------------------------------
+    def calculate_batch(self, atoms_list, properties: Sequence[str] = ("energy", "forces")
+                        ) -> List[Dict[str, Any]]:
+        """One fused evaluation for many structures (ase_calculator.py:590-645).  ``[]`` -> ``[]``;
+        a single structure takes the single path; PBC is ignored in batch mode like the
+        reference (:735-736) unless ``pbc_mode='minimum_image'``."""
+        if not atoms_list:
+            return []
+        if len(atoms_list) == 1:
+            atoms = atoms_list[0]
+            atoms.calc = self
+            return [{
+                "energy": self.get_potential_energy(atoms) if "energy" in properties else None,
+                "forces": self.get_forces(atoms) if "forces" in properties else None,
+                "stress": None,
+            }]
+        counts = np.array([len(a) for a in atoms_list], dtype=np.int64)
+        if np.any(counts == 0):
+            raise ValueError("Cannot calculate properties for empty structure")
+        numbers = np.concatenate([a.get_atomic_numbers() for a in atoms_list])
+        positions = np.concatenate([a.get_positions() for a in atoms_list])
+        cells = pbcs = None
+        if self.pbc_mode == "minimum_image" and any(np.any(a.get_pbc()) for a in atoms_list):
+            cells = np.stack([np.asarray(a.get_cell(), dtype=np.float64) for a in atoms_list])
+            pbcs = np.stack([np.asarray(a.get_pbc(), dtype=bool) for a in atoms_list])
+        energies, forces = self.evaluate_arrays(numbers, positions, counts, cells, pbcs)
+        results, off = [], 0
+        for i, c in enumerate(counts):
+            r: Dict[str, Any] = {}
+            if "energy" in properties:
+                r["energy"] = float(energies[i])
+            if "forces" in properties:
+                r["forces"] = forces[off:off + c]
+            if "stress" in properties and self.enable_stress:
+                r["stress"] = None
+            results.append(r)
+            off += c
+        return results
+
+    def evaluate_arrays(self, numbers: np.ndarray, positions: np.ndarray, counts: np.ndarray,
+                        cells: Optional[np.ndarray] = None, pbcs: Optional[np.ndarray] = None):
+        """Host arrays in, host arrays out: (energies [B] float32, forces [N,3] float32).  The
+        batched-structure interface underneath ``calculate_batch``; validation included."""
+        numbers = np.asarray(numbers)
+        positions = np.asarray(positions)
+        counts = np.asarray(counts, dtype=np.int64)
+        if len(numbers) == 0 or np.any(counts == 0):
+            raise ValueError("Cannot calculate properties for empty structure")
+        if np.any(numbers < 1) or np.any(numbers > min(118, self.model.max_z)):
+            raise ValueError(f"Invalid atomic numbers: must be 1-{min(118, self.model.max_z)}")
+        if not np.isfinite(positions).all():
+            raise ValueError("Positions contain NaN or Inf values")
+        dev = self.device
+        nb = len(counts)
+        offsets = np.zeros(nb + 1, dtype=np.int32)
+        np.cumsum(counts, out=offsets[1:])
+        z_d = torch.from_numpy(np.ascontiguousarray(numbers, dtype=np.int32)).pin_memory().to(dev, non_blocking=True)
+        pos_d = torch.from_numpy(np.ascontiguousarray(positions, dtype=np.float32)).pin_memory().to(dev, non_blocking=True)
+        off_d = torch.from_numpy(offsets).pin_memory().to(dev, non_blocking=True)
+        cells_d = pbc_d = None
+        if cells is not None and pbcs is not None and np.any(pbcs):
+            cells_d, pbc_d = StudentForceField.pack_cells(torch.from_numpy(np.asarray(cells)),
+                                                          torch.from_numpy(np.asarray(pbcs)), nb, dev)
+        try:
+            e_d, f_d = self.model.energy_and_forces_packed(z_d, pos_d, off_d, nb, cells_d, pbc_d)
+            energies = e_d.cpu().numpy()
+            forces = f_d.cpu().numpy()
+        except Exception as e:
+            raise RuntimeError(f"Failed to calculate properties for {len(numbers)} atoms: {e}") from e
+        self._n_calls += 1
+        return energies, forces
+
+    # ---- bookkeeping ----------------------------------------------------------------------
+    def reset(self):
+        _AseCalculator.reset(self)
+        self._numbers_cache = None
+
+    @property
+    def n_calls(self) -> int:
+        return self._n_calls
+
+    @property
+    def avg_time(self) -> float:
+        return 0.0 if self._n_calls == 0 else self._total_time / self._n_calls
+
+    def get_timing_stats(self) -> Dict[str, float]:
+        if not self._call_times:
+            return {"n_calls": 0, "total_time": 0.0, "avg_time": 0.0, "min_time": 0.0,
+                    "max_time": 0.0, "median_time": 0.0}
+        t = np.array(self._call_times)
+        return {"n_calls": self._n_calls, "total_time": self._total_time,
+                "avg_time": float(np.mean(t)), "min_time": float(np.min(t)),
+                "max_time": float(np.max(t)), "median_time": float(np.median(t)),
+                "std_time": float(np.std(t))}
+
+    def __repr__(self) -> str:
+        return (f"StudentForceFieldCalculator(checkpoint={self.checkpoint_path.name}, "
+                f"device={self.device}, calls={self._n_calls})")
+
+
+__all__ = ["StudentForceFieldCalculator"]

@@ -1,0 +1,696 @@
+// libmlffd.so -- C-ABI front end (include/mlffd.h) and step orchestration.
+//
+// One context = one device: weights re-laid out for the kernels, and a workspace sized once by
+// mlffd_workspace_reserve so the hot path never allocates.  A step is a fixed sequence of kernel
+// launches on the caller's stream with no host synchronisation; sizes discovered on the device
+// (number of edges / pairs) stay on the device (DeviceStatus) and are read by later kernels.
+#include "../../include/mlffd.h"
+
+#include <cub/device/device_scan.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "filter.cuh"
+#include "message.cuh"
+#include "neighbor.cuh"
+#include "readout.cuh"
+#include "update.cuh"
+
+using namespace mlffd;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct LayerWeights {
+    FilterWeights filter;
+    UpdateWeights update;
+};
+
+struct Workspace {
+    int64_t cap_atoms = 0, cap_edges = 0, cap_structs = 0, cap_pairs = 0;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    // graph
+    int *atom_struct = nullptr, *deg = nullptr, *deg_low = nullptr, *rowptr = nullptr, *lowptr = nullptr;
+    int *col = nullptr, *edge_dst = nullptr, *rev = nullptr, *pair = nullptr;
+    float4 *geo = nullptr, *edge_adj = nullptr;
+    float* pair_dist = nullptr;
+    // per layer
+    float* filt[kMaxLayers] = {};
+    float* dfilt[kMaxLayers] = {};
+    float* s_in[kMaxLayers + 1] = {};   // s_in[L] = final scalar features
+    float* v_in[kMaxLayers] = {};       // v_in[0] unused (zero)
+    float* s_msg[kMaxLayers] = {};
+    float* v_msg[kMaxLayers] = {};
+    float* y1[kMaxLayers] = {};
+    float* gates[kMaxLayers] = {};
+    float* eps = nullptr;
+    float* sbar[kMaxLayers] = {};       // adjoint sets (ping-pong unless debug)
+    float* vbar[kMaxLayers] = {};
+    void* cub_temp = nullptr;
+    size_t cub_bytes = 0;
+};
+
+}  // namespace
+
+struct mlffd_ctx {
+    int device = 0;
+    mlffd_config cfg{};
+    int H = 0, K = 0, L = 0;
+    bool debug_keep = false;
+    std::string err;
+    float* weights_d = nullptr;
+    const float *emb = nullptr, *centers = nullptr, *gammas = nullptr;
+    LayerWeights layer[kMaxLayers];
+    HeadWeights head{};
+    Workspace ws;
+    DeviceStatus* status_d = nullptr;
+    int64_t last_atoms = 0;
+    int last_structs = 0;
+    bool last_had_forces = false;
+    cudaStream_t last_stream = nullptr;
+    // optional per-stage timing: an event after every launch group (mlffd_profile_enable)
+    bool profiling = false;
+    int64_t launches = 0;
+    int64_t stage_launches[MLFFD_NUM_STAGES] = {};
+    double stage_ms[MLFFD_NUM_STAGES] = {};
+    std::vector<cudaEvent_t> event_pool;
+    std::vector<std::pair<cudaEvent_t, int>> marks;  // (event, stage it closes; -1 = step start)
+    size_t events_used = 0;
+};
+
+namespace {
+
+int fail(mlffd_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+// Count launches; in profiling mode also drop an event that closes `stage`.
+void mark(mlffd_ctx* ctx, int stage, cudaStream_t st, int launches = 1) {
+    ctx->launches += launches;
+    if (stage >= 0) ctx->stage_launches[stage] += launches;
+    if (!ctx->profiling) return;
+    if (ctx->events_used == ctx->event_pool.size()) {
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) != cudaSuccess) return;
+        ctx->event_pool.push_back(ev);
+    }
+    cudaEvent_t ev = ctx->event_pool[ctx->events_used++];
+    cudaEventRecord(ev, st);
+    ctx->marks.emplace_back(ev, stage);
+}
+
+int drain_marks(mlffd_ctx* ctx) {
+    for (size_t i = 1; i < ctx->marks.size(); ++i) {
+        const int stage = ctx->marks[i].second;
+        if (stage < 0) continue;  // a step-start mark: gap between steps is not attributed
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->marks[i - 1].first, ctx->marks[i].first) == cudaSuccess)
+            ctx->stage_ms[stage] += ms;
+    }
+    ctx->marks.clear();
+    ctx->events_used = 0;
+    return 0;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(ctx, MLFFD_ECUDA,                                                     \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                  \
+    } while (0)
+
+#define LAUNCH_CHECK(ctx, what)                                                               \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return fail(ctx, MLFFD_ECUDA, std::string(what) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// launch check + launch accounting for `stage` on stream `st`
+#define LAUNCHED(ctx, what, stage, st)                                                        \
+    do {                                                                                      \
+        LAUNCH_CHECK(ctx, what);                                                              \
+        mark(ctx, stage, st);                                                                 \
+    } while (0)
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+inline int clamp_grid(int64_t wanted, int max_blocks) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>(wanted, max_blocks));
+}
+
+// ---- host-side weight re-layout -------------------------------------------------------------
+struct Stager {
+    std::vector<float> buf;
+    size_t push(const float* src, size_t n) {
+        const size_t off = (buf.size() + 63) / 64 * 64;  // 256-byte alignment
+        buf.resize(off + n);
+        std::memcpy(buf.data() + off, src, n * sizeof(float));
+        return off;
+    }
+    // src is [rows][cols] row-major; stores its transpose [cols][rows]
+    size_t push_transposed(const float* src, int rows, int cols) {
+        std::vector<float> t((size_t)rows * cols);
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c) t[(size_t)c * rows + r] = src[(size_t)r * cols + c];
+        return push(t.data(), t.size());
+    }
+};
+
+template <int H>
+int set_kernel_attributes(mlffd_ctx* ctx) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(filter_table_kernel<H>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)filter_smem_bytes<H>()));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(update_forward_kernel<H, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)update_fwd_smem_bytes<H>()));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(update_forward_kernel<H, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)update_fwd_smem_bytes<H>()));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(update_backward_kernel<H, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)update_bwd_smem_bytes<H>()));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(update_backward_kernel<H, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)update_bwd_smem_bytes<H>()));
+    return MLFFD_OK;
+}
+
+// ---- per-H launch sequences -----------------------------------------------------------------
+template <int H>
+int launch_filter(mlffd_ctx* ctx, int l, const float* dist, const int* num_pairs_ptr,
+                  int num_pairs_arg, const DeviceStatus* status, float* filt, float* dfilt,
+                  int64_t pair_bound, cudaStream_t st) {
+    const int blocks_per_sm = (filter_smem_bytes<H>() <= 110 * 1024) ? 2 : 1;
+    const int grid = clamp_grid(ceil_div(std::max<int64_t>(pair_bound, 1), kFilterPairs),
+                                kNumSMs * blocks_per_sm);
+    filter_table_kernel<H><<<grid, kGemmThreads, filter_smem_bytes<H>(), st>>>(
+        dist, num_pairs_ptr, num_pairs_arg, status, ctx->centers, ctx->gammas, ctx->K,
+        ctx->cfg.cutoff, ctx->layer[l].filter, (l == 0 && status != nullptr) ? 1 : 0, filt, dfilt);
+    LAUNCHED(ctx, "filter_table_kernel", MLFFD_STAGE_FILTER, st);
+    return MLFFD_OK;
+}
+
+template <int H>
+int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets, int n_structs,
+              float* energy, float* forces, cudaStream_t st) {
+    Workspace& ws = ctx->ws;
+    const int N = (int)n_atoms, L = ctx->L;
+    const DeviceStatus* status = ctx->status_d;
+    using M = MsgTraits<H>;
+    const int msg_grid = clamp_grid(ceil_div(N, 8 * M::APW), kNumSMs * 8);
+    const int tiles = ceil_div(N, kTileRows);
+    const int upd_fwd_grid = clamp_grid(tiles, kNumSMs * (update_fwd_smem_bytes<H>() <= 110 * 1024 ? 2 : 1));
+    const int upd_bwd_grid = clamp_grid(tiles, kNumSMs * (update_bwd_smem_bytes<H>() <= 110 * 1024 ? 2 : 1));
+    const int warp_grid = clamp_grid(ceil_div(N, 8), kNumSMs * 8);
+
+    embedding_kernel<H><<<clamp_grid(ceil_div((int64_t)N * (H / 4), 256), kNumSMs * 8), 256, 0, st>>>(
+        z, ctx->emb, ctx->cfg.max_z, ws.s_in[0], N);
+    LAUNCHED(ctx, "embedding_kernel", MLFFD_STAGE_EMBEDDING, st);
+
+    for (int l = 0; l < L; ++l) {
+        int rc = launch_filter<H>(ctx, l, ws.pair_dist, &ctx->status_d->num_pairs, 0, status,
+                                  ws.filt[l], ws.dfilt[l], ws.cap_pairs, st);
+        if (rc) return rc;
+        if (l == 0)
+            message_forward_kernel<H, true><<<msg_grid, 256, 0, st>>>(
+                ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], nullptr, ws.s_msg[l],
+                ws.v_msg[l], N, status);
+        else
+            message_forward_kernel<H, false><<<msg_grid, 256, 0, st>>>(
+                ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], ws.v_in[l], ws.s_msg[l],
+                ws.v_msg[l], N, status);
+        LAUNCHED(ctx, "message_forward_kernel", MLFFD_STAGE_MESSAGE_FWD, st);
+        if (l == L - 1)
+            update_forward_kernel<H, true><<<upd_fwd_grid, kGemmThreads, update_fwd_smem_bytes<H>(), st>>>(
+                ws.s_msg[l], ws.v_msg[l], ctx->layer[l].update, ws.s_in[l + 1], nullptr, ws.y1[l],
+                nullptr, N, status);
+        else
+            update_forward_kernel<H, false><<<upd_fwd_grid, kGemmThreads, update_fwd_smem_bytes<H>(), st>>>(
+                ws.s_msg[l], ws.v_msg[l], ctx->layer[l].update, ws.s_in[l + 1], ws.v_in[l + 1],
+                ws.y1[l], ws.gates[l], N, status);
+        LAUNCHED(ctx, "update_forward_kernel", MLFFD_STAGE_UPDATE_FWD, st);
+    }
+
+    const bool want_forces = forces != nullptr;
+    auto adj = [&](int l) { return ctx->debug_keep ? l : (l & 1); };
+    readout_kernel<H><<<warp_grid, 256, 0, st>>>(ws.s_in[L], ctx->head, ws.eps,
+                                                 want_forces ? ws.sbar[adj(L - 1)] : nullptr, N, status);
+    LAUNCHED(ctx, "readout_kernel", MLFFD_STAGE_READOUT, st);
+    structure_energy_kernel<<<clamp_grid(ceil_div(n_structs, 8), kNumSMs * 8), 256, 0, st>>>(
+        ws.eps, offsets, n_structs, energy, status);
+    LAUNCHED(ctx, "structure_energy_kernel", MLFFD_STAGE_ENERGY_SUM, st);
+    if (!want_forces) return MLFFD_OK;
+
+    for (int l = L - 1; l >= 0; --l) {
+        float* sb = ws.sbar[adj(l)];
+        float* vb = ws.vbar[adj(l)];
+        if (l == L - 1)
+            update_backward_kernel<H, true><<<upd_bwd_grid, kGemmThreads, update_bwd_smem_bytes<H>(), st>>>(
+                ws.v_msg[l], ws.y1[l], nullptr, ctx->layer[l].update, sb, vb, N, status);
+        else
+            update_backward_kernel<H, false><<<upd_bwd_grid, kGemmThreads, update_bwd_smem_bytes<H>(), st>>>(
+                ws.v_msg[l], ws.y1[l], ws.gates[l], ctx->layer[l].update, sb, vb, N, status);
+        LAUNCHED(ctx, "update_backward_kernel", MLFFD_STAGE_UPDATE_BWD, st);
+        float* sb_in = (l > 0) ? ws.sbar[adj(l - 1)] : nullptr;
+        float* vb_in = (l > 0) ? ws.vbar[adj(l - 1)] : nullptr;
+        const bool first = (l == L - 1);
+#define MSG_BWD(LAYER0, ACC)                                                                     \
+    message_backward_kernel<H, LAYER0, ACC><<<msg_grid, 256, 0, st>>>(                           \
+        ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.dfilt[l], ws.s_in[l], ws.v_in[l], sb, \
+        vb, sb_in, vb_in, ws.edge_adj, N, status)
+        if (l == 0) { if (first) MSG_BWD(true, false); else MSG_BWD(true, true); }
+        else        { if (first) MSG_BWD(false, false); else MSG_BWD(false, true); }
+#undef MSG_BWD
+        LAUNCHED(ctx, "message_backward_kernel", MLFFD_STAGE_MESSAGE_BWD, st);
+    }
+    force_kernel<<<warp_grid, 256, 0, st>>>(ws.rowptr, ws.rev, ws.geo, ws.edge_adj, forces, N, status);
+    LAUNCHED(ctx, "force_kernel", MLFFD_STAGE_FORCE, st);
+    return MLFFD_OK;
+}
+
+int build_neighbors(mlffd_ctx* ctx, const float* pos, const int* offsets, int n_structs,
+                    int64_t n_atoms, const float* cells, const uint8_t* pbc, cudaStream_t st) {
+    Workspace& ws = ctx->ws;
+    if (n_atoms > ws.cap_atoms || n_structs > ws.cap_structs)
+        return fail(ctx, MLFFD_ECAPACITY, "workspace too small: call mlffd_workspace_reserve");
+    if ((cells == nullptr) != (pbc == nullptr))
+        return fail(ctx, MLFFD_EINVAL, "cells_d and pbc_d must both be given or both be NULL");
+    const int N = (int)n_atoms;
+    ctx->last_atoms = n_atoms;
+    ctx->last_structs = n_structs;
+    ctx->last_stream = st;
+    mark(ctx, -1, st, 0);  // step start
+    atom_structure_kernel<<<clamp_grid(ceil_div(N, 256), kNumSMs * 8), 256, 0, st>>>(
+        offsets, n_structs, N, ws.atom_struct);
+    LAUNCHED(ctx, "atom_structure_kernel", MLFFD_STAGE_NEIGHBOR, st);
+    CUDA_TRY(ctx, cudaMemsetAsync(ws.deg + N, 0, sizeof(int), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ws.deg_low + N, 0, sizeof(int), st));
+    const int sweep_grid = clamp_grid(ceil_div(N, 8), kNumSMs * 16);
+    neighbor_sweep_kernel<false><<<sweep_grid, 256, 0, st>>>(
+        pos, offsets, ws.atom_struct, cells, pbc, N, ctx->cfg.cutoff, ws.deg, ws.deg_low, nullptr,
+        nullptr, nullptr, nullptr, ctx->status_d);
+    LAUNCHED(ctx, "neighbor_sweep_kernel<count>", MLFFD_STAGE_NEIGHBOR, st);
+    size_t bytes = ws.cub_bytes;
+    CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ws.cub_temp, bytes, ws.deg, ws.rowptr, N + 1, st));
+    bytes = ws.cub_bytes;
+    CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ws.cub_temp, bytes, ws.deg_low, ws.lowptr, N + 1, st));
+    mark(ctx, MLFFD_STAGE_NEIGHBOR, st, 4);  // two CUB scans = 2 x (init + scan) kernels
+    neighbor_finalize_kernel<<<1, 32, 0, st>>>(ws.rowptr, ws.lowptr, N, (int)ws.cap_edges,
+                                               ctx->status_d);
+    LAUNCHED(ctx, "neighbor_finalize_kernel", MLFFD_STAGE_NEIGHBOR, st);
+    neighbor_sweep_kernel<true><<<sweep_grid, 256, 0, st>>>(
+        pos, offsets, ws.atom_struct, cells, pbc, N, ctx->cfg.cutoff, nullptr, nullptr, ws.rowptr,
+        ws.col, ws.edge_dst, ws.geo, ctx->status_d);
+    LAUNCHED(ctx, "neighbor_sweep_kernel<fill>", MLFFD_STAGE_NEIGHBOR, st);
+    reverse_pair_kernel<<<clamp_grid(ceil_div(std::max<int64_t>(ws.cap_edges, 1), 256), kNumSMs * 8),
+                          256, 0, st>>>(ws.rowptr, ws.lowptr, ws.col, ws.edge_dst, ws.geo, ws.rev,
+                                        ws.pair, ws.pair_dist, ctx->status_d);
+    LAUNCHED(ctx, "reverse_pair_kernel", MLFFD_STAGE_NEIGHBOR, st);
+    return MLFFD_OK;
+}
+
+struct ArenaPlan {
+    size_t total = 0;
+    size_t take(size_t bytes) {
+        const size_t off = total;
+        total += (bytes + 255) / 256 * 256;
+        return off;
+    }
+};
+
+}  // namespace
+
+// ================================ C ABI =====================================================
+
+extern "C" int mlffd_version(void) { return MLFFD_ABI_VERSION; }
+
+extern "C" const char* mlffd_last_error(const mlffd_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_config* config,
+                                  const float* weights_host, size_t num_floats) {
+    if (!out || !config || !weights_host) return fail(nullptr, MLFFD_EINVAL, "null argument");
+    *out = nullptr;
+    const int H = config->hidden_dim, K = config->num_rbf, L = config->num_interactions;
+    if (H != 32 && H != 64 && H != 128)
+        return fail(nullptr, MLFFD_EINVAL, "hidden_dim must be 32, 64 or 128");
+    if (K < 1 || K > kMaxRbf) return fail(nullptr, MLFFD_EINVAL, "num_rbf must be in 1..32");
+    if (L < 1 || L > kMaxLayers) return fail(nullptr, MLFFD_EINVAL, "num_interactions must be in 1..8");
+    if (config->max_z < 1 || !(config->cutoff > 0.f))
+        return fail(nullptr, MLFFD_EINVAL, "max_z and cutoff must be positive");
+    if (config->precision != MLFFD_PREC_FP32)
+        return fail(nullptr, MLFFD_EINVAL, "only MLFFD_PREC_FP32 is implemented in this build");
+    const size_t per_layer = (size_t)H * K + H + 3 * H * H + 3 * H + 2 * H * H + H + 3 * H * H + 3 * H + 9;
+    const size_t expect = (size_t)(config->max_z + 1) * H + 2 * K + L * per_layer +
+                          (size_t)(H / 2) * H + H / 2 + (size_t)(H / 4) * (H / 2) + H / 4 + H / 4 + 1;
+    if (num_floats != expect)
+        return fail(nullptr, MLFFD_EINVAL, "weight blob has " + std::to_string(num_floats) +
+                                               " floats, expected " + std::to_string(expect));
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, MLFFD_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, MLFFD_EINVAL, "bad device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, MLFFD_ECUDA, cudaGetErrorString(e));
+
+    mlffd_ctx* ctx = new (std::nothrow) mlffd_ctx();
+    if (!ctx) return fail(nullptr, MLFFD_ENOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->cfg = *config;
+    ctx->H = H; ctx->K = K; ctx->L = L;
+    const char* dbg = std::getenv("MLFFD_DEBUG_KEEP");
+    ctx->debug_keep = dbg && dbg[0] == '1';
+
+    // walk the blob in state_dict order and stage the device layout
+    Stager st;
+    const float* p = weights_host;
+    auto take = [&](size_t n) { const float* q = p; p += n; return q; };
+    const size_t o_emb = st.push(take((size_t)(config->max_z + 1) * H), (size_t)(config->max_z + 1) * H);
+    const size_t o_centers = st.push(take(K), K);
+    const float* widths = take(K);
+    std::vector<float> gam(K);
+    for (int k = 0; k < K; ++k) gam[k] = 1.0f / (widths[k] * widths[k]);  // student_model.py:252
+    const size_t o_gammas = st.push(gam.data(), K);
+    struct LOff { size_t W1t, b1, W2t, b2, M1t, m1, M2t, m2, M1, M2, U; } lo[kMaxLayers];
+    for (int l = 0; l < L; ++l) {
+        const float* W1 = take((size_t)H * K);
+        lo[l].W1t = st.push_transposed(W1, H, K);
+        lo[l].b1 = st.push(take(H), H);
+        const float* W2 = take((size_t)3 * H * H);
+        lo[l].W2t = st.push_transposed(W2, 3 * H, H);
+        lo[l].b2 = st.push(take(3 * H), 3 * H);
+        const float* M1 = take((size_t)H * 2 * H);
+        lo[l].M1t = st.push_transposed(M1, H, 2 * H);
+        lo[l].M1 = st.push(M1, (size_t)H * 2 * H);
+        lo[l].m1 = st.push(take(H), H);
+        const float* M2 = take((size_t)3 * H * H);
+        lo[l].M2t = st.push_transposed(M2, 3 * H, H);
+        lo[l].M2 = st.push(M2, (size_t)3 * H * H);
+        lo[l].m2 = st.push(take(3 * H), 3 * H);
+        lo[l].U = st.push(take(9), 9);
+    }
+    const float* A1 = take((size_t)(H / 2) * H);
+    const size_t o_A1t = st.push_transposed(A1, H / 2, H);
+    const size_t o_A1 = st.push(A1, (size_t)(H / 2) * H);
+    const size_t o_a1 = st.push(take(H / 2), H / 2);
+    const float* A2 = take((size_t)(H / 4) * (H / 2));
+    const size_t o_A2t = st.push_transposed(A2, H / 4, H / 2);
+    const size_t o_A2 = st.push(A2, (size_t)(H / 4) * (H / 2));
+    const size_t o_a2 = st.push(take(H / 4), H / 4);
+    const size_t o_A3 = st.push(take(H / 4), H / 4);
+    const size_t o_a3 = st.push(take(1), 1);
+
+    auto bail = [&](int code, const std::string& msg) {
+        g_create_error = msg;
+        if (ctx->weights_d) cudaFree(ctx->weights_d);
+        if (ctx->status_d) cudaFree(ctx->status_d);
+        delete ctx;
+        return code;
+    };
+    e = cudaMalloc(&ctx->weights_d, st.buf.size() * sizeof(float));
+    if (e != cudaSuccess) return bail(MLFFD_ENOMEM, cudaGetErrorString(e));
+    e = cudaMemcpy(ctx->weights_d, st.buf.data(), st.buf.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
+    e = cudaMalloc(&ctx->status_d, sizeof(DeviceStatus));
+    if (e != cudaSuccess) return bail(MLFFD_ENOMEM, cudaGetErrorString(e));
+    cudaMemset(ctx->status_d, 0, sizeof(DeviceStatus));
+    const float* W = ctx->weights_d;
+    ctx->emb = W + o_emb; ctx->centers = W + o_centers; ctx->gammas = W + o_gammas;
+    for (int l = 0; l < L; ++l) {
+        ctx->layer[l].filter = FilterWeights{W + lo[l].W1t, W + lo[l].b1, W + lo[l].W2t, W + lo[l].b2};
+        ctx->layer[l].update = UpdateWeights{W + lo[l].M1t, W + lo[l].m1, W + lo[l].M2t, W + lo[l].m2,
+                                             W + lo[l].M1, W + lo[l].M2, W + lo[l].U};
+    }
+    ctx->head = HeadWeights{W + o_A1t, W + o_a1, W + o_A2t, W + o_a2, W + o_A3, W + o_a3, W + o_A1, W + o_A2};
+    int rc = (H == 128) ? set_kernel_attributes<128>(ctx)
+           : (H == 64)  ? set_kernel_attributes<64>(ctx)
+                        : set_kernel_attributes<32>(ctx);
+    if (rc != MLFFD_OK) return bail(rc, ctx->err);
+    *out = ctx;
+    return MLFFD_OK;
+}
+
+extern "C" void mlffd_model_destroy(mlffd_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (cudaEvent_t ev : ctx->event_pool) cudaEventDestroy(ev);
+    if (ctx->ws.arena) cudaFree(ctx->ws.arena);
+    if (ctx->weights_d) cudaFree(ctx->weights_d);
+    if (ctx->status_d) cudaFree(ctx->status_d);
+    delete ctx;
+}
+
+extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_t max_edges,
+                                       int64_t max_structures) {
+    if (!ctx) return MLFFD_EINVAL;
+    Workspace& ws = ctx->ws;
+    if (max_atoms <= ws.cap_atoms && max_edges <= ws.cap_edges && max_structures <= ws.cap_structs)
+        return MLFFD_OK;
+    max_atoms = std::max<int64_t>(std::max(max_atoms, ws.cap_atoms), 1);
+    max_edges = std::max<int64_t>(std::max(max_edges, ws.cap_edges), 2);
+    max_structures = std::max<int64_t>(std::max(max_structures, ws.cap_structs), 1);
+    if (max_atoms >= (1ll << 30) || max_edges >= (1ll << 31) - 64)
+        return fail(ctx, MLFFD_EINVAL, "workspace request exceeds 32-bit indexing");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    const int64_t N = max_atoms, E = max_edges, P = max_edges / 2 + 1;
+    const int H = ctx->H, L = ctx->L;
+    size_t cub_bytes = 0;
+    CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int*)nullptr, (int*)nullptr,
+                                                (int)(N + 1)));
+    ArenaPlan plan;
+    const size_t o_atom_struct = plan.take(sizeof(int) * N);
+    const size_t o_deg = plan.take(sizeof(int) * (N + 1));
+    const size_t o_deg_low = plan.take(sizeof(int) * (N + 1));
+    const size_t o_rowptr = plan.take(sizeof(int) * (N + 1));
+    const size_t o_lowptr = plan.take(sizeof(int) * (N + 1));
+    const size_t o_col = plan.take(sizeof(int) * E);
+    const size_t o_edge_dst = plan.take(sizeof(int) * E);
+    const size_t o_rev = plan.take(sizeof(int) * E);
+    const size_t o_pair = plan.take(sizeof(int) * E);
+    const size_t o_geo = plan.take(sizeof(float4) * E);
+    const size_t o_adj = plan.take(sizeof(float4) * E);
+    const size_t o_pdist = plan.take(sizeof(float) * P);
+    const size_t o_eps = plan.take(sizeof(float) * N);
+    const size_t o_cub = plan.take(cub_bytes);
+    size_t o_filt[kMaxLayers], o_dfilt[kMaxLayers], o_s_in[kMaxLayers + 1], o_v_in[kMaxLayers],
+        o_s_msg[kMaxLayers], o_v_msg[kMaxLayers], o_y1[kMaxLayers], o_gates[kMaxLayers],
+        o_sbar[kMaxLayers], o_vbar[kMaxLayers];
+    const int adj_sets = ctx->debug_keep ? L : std::min(L, 2);
+    for (int l = 0; l < L; ++l) {
+        o_filt[l] = plan.take(sizeof(float) * P * 3 * H);
+        o_dfilt[l] = plan.take(sizeof(float) * P * 3 * H);
+        o_s_in[l] = plan.take(sizeof(float) * N * H);
+        o_v_in[l] = (l > 0) ? plan.take(sizeof(float) * N * 3 * H) : 0;
+        o_s_msg[l] = plan.take(sizeof(float) * N * H);
+        o_v_msg[l] = plan.take(sizeof(float) * N * 3 * H);
+        o_y1[l] = plan.take(sizeof(float) * N * H);
+        o_gates[l] = (l < L - 1) ? plan.take(sizeof(float) * N * 2 * H) : 0;
+        if (l < adj_sets) {
+            o_sbar[l] = plan.take(sizeof(float) * N * H);
+            o_vbar[l] = plan.take(sizeof(float) * N * 3 * H);
+        }
+    }
+    o_s_in[L] = plan.take(sizeof(float) * N * H);
+    if (ws.arena) { cudaFree(ws.arena); ws = Workspace(); }
+    void* arena = nullptr;
+    cudaError_t e = cudaMalloc(&arena, plan.total);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, MLFFD_ENOMEM, "cudaMalloc of " + std::to_string(plan.total) +
+                                           " bytes failed: " + cudaGetErrorString(e));
+    }
+    char* base = (char*)arena;
+    ws.arena = arena; ws.arena_bytes = plan.total;
+    ws.cap_atoms = N; ws.cap_edges = E; ws.cap_structs = max_structures; ws.cap_pairs = P;
+    ws.atom_struct = (int*)(base + o_atom_struct);
+    ws.deg = (int*)(base + o_deg); ws.deg_low = (int*)(base + o_deg_low);
+    ws.rowptr = (int*)(base + o_rowptr); ws.lowptr = (int*)(base + o_lowptr);
+    ws.col = (int*)(base + o_col); ws.edge_dst = (int*)(base + o_edge_dst);
+    ws.rev = (int*)(base + o_rev); ws.pair = (int*)(base + o_pair);
+    ws.geo = (float4*)(base + o_geo); ws.edge_adj = (float4*)(base + o_adj);
+    ws.pair_dist = (float*)(base + o_pdist);
+    ws.eps = (float*)(base + o_eps);
+    ws.cub_temp = base + o_cub; ws.cub_bytes = cub_bytes;
+    for (int l = 0; l < L; ++l) {
+        ws.filt[l] = (float*)(base + o_filt[l]); ws.dfilt[l] = (float*)(base + o_dfilt[l]);
+        ws.s_in[l] = (float*)(base + o_s_in[l]);
+        ws.v_in[l] = (l > 0) ? (float*)(base + o_v_in[l]) : nullptr;
+        ws.s_msg[l] = (float*)(base + o_s_msg[l]); ws.v_msg[l] = (float*)(base + o_v_msg[l]);
+        ws.y1[l] = (float*)(base + o_y1[l]);
+        ws.gates[l] = (l < L - 1) ? (float*)(base + o_gates[l]) : nullptr;
+        if (l < adj_sets) {
+            ws.sbar[l] = (float*)(base + o_sbar[l]);
+            ws.vbar[l] = (float*)(base + o_vbar[l]);
+        }
+    }
+    ws.s_in[L] = (float*)(base + o_s_in[L]);
+    return MLFFD_OK;
+}
+
+extern "C" int mlffd_neighbor_list(mlffd_ctx* ctx, const float* pos_d, const int32_t* offsets_d,
+                                   int32_t num_structures, int64_t num_atoms, const float* cells_d,
+                                   const uint8_t* pbc_d, void* stream) {
+    if (!ctx) return MLFFD_EINVAL;
+    if (!pos_d || !offsets_d || num_structures < 1 || num_atoms < 1)
+        return fail(ctx, MLFFD_EINVAL, "mlffd_neighbor_list: bad argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return build_neighbors(ctx, pos_d, offsets_d, num_structures, num_atoms, cells_d, pbc_d,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int mlffd_export_edges(mlffd_ctx* ctx, int64_t* edge_index_d, int64_t capacity_edges,
+                                  int64_t* num_edges_out, void* stream) {
+    if (!ctx || !edge_index_d) return MLFFD_EINVAL;
+    mlffd_status s;
+    int rc = mlffd_get_status(ctx, &s);
+    if (rc) return rc;
+    if (num_edges_out) *num_edges_out = s.num_edges;
+    if (s.overflow) return fail(ctx, MLFFD_ECAPACITY, "edge capacity exceeded in the last build");
+    if (s.num_edges > capacity_edges)
+        return fail(ctx, MLFFD_ECAPACITY, "edge_index buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s.num_edges > 0) {
+        export_edges_kernel<<<clamp_grid(ceil_div(s.num_edges, 256), kNumSMs * 8), 256, 0, st>>>(
+            ctx->ws.col, ctx->ws.edge_dst, (int)s.num_edges, (long long)capacity_edges,
+            (long long*)edge_index_d);
+        LAUNCH_CHECK(ctx, "export_edges_kernel");
+    }
+    return MLFFD_OK;
+}
+
+extern "C" int mlffd_energy_forces(mlffd_ctx* ctx, const int32_t* z_d, const float* pos_d,
+                                   const int32_t* offsets_d, int32_t num_structures,
+                                   int64_t num_atoms, const float* cells_d, const uint8_t* pbc_d,
+                                   float* energy_d, float* forces_d, void* stream) {
+    if (!ctx) return MLFFD_EINVAL;
+    if (!z_d || !pos_d || !offsets_d || !energy_d || num_structures < 1 || num_atoms < 1)
+        return fail(ctx, MLFFD_EINVAL, "mlffd_energy_forces: bad argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = build_neighbors(ctx, pos_d, offsets_d, num_structures, num_atoms, cells_d, pbc_d, st);
+    if (rc) return rc;
+    ctx->last_had_forces = forces_d != nullptr;
+    switch (ctx->H) {
+        case 128: return run_model<128>(ctx, z_d, num_atoms, offsets_d, num_structures, energy_d, forces_d, st);
+        case 64:  return run_model<64>(ctx, z_d, num_atoms, offsets_d, num_structures, energy_d, forces_d, st);
+        default:  return run_model<32>(ctx, z_d, num_atoms, offsets_d, num_structures, energy_d, forces_d, st);
+    }
+}
+
+extern "C" int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out) {
+    if (!ctx || !out) return MLFFD_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->last_stream));
+    DeviceStatus h{};
+    CUDA_TRY(ctx, cudaMemcpy(&h, ctx->status_d, sizeof(h), cudaMemcpyDeviceToHost));
+    out->num_atoms = ctx->last_atoms;
+    out->num_edges = h.num_edges;
+    out->num_pairs = h.num_pairs;
+    out->edge_capacity = ctx->ws.cap_edges;
+    out->overflow = h.overflow;
+    out->max_degree = h.max_degree;
+    return MLFFD_OK;
+}
+
+extern "C" int mlffd_filter_table(mlffd_ctx* ctx, int32_t layer, const float* dist_d,
+                                  int64_t num_pairs, float* filter_d, float* dfilter_d,
+                                  void* stream) {
+    if (!ctx) return MLFFD_EINVAL;
+    if (!dist_d || !filter_d || !dfilter_d || layer < 0 || layer >= ctx->L || num_pairs < 0 ||
+        num_pairs >= (1ll << 31) / (3 * ctx->H))
+        return fail(ctx, MLFFD_EINVAL, "mlffd_filter_table: bad argument");
+    if (num_pairs == 0) return MLFFD_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ctx->H) {
+        case 128: return launch_filter<128>(ctx, layer, dist_d, nullptr, (int)num_pairs, nullptr, filter_d, dfilter_d, num_pairs, st);
+        case 64:  return launch_filter<64>(ctx, layer, dist_d, nullptr, (int)num_pairs, nullptr, filter_d, dfilter_d, num_pairs, st);
+        default:  return launch_filter<32>(ctx, layer, dist_d, nullptr, (int)num_pairs, nullptr, filter_d, dfilter_d, num_pairs, st);
+    }
+}
+
+extern "C" int mlffd_debug_buffer(mlffd_ctx* ctx, const char* name, int32_t layer, void** ptr_out,
+                                  int64_t* count_out, int32_t* elem_size_out) {
+    if (!ctx || !name || !ptr_out || !count_out || !elem_size_out) return MLFFD_EINVAL;
+    mlffd_status s;
+    int rc = mlffd_get_status(ctx, &s);
+    if (rc) return rc;
+    const Workspace& ws = ctx->ws;
+    const int64_t N = ctx->last_atoms, E = s.overflow ? 0 : s.num_edges, P = s.overflow ? 0 : s.num_pairs;
+    const int H = ctx->H, L = ctx->L;
+    const std::string n(name);
+    const bool layer_ok = layer >= 0 && layer < L;
+    void* p = nullptr; int64_t cnt = 0; int es = 4;
+    auto adj = [&](int l) { return ctx->debug_keep ? l : (l & 1); };
+    if (n == "rowptr") { p = ws.rowptr; cnt = N + 1; }
+    else if (n == "col") { p = ws.col; cnt = E; }
+    else if (n == "rev") { p = ws.rev; cnt = E; }
+    else if (n == "pair") { p = ws.pair; cnt = E; }
+    else if (n == "edge_dst") { p = ws.edge_dst; cnt = E; }
+    else if (n == "geo") { p = ws.geo; cnt = E; es = 16; }
+    else if (n == "edge_adj") { p = ws.edge_adj; cnt = E; es = 16; }
+    else if (n == "pair_dist") { p = ws.pair_dist; cnt = P; }
+    else if (n == "atom_energy") { p = ws.eps; cnt = N; }
+    else if (n == "s_out") { p = ws.s_in[L]; cnt = N * H; }
+    else if (!layer_ok) return fail(ctx, MLFFD_EINVAL, "mlffd_debug_buffer: bad layer");
+    else if (n == "filter") { p = ws.filt[layer]; cnt = P * 3 * H; }
+    else if (n == "dfilter") { p = ws.dfilt[layer]; cnt = P * 3 * H; }
+    else if (n == "s_in") { p = ws.s_in[layer]; cnt = N * H; }
+    else if (n == "v_in") { p = ws.v_in[layer]; cnt = ws.v_in[layer] ? N * 3 * H : 0; }
+    else if (n == "s_msg") { p = ws.s_msg[layer]; cnt = N * H; }
+    else if (n == "v_msg") { p = ws.v_msg[layer]; cnt = N * 3 * H; }
+    else if (n == "y1") { p = ws.y1[layer]; cnt = N * H; }
+    else if (n == "gates") { p = ws.gates[layer]; cnt = ws.gates[layer] ? N * 2 * H : 0; }
+    else if (n == "sbar") { p = ws.sbar[adj(layer)]; cnt = N * H; }
+    else if (n == "vbar") { p = ws.vbar[adj(layer)]; cnt = N * 3 * H; }
+    else return fail(ctx, MLFFD_EINVAL, "mlffd_debug_buffer: unknown buffer '" + n + "'");
+    *ptr_out = p; *count_out = cnt; *elem_size_out = es;
+    return MLFFD_OK;
+}
+
+extern "C" int mlffd_profile_enable(mlffd_ctx* ctx, int32_t enable) {
+    if (!ctx) return MLFFD_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->last_stream));
+    ctx->marks.clear();
+    ctx->events_used = 0;
+    ctx->profiling = enable != 0;
+    ctx->launches = 0;
+    for (int i = 0; i < MLFFD_NUM_STAGES; ++i) { ctx->stage_ms[i] = 0.0; ctx->stage_launches[i] = 0; }
+    return MLFFD_OK;
+}
+
+extern "C" int mlffd_profile_read(mlffd_ctx* ctx, mlffd_profile* out) {
+    if (!ctx || !out) return MLFFD_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->last_stream));
+    drain_marks(ctx);
+    out->launches = ctx->launches;
+    for (int i = 0; i < MLFFD_NUM_STAGES; ++i) {
+        out->stage_ms[i] = ctx->stage_ms[i];
+        out->stage_launches[i] = ctx->stage_launches[i];
+    }
+    return MLFFD_OK;
+}
+
+extern "C" const char* mlffd_stage_name(int32_t stage) {
+    static const char* names[MLFFD_NUM_STAGES] = {
+        "neighbor", "embedding", "filter", "message_fwd", "update_fwd", "readout", "energy_sum",
+        "update_bwd", "message_bwd", "force"};
+    return (stage >= 0 && stage < MLFFD_NUM_STAGES) ? names[stage] : "";
+}

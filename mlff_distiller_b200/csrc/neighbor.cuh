@@ -1,0 +1,157 @@
+// Radius-graph neighbour list: destination-sorted CSR with sources ascending inside a row.
+//
+// Replaces radius_graph_native (reference src/mlff_distiller/models/student_model.py:63-109),
+// whose dense [N,N,3] difference tensor is O(N^2) memory.  Semantics kept: ordered pairs i != j
+// of the same structure with d <= cutoff (inclusive), FP32.  Because the edge set is symmetric,
+// CSR order (dst row, src ascending) enumerates the same sequence of index pairs as the
+// reference's lexicographic (src, dst) order with the two labels swapped; mlffd_export_edges uses
+// that to hand back the reference's edge_index without a sort.
+//
+// Two candidate generators feed the same warp-cooperative pair test:
+//   * per-structure sweep  (small structures: every atom of the structure is a candidate)
+//   * cell list            (large structures: candidates from the 27 surrounding cells)
+// A warp owns one destination atom; lanes test 32 candidates at a time, and a ballot/popc
+// compaction keeps sources in ascending order without atomics or a sort.
+#pragma once
+#include "common.cuh"
+
+namespace mlffd {
+
+// structure id of every atom from the offsets array (binary search; B is small or N is large)
+__global__ void atom_structure_kernel(const int* __restrict__ offsets, int num_structures,
+                                      int num_atoms, int* __restrict__ atom_struct) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < num_atoms; i += gridDim.x * blockDim.x) {
+        int lo = 0, hi = num_structures;  // invariant: offsets[lo] <= i < offsets[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(offsets + mid) <= i) lo = mid; else hi = mid;
+        }
+        atom_struct[i] = lo;
+    }
+}
+
+// One warp per destination atom j; candidates = all atoms of j's structure.
+// FILL == false: deg[j] = #neighbours, deg_low[j] = #neighbours with index < j.
+// FILL == true : writes col/edge_dst/geo at rowptr[j]... (sources ascending).
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+neighbor_sweep_kernel(const float* __restrict__ pos, const int* __restrict__ offsets,
+                      const int* __restrict__ atom_struct, const float* __restrict__ cells,
+                      const uint8_t* __restrict__ pbc, int num_atoms, float cutoff,
+                      int* __restrict__ deg, int* __restrict__ deg_low,
+                      const int* __restrict__ rowptr, int* __restrict__ col,
+                      int* __restrict__ edge_dst, float4* __restrict__ geo,
+                      DeviceStatus* __restrict__ status) {
+    if (FILL && status->overflow) return;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int warp0 = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int warp_stride = gridDim.x * warps_per_block;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int j = warp0; j < num_atoms; j += warp_stride) {
+        const int b = atom_struct[j];
+        const int lo = __ldg(offsets + b), hi = __ldg(offsets + b + 1);
+        const float xj = __ldg(pos + 3 * j), yj = __ldg(pos + 3 * j + 1), zj = __ldg(pos + 3 * j + 2);
+        unsigned pmask = 0;
+        const float* cell18 = nullptr;
+        if (pbc != nullptr) {
+            pmask = (pbc[3 * b] ? 1u : 0u) | (pbc[3 * b + 1] ? 2u : 0u) | (pbc[3 * b + 2] ? 4u : 0u);
+            cell18 = cells + 18 * b;
+        }
+        int count = 0, count_low = 0;
+        const int base = FILL ? rowptr[j] : 0;
+        for (int i0 = lo; i0 < hi; i0 += 32) {
+            const int i = i0 + lane;
+            bool ok = false;
+            float dx = 0.f, dy = 0.f, dz = 0.f, d = 0.f;
+            if (i < hi && i != j) {
+                dx = __fsub_rn(__ldg(pos + 3 * i), xj);      // x_src - x_dst
+                dy = __fsub_rn(__ldg(pos + 3 * i + 1), yj);
+                dz = __fsub_rn(__ldg(pos + 3 * i + 2), zj);
+                if (pmask) min_image(dx, dy, dz, cell18, pmask);
+                d = pair_distance(dx, dy, dz);
+                ok = d <= cutoff;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (FILL) {
+                if (ok) {
+                    const int e = base + count + __popc(m & lt_mask);
+                    const float q = __fadd_rn(d, kUnitEps);
+                    col[e] = i;
+                    edge_dst[e] = j;
+                    geo[e] = make_float4(__fdiv_rn(dx, q), __fdiv_rn(dy, q), __fdiv_rn(dz, q), d);
+                }
+            } else {
+                count_low += __popc(__ballot_sync(0xffffffffu, ok && i < j));
+            }
+            count += __popc(m);
+        }
+        if (!FILL && lane == 0) {
+            deg[j] = count;
+            deg_low[j] = count_low;
+        }
+    }
+}
+
+// After the two exclusive scans: publish E and P, flag overflow.
+__global__ void neighbor_finalize_kernel(const int* __restrict__ rowptr,
+                                         const int* __restrict__ lowptr, int num_atoms,
+                                         int edge_capacity, DeviceStatus* __restrict__ status) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int e = rowptr[num_atoms];
+        status->num_edges = e;
+        status->num_pairs = lowptr[num_atoms];
+        status->overflow = (e > edge_capacity) ? 1 : 0;
+        status->max_degree = 0;
+    }
+}
+
+// Per edge e = (i -> j): rev[e] = position of (j -> i) (binary search in row i), pair id, and the
+// compact per-pair distance list the filter-table kernel consumes.  Lower edges (i < j) come
+// first in a row because sources ascend, so pair ids need no extra sort.
+__global__ void reverse_pair_kernel(const int* __restrict__ rowptr, const int* __restrict__ lowptr,
+                                    const int* __restrict__ col, const int* __restrict__ edge_dst,
+                                    const float4* __restrict__ geo, int* __restrict__ rev,
+                                    int* __restrict__ pair, float* __restrict__ pair_dist,
+                                    DeviceStatus* __restrict__ status) {
+    if (status->overflow) return;
+    const int num_edges = status->num_edges;
+    int local_max = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < num_edges; e += gridDim.x * blockDim.x) {
+        const int i = col[e], j = edge_dst[e];
+        int lo = rowptr[i], hi = rowptr[i + 1] - 1;
+        local_max = max(local_max, rowptr[j + 1] - rowptr[j]);
+        while (lo < hi) {  // sources ascending -> lower_bound of j in row i
+            const int mid = (lo + hi) >> 1;
+            if (col[mid] < j) lo = mid + 1; else hi = mid;
+        }
+        rev[e] = lo;
+        int p;
+        if (i < j) {
+            p = lowptr[j] + (e - rowptr[j]);
+            pair_dist[p] = geo[e].w;
+        } else {
+            p = lowptr[i] + (lo - rowptr[i]);
+        }
+        pair[e] = p;
+    }
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 16));
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 8));
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 4));
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 2));
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 1));
+    if ((threadIdx.x & 31) == 0 && local_max > 0) atomicMax(&status->max_degree, local_max);
+}
+
+// edge_index [2, cap] int64 in the reference's order: row 0 = src, row 1 = dst, lexicographic.
+// By symmetry the k-th CSR entry (row j, col i) is the k-th lexicographic pair (src=j, dst=i).
+__global__ void export_edges_kernel(const int* __restrict__ col, const int* __restrict__ edge_dst,
+                                    int num_edges, long long capacity,
+                                    long long* __restrict__ edge_index) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < num_edges; e += gridDim.x * blockDim.x) {
+        edge_index[e] = edge_dst[e];
+        edge_index[capacity + e] = col[e];
+    }
+}
+
+}  // namespace mlffd

@@ -1,0 +1,159 @@
+// Embedding lookup, energy read-out (forward and reverse fused), per-structure energy sums and
+// the final edge-geometry reverse + force gather.
+//
+// Read-out restates energy_head (reference src/mlff_distiller/models/student_model.py:599-605,
+// 736-755): eps_j = A3 SiLU(A2 SiLU(A1 s_j + a1) + a2) + a3, E_b = sum_{j in b} eps_j.  Since
+// dE/d eps_j = 1 for every atom, the reverse of the head is computed in the same kernel and
+// seeds the adjoint s_bar of the last layer.
+//
+// Forces restate what autograd does through student_model.py:709-715 (r = x_src - x_dst,
+// d = |r|, u = r / (d + 1e-8)):  r_bar = (d_bar - (u_bar . u) / q) * (r / d) + u_bar / q,
+// q = d + 1e-8;  F_j = sum_{e -> j} (r_bar_e - r_bar_rev(e))  -- a CSR gather through the
+// reverse-edge index instead of the +/- atomic scatter of
+// analytical_gradients.accumulate_forces_from_edges (:325-339).
+#pragma once
+#include "common.cuh"
+
+namespace mlffd {
+
+struct HeadWeights {
+    const float* A1t;  // [H][H/2]   transposed energy_head.0.weight
+    const float* a1;   // [H/2]
+    const float* A2t;  // [H/2][H/4] transposed energy_head.2.weight
+    const float* a2;   // [H/4]
+    const float* A3;   // [H/4]      energy_head.4.weight
+    const float* a3;   // [1]
+    const float* A1;   // [H/2][H]   original layout (reverse)
+    const float* A2;   // [H/4][H/2] original layout (reverse)
+};
+
+template <int H>
+__global__ void __launch_bounds__(256)
+embedding_kernel(const int* __restrict__ z, const float* __restrict__ emb, int max_z,
+                 float* __restrict__ s0, int num_atoms) {
+    constexpr int V = H / 4;
+    const size_t total = (size_t)num_atoms * V;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int atom = (int)(idx / V), c4 = (int)(idx % V) * 4;
+        int zi = __ldg(z + atom);
+        zi = min(max(zi, 0), max_z);
+        st4(s0 + (size_t)atom * H + c4, ldg4(emb + (size_t)zi * H + c4));
+    }
+}
+
+// One warp per atom (grid-stride).  Writes eps[atom] and, if sbar != nullptr, d eps / d s.
+template <int H>
+__global__ void __launch_bounds__(256)
+readout_kernel(const float* __restrict__ s, HeadWeights w, float* __restrict__ eps,
+               float* __restrict__ sbar, int num_atoms, const DeviceStatus* __restrict__ status) {
+    constexpr int H2 = H / 2, H4 = H / 4;
+    constexpr int WARPS = 8;
+    if (status->overflow) return;
+    __shared__ float s_sh[WARPS][H];
+    __shared__ float y1_sh[WARPS][H2];   // pre-activations, then adjoints
+    __shared__ float h1_sh[WARPS][H2];
+    __shared__ float y2_sh[WARPS][H4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * WARPS + wib;
+    const int num_warps = gridDim.x * WARPS;
+    for (int atom = warp; atom < num_atoms; atom += num_warps) {
+        for (int c = lane; c < H; c += 32) s_sh[wib][c] = __ldg(s + (size_t)atom * H + c);
+        __syncwarp();
+        // layer 1: H -> H/2
+        for (int o = lane; o < H2; o += 32) {
+            float y = __ldg(w.a1 + o);
+            for (int k = 0; k < H; ++k) y = fmaf(s_sh[wib][k], __ldg(w.A1t + k * H2 + o), y);
+            y1_sh[wib][o] = y;
+            h1_sh[wib][o] = siluf_(y);
+        }
+        __syncwarp();
+        // layer 2: H/2 -> H/4, layer 3: H/4 -> 1
+        float part = 0.f;
+        for (int o = lane; o < H4; o += 32) {
+            float y = __ldg(w.a2 + o);
+            for (int k = 0; k < H2; ++k) y = fmaf(h1_sh[wib][k], __ldg(w.A2t + k * H4 + o), y);
+            const float a3 = __ldg(w.A3 + o);
+            part = fmaf(siluf_(y), a3, part);
+            y2_sh[wib][o] = a3 * silu_gradf_(y);   // adjoint of the layer-2 pre-activation
+        }
+        part = group_sum<32>(part);
+        if (lane == 0) eps[atom] = part + __ldg(w.a3);
+        __syncwarp();
+        if (sbar != nullptr) {
+            // y1_bar = (A2^T y2_bar) * SiLU'(y1)
+            for (int k = lane; k < H2; k += 32) {
+                float hb = 0.f;
+                for (int o = 0; o < H4; ++o) hb = fmaf(y2_sh[wib][o], __ldg(w.A2 + o * H2 + k), hb);
+                h1_sh[wib][k] = hb * silu_gradf_(y1_sh[wib][k]);
+            }
+            __syncwarp();
+            for (int c = lane; c < H; c += 32) {
+                float sb = 0.f;
+                for (int k = 0; k < H2; ++k) sb = fmaf(h1_sh[wib][k], __ldg(w.A1 + k * H + c), sb);
+                sbar[(size_t)atom * H + c] = sb;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// One warp per structure: E_b = sum of eps over the structure's atoms (FP64 accumulation, fixed
+// order -> deterministic).
+__global__ void __launch_bounds__(256)
+structure_energy_kernel(const float* __restrict__ eps, const int* __restrict__ offsets,
+                        int num_structures, float* __restrict__ energy,
+                        const DeviceStatus* __restrict__ status) {
+    if (status->overflow) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int num_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int b = warp; b < num_structures; b += num_warps) {
+        const int lo = __ldg(offsets + b), hi = __ldg(offsets + b + 1);
+        double acc = 0.0;
+        for (int i = lo + lane; i < hi; i += 32) acc += (double)__ldg(eps + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) energy[b] = (float)acc;
+    }
+}
+
+__device__ __forceinline__ float3 edge_position_adjoint(const float4 g, const float4 adj) {
+    // g = (u_x, u_y, u_z, d), adj = (u_bar_x, u_bar_y, u_bar_z, d_bar)
+    const float q = g.w + kUnitEps;
+    const float udot = g.x * adj.x + g.y * adj.y + g.z * adj.z;
+    const float inv_q = 1.0f / q;
+    // r / d = u * q / d ; torch's norm backward gives 0 at d == 0
+    const float scale = (g.w > 0.f) ? (adj.w - udot * inv_q) * (q / g.w) : 0.f;
+    return make_float3(fmaf(scale, g.x, adj.x * inv_q), fmaf(scale, g.y, adj.y * inv_q),
+                       fmaf(scale, g.z, adj.z * inv_q));
+}
+
+// One warp per atom j: F_j = sum_{e in row j} (r_bar_e - r_bar_rev(e)).
+__global__ void __launch_bounds__(256)
+force_kernel(const int* __restrict__ rowptr, const int* __restrict__ rev,
+             const float4* __restrict__ geo, const float4* __restrict__ edge_adj,
+             float* __restrict__ forces, int num_atoms, const DeviceStatus* __restrict__ status) {
+    if (status->overflow) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int num_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = warp; j < num_atoms; j += num_warps) {
+        const int e0 = rowptr[j], e1 = rowptr[j + 1];
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        for (int e = e0 + lane; e < e1; e += 32) {
+            const int r = __ldg(rev + e);
+            const float3 a = edge_position_adjoint(__ldg(geo + e), __ldg(edge_adj + e));
+            const float3 b = edge_position_adjoint(__ldg(geo + r), __ldg(edge_adj + r));
+            fx += a.x - b.x; fy += a.y - b.y; fz += a.z - b.z;
+        }
+        fx = group_sum<32>(fx); fy = group_sum<32>(fy); fz = group_sum<32>(fz);
+        if (lane == 0) {
+            forces[3 * (size_t)j] = fx;
+            forces[3 * (size_t)j + 1] = fy;
+            forces[3 * (size_t)j + 2] = fz;
+        }
+    }
+}
+
+}  // namespace mlffd

