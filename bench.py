@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Headline benchmark: structures/s (energy + forces), BASELINE.json config C2.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework, N GPUs (torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference path on the host CPU
+
+A "step" = one energy+force evaluation of one batch of 1024 synthetic drug-like structures of 50
+atoms (Original 427K weights; seeds fixed, mlff_distiller_b200/synthetic.py) per GPU.  With N > 1
+every rank owns its own shard of 1024 structures (weak scaling, no collective on the data path).
+`value` is timed with inputs resident in HBM; `e2e` goes through the calculator's host-array API
+(pinned H2D of numbers/positions/offsets and D2H of energies/forces inside the timed region).
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "structures_per_second_energy_forces"
+UNIT = "structures/s"
+VARIANT_FILES = {"original": "weights_original.npz", "tiny": "weights_tiny.npz",
+                 "ultra_tiny": "weights_ultra_tiny.npz"}
+POSITION_SETS = 4        # rotate perturbed inputs so no step repeats the previous one
+REFERENCE_CHUNK = 32     # structures per reference call: un-chunked needs a 31 GB dense mask
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--variant", choices=sorted(VARIANT_FILES), default="original")
+    ap.add_argument("--batch", type=int, default=1024, help="structures per GPU per step")
+    ap.add_argument("--atoms", type=int, default=50)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def load_state(variant):
+    with np.load(ROOT / "tests" / "golden" / VARIANT_FILES[variant]) as z:
+        state = {k: z[k] for k in z.files if not k.startswith("__")}
+        cfg = json.loads(str(z["__config__"]))
+    return state, cfg
+
+
+def workload_config(args, world):
+    return {"workload": f"C2: {args.batch} drug-like structures x {args.atoms} atoms per GPU per step, "
+                        f"energy+forces, PaiNN student '{args.variant}'",
+            "variant": args.variant, "structures_per_gpu": args.batch, "atoms_per_structure": args.atoms,
+            "global_batch": args.batch * world, "parallelism": f"structure-sharded x{world}, no collective",
+            "l2_policy": "per-step working set (filter tables + features, >4 GB) exceeds the 126 MB L2; "
+                         f"{POSITION_SETS} rotating perturbed input sets"}
+
+
+def measured_peaks():
+    for p in (ROOT / "MEASURED_PEAKS.json", Path("/root/repo/MEASURED_PEAKS.json")):
+        if p.exists():
+            d = json.loads(p.read_text())
+            return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    "bf16_tflops_burst": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic work per step (SURVEY 8d per-unit figures)
+# ------------------------------------------------------------------------------------------
+def algorithmic_work(N, E, P, H, K, L):
+    w = {}
+    f_flops = f_bytes = 0
+    for l in range(L):
+        nout = 2 * H if l == 0 else 3 * H           # layer 0 never reads the b gate (v_in = 0)
+        f_flops += P * (2 * (2 * K * H) + 2 * (2 * H * nout))
+        f_bytes += P * (4 + 2 * nout * 4)
+    w["filter"] = {"flops": f_flops, "bytes": f_bytes}
+    mf_b = mf_f = mb_b = mb_f = 0
+    for l in range(L):
+        nf = (2 if l == 0 else 3) * H * 4
+        gather = (1 if l == 0 else 4) * H * 4
+        mf_b += E * (nf + gather + 24) + N * (4 * H * 4 + gather)
+        mf_f += E * 2 * H * (1 + (0 if l == 0 else 3) + 3)
+        mb_b += E * (2 * nf + H * 4 + (0 if l == 0 else 7 * H * 4) + 24 + 16 + (0 if l == L - 1 else 16)) \
+            + N * (4 * H * 4 + (0 if l == 0 else 4 * H * 4))
+        mb_f += E * 2 * H * (2 + 6 + 3 + (0 if l == 0 else 3 + 2 + 4))
+    w["message_fwd"] = {"flops": mf_f, "bytes": mf_b}
+    w["message_bwd"] = {"flops": mb_f, "bytes": mb_b}
+    uf_f = uf_b = ub_f = ub_b = 0
+    for l in range(L):
+        last = l == L - 1
+        nout = H if last else 3 * H
+        uf_f += N * (2 * 2 * H * H + 2 * H * nout)
+        uf_b += N * 4 * (4 * H + H + (H if last else 2 * H + 4 * H + 3 * H))
+        ub_f += N * (2 * nout * H + 2 * H * 2 * H)
+        ub_b += N * 4 * (H + 3 * H + H + (4 * H if last else 2 * H + 3 * H + 4 * H))
+    w["update_fwd"] = {"flops": uf_f, "bytes": uf_b}
+    w["update_bwd"] = {"flops": ub_f, "bytes": ub_b}
+    head = H * H // 2 + H * H // 8 + H // 4
+    w["readout"] = {"flops": N * 4 * head, "bytes": N * 4 * (2 * H + 1)}
+    w["neighbor"] = {"flops": 0, "bytes": N * (12 + 4 + 16) + E * (4 * 4 + 16) + P * 4}
+    w["force"] = {"flops": E * 40, "bytes": E * (4 + 4 * 16) + N * 12}
+    w["embedding"] = {"flops": 0, "bytes": N * (4 + 2 * H * 4)}
+    w["energy_sum"] = {"flops": N, "bytes": N * 4}
+    return w
+
+
+COMPUTE_BOUND = {"filter", "update_fwd", "update_bwd"}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference path, all host threads
+# ------------------------------------------------------------------------------------------
+def cpu_chunk_runner(args):
+    import torch
+    from mlff_distiller_b200 import synthetic
+    from oracle import painn_oracle as po
+    torch.set_num_threads(os.cpu_count() or 1)
+    state, cfg = load_state(args.variant)
+    w = po.to_torch_weights(state)
+
+    def run_chunk(first):
+        structs = synthetic.druglike_batch(REFERENCE_CHUNK, first=first, n=args.atoms)
+        z, pos, off = synthetic.concatenate(structs)
+        e, f = po.energy_and_forces(w, torch.from_numpy(z), torch.from_numpy(pos.astype(np.float32)),
+                                    cfg["cutoff"], po.batch_from_offsets(off))
+        return float(e.sum()), f
+
+    return run_chunk, torch.get_num_threads()
+
+
+def cpu_baseline(args):
+    run_chunk, threads = cpu_chunk_runner(args)
+    run_chunk(0)  # warm-up
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < args.cpu_seconds and done < args.batch:
+        run_chunk(done)
+        done += REFERENCE_CHUNK
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {done} structures of the workload in chunks of {REFERENCE_CHUNK} "
+                      f"(oracle/painn_oracle.py = torch CPU restatement of the reference, autograd forces), {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    run_chunk, threads = cpu_chunk_runner(args)
+    for i in range(max(args.warmup, 1)):
+        run_chunk(i * REFERENCE_CHUNK)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        run_chunk((i % (max(args.batch // REFERENCE_CHUNK, 1))) * REFERENCE_CHUNK)
+    dt = time.perf_counter() - t0
+    value = args.steps * REFERENCE_CHUNK / dt
+    sample = (f"each step = {REFERENCE_CHUNK} structures of the workload through the torch CPU "
+              f"restatement of the reference path (the reference cannot batch 1024: 31 GB dense mask)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from mlff_distiller_b200 import synthetic
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a GPU (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- workload: this rank's shard ----
+    structs = synthetic.druglike_batch(args.batch, first=rank * args.batch, n=args.atoms)
+    numbers, pos64, offsets = synthetic.concatenate(structs)
+    counts = np.diff(offsets)
+    N, B = len(numbers), len(structs)
+    rng = np.random.default_rng(1234 + rank)
+    pos_sets64 = [pos64 + rng.normal(0.0, 0.01, pos64.shape) for _ in range(POSITION_SETS)]
+
+    calc = StudentForceFieldCalculator(ROOT / "tests" / "golden" / VARIANT_FILES[args.variant], device=str(dev))
+    model = calc.model
+    eng = model.engine()
+    cfg = model.config
+
+    z_d = torch.from_numpy(numbers.astype(np.int32)).to(dev)
+    off_d = torch.from_numpy(offsets.astype(np.int32)).to(dev)
+    pos_d = [torch.from_numpy(p.astype(np.float32)).to(dev) for p in pos_sets64]
+    energy_d = torch.empty(B, dtype=torch.float32, device=dev)
+    forces_d = torch.empty((N, 3), dtype=torch.float32, device=dev)
+
+    # sizing call (grows the edge workspace if the first guess overflows)
+    model.energy_and_forces_packed(z_d, pos_d[0], off_d, B)
+    st = eng.status()
+    E, P = int(st.num_edges), int(st.num_pairs)
+
+    # ---- device-resident timing ----
+    for i in range(max(args.warmup, 3)):
+        eng.energy_forces_async(z_d, pos_d[i % POSITION_SETS], off_d, B, energy_d, forces_d)
+    barrier()
+    eng.profile_enable(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for i in range(args.steps):
+        eng.energy_forces_async(z_d, pos_d[i % POSITION_SETS], off_d, B, energy_d, forces_d)
+    end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = start.elapsed_time(end)
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    if eng.status().overflow:
+        raise SystemExit("edge workspace overflow during the timed region")
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end-to-end through the calculator's host-array API ----
+    for i in range(3):
+        calc.evaluate_arrays(numbers, pos_sets64[i % POSITION_SETS], counts)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e_host, f_host = calc.evaluate_arrays(numbers, pos_sets64[i % POSITION_SETS], counts)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t.item())
+    h2d = 4 * N + 12 * N + 4 * (B + 1)
+    d2h = 4 * B + 12 * N
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peaks = measured_peaks()
+    work = algorithmic_work(N, E, P, cfg.hidden_dim, cfg.num_rbf, cfg.num_interactions)
+    stages = {}
+    for name, s in prof["stages"].items():
+        if s["launches"] == 0:
+            continue
+        per_launch_ms = s["ms"] / s["launches"]
+        per_step_ms = s["ms"] / args.steps
+        wk = work.get(name, {"flops": 0, "bytes": 0})
+        stages[name] = {"ms_per_step": per_step_ms, "launches_per_step": s["launches"] / args.steps,
+                        "ms_per_launch": per_launch_ms,
+                        "GBps": wk["bytes"] / (per_step_ms * 1e-3) / 1e9 if per_step_ms > 0 else None,
+                        "TFLOPs": wk["flops"] / (per_step_ms * 1e-3) / 1e12 if per_step_ms > 0 else None}
+    top = max(stages, key=lambda k: stages[k]["ms_per_step"])
+    if top in COMPUTE_BOUND:
+        achieved, peak, unit, bound = stages[top]["TFLOPs"], peaks["bf16_tflops"], "TFLOP/s", "tensor"
+    else:
+        achieved, peak, unit, bound = stages[top]["GBps"], peaks["hbm_gbs"], "GB/s", "hbm"
+    roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                "frac": achieved / peak if achieved else None, "traffic": None,
+                "peak_source": peaks["source"],
+                "share_of_step": stages[top]["ms_per_step"] / (elapsed_ms / args.steps)}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": prof["launches"], "clocks": clocks, "roofline": roofline,
+        "stages": stages, "graph": {"atoms": N, "edges": E, "pairs": P},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
