@@ -270,24 +270,54 @@ class StudentForceFieldCalculator(_AseCalculator):
         if not np.isfinite(positions).all():
             raise ValueError("Positions contain NaN or Inf values")
         dev = self.device
-        nb = len(counts)
-        offsets = np.zeros(nb + 1, dtype=np.int32)
-        np.cumsum(counts, out=offsets[1:])
-        z_d = torch.from_numpy(np.ascontiguousarray(numbers, dtype=np.int32)).pin_memory().to(dev, non_blocking=True)
-        pos_d = torch.from_numpy(np.ascontiguousarray(positions, dtype=np.float32)).pin_memory().to(dev, non_blocking=True)
-        off_d = torch.from_numpy(offsets).pin_memory().to(dev, non_blocking=True)
+        nb, n = len(counts), len(numbers)
+        st = self._batch_staging(n, nb)
+        # host -> pinned staging (dtype conversion happens in this copy) -> device, async
+        st["z_h"][:n].copy_(torch.from_numpy(np.ascontiguousarray(numbers)))
+        st["pos_h"][:n].copy_(torch.from_numpy(np.ascontiguousarray(positions)))
+        off_np = st["off_h"].numpy()
+        off_np[0] = 0
+        np.cumsum(counts, out=off_np[1:nb + 1])
+        z_d, pos_d, off_d = st["z_d"][:n], st["pos_d"][:n], st["off_d"][:nb + 1]
+        z_d.copy_(st["z_h"][:n], non_blocking=True)
+        pos_d.copy_(st["pos_h"][:n], non_blocking=True)
+        off_d.copy_(st["off_h"][:nb + 1], non_blocking=True)
         cells_d = pbc_d = None
         if cells is not None and pbcs is not None and np.any(pbcs):
             cells_d, pbc_d = StudentForceField.pack_cells(torch.from_numpy(np.asarray(cells)),
                                                           torch.from_numpy(np.asarray(pbcs)), nb, dev)
         try:
             e_d, f_d = self.model.energy_and_forces_packed(z_d, pos_d, off_d, nb, cells_d, pbc_d)
-            energies = e_d.cpu().numpy()
-            forces = f_d.cpu().numpy()
+            st["e_h"][:nb].copy_(e_d, non_blocking=True)
+            st["f_h"][:n].copy_(f_d, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            energies = st["e_h"][:nb].numpy().copy()
+            forces = st["f_h"][:n].numpy().copy()
         except Exception as e:
             raise RuntimeError(f"Failed to calculate properties for {len(numbers)} atoms: {e}") from e
         self._n_calls += 1
         return energies, forces
+
+    def _batch_staging(self, n_atoms: int, n_structs: int):
+        """Grow-only pinned host + device staging buffers for the batched interface."""
+        st = getattr(self, "_staging", None)
+        if st is None or st["cap_n"] < n_atoms or st["cap_b"] < n_structs:
+            cap_n = max(n_atoms, int(1.25 * (st["cap_n"] if st else 0)))
+            cap_b = max(n_structs, int(1.25 * (st["cap_b"] if st else 0)))
+            dev = self.device
+            st = {
+                "cap_n": cap_n, "cap_b": cap_b,
+                "z_h": torch.empty(cap_n, dtype=torch.int32).pin_memory(),
+                "pos_h": torch.empty((cap_n, 3), dtype=torch.float32).pin_memory(),
+                "off_h": torch.empty(cap_b + 1, dtype=torch.int32).pin_memory(),
+                "e_h": torch.empty(cap_b, dtype=torch.float32).pin_memory(),
+                "f_h": torch.empty((cap_n, 3), dtype=torch.float32).pin_memory(),
+                "z_d": torch.empty(cap_n, dtype=torch.int32, device=dev),
+                "pos_d": torch.empty((cap_n, 3), dtype=torch.float32, device=dev),
+                "off_d": torch.empty(cap_b + 1, dtype=torch.int32, device=dev),
+            }
+            self._staging = st
+        return st
 
     # ---- bookkeeping ----------------------------------------------------------------------
     def reset(self):

@@ -1,0 +1,120 @@
+"""Host-side logic that needs no GPU: sharding, MD driver, synthetic workloads, validation."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from mlff_distiller_b200 import md, sharding, synthetic
+
+
+def test_partition_covers_everything_once():
+    rng = np.random.default_rng(0)
+    counts = rng.integers(20, 81, size=1000)
+    for shards in (1, 2, 4, 8, 3):
+        parts = sharding.partition_by_atoms(counts, shards)
+        assert parts[0][0] == 0 and parts[-1][1] == len(counts)
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(shards - 1))
+        loads = [counts[a:b].sum() for a, b in parts]
+        assert max(loads) - min(loads) <= 2 * counts.max()
+    assert sharding.partition_by_atoms([5, 5], 4)[-1][1] == 2
+    chunks = sharding.chunk_by_budget(counts, max_atoms=4096, max_structs=64)
+    assert chunks[0][0] == 0 and chunks[-1][1] == len(counts)
+    assert all(counts[a:b].sum() <= 4096 and b - a <= 64 for a, b in chunks)
+
+
+def test_synthetic_workloads_are_seeded_and_sane():
+    a = synthetic.druglike_batch(3)
+    b = synthetic.druglike_batch(3)
+    for x, y in zip(a, b):
+        assert np.array_equal(x.positions, y.positions) and np.array_equal(x.numbers, y.numbers)
+    z, pos, off = synthetic.concatenate(a)
+    assert list(off) == [0, 50, 100, 150] and synthetic.min_pair_distance(pos, off) >= 0.95
+    r = synthetic.druglike_batch(20, ragged=True)
+    assert {len(s) for s in r} != {50} and all(20 <= len(s) <= 80 for s in r)
+    chain = synthetic.alkane_chain(100)
+    assert len(chain) == 300 and list(chain.numbers[:3]) == [6, 1, 1]
+    box = synthetic.water_box(64, seed=1)
+    assert len(box) == 192 and box.pbc.all() and abs(box.cell[0, 0] - (64 / 0.0334) ** (1 / 3)) < 1e-9
+    w = synthetic.water()
+    assert np.allclose(w.positions[1], [0, 0.763239, -0.477047])
+
+
+def test_velocity_verlet_conserves_energy_on_a_harmonic_toy():
+    k = 5.0
+
+    def force_fn(x):
+        return 0.5 * k * float(np.sum(x ** 2)), -k * x
+
+    rng = np.random.default_rng(3)
+    masses = np.array([12.011, 1.008, 1.008])
+    x0 = rng.normal(size=(3, 3)) * 0.1
+    v0 = md.maxwell_boltzmann(masses, 300.0, rng)
+    assert np.abs((masses[:, None] * v0).sum(0)).max() < 1e-12
+    out = md.velocity_verlet(force_fn, x0, v0, masses, steps=2000, dt_fs=0.1)
+    assert abs(out["drift_percent"]) < 0.02
+    assert len(out["total"]) == 2001
+    assert abs(md.FS - 0.09822694788) < 1e-9
+    assert abs(md.ns_per_day(1000.0, 0.5) - 43.2) < 1e-9
+
+
+def test_sharded_gather_world_size_2_gloo(tmp_path):
+    """N>1 host logic on CPU: two gloo ranks take their shard, produce per-structure results with a
+    stand-in evaluator and gather them back in input order."""
+    script = tmp_path / "worker.py"
+    script.write_text(f"""
+import os, sys
+sys.path.insert(0, {str(ROOT)!r})
+import numpy as np
+import torch.distributed as dist
+from mlff_distiller_b200 import sharding, synthetic
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+structs = synthetic.druglike_batch(11, ragged=True)
+counts = [len(s) for s in structs]
+a, b = sharding.shard_slice(counts, rank, world)
+z, pos, off = synthetic.concatenate(structs[a:b])
+e_local = np.array([pos[off[i]:off[i+1]].sum() for i in range(b - a)])   # stand-in "energy"
+f_local = pos * 2.0                                                        # stand-in "forces"
+e, f = sharding.gather_in_order(e_local, f_local)
+zz, pp, oo = synthetic.concatenate(structs)
+assert np.allclose(e, [pp[oo[i]:oo[i+1]].sum() for i in range(len(structs))])
+assert np.allclose(f, pp * 2.0)
+if rank == 0:
+    print('GATHER_OK', a, b)
+dist.destroy_process_group()
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    proc = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                           "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29731",
+                           str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert "GATHER_OK" in proc.stdout
+
+
+def test_calculator_validation_messages_without_gpu():
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+
+    class Fake:
+        max_z = 100
+        cutoff = 5.0
+
+    calc = object.__new__(StudentForceFieldCalculator)
+    calc.model = Fake()
+    calc.pbc_mode = "minimum_image"
+    ok = (np.zeros((2, 3)), np.array([1, 8]), np.eye(3) * 20, np.array([False] * 3))
+    calc._validate_inputs(*ok)
+    with pytest.raises(ValueError, match="empty structure"):
+        calc._validate_inputs(np.zeros((0, 3)), np.array([], dtype=int), np.eye(3), np.array([False] * 3))
+    with pytest.raises(ValueError, match="Invalid atomic numbers"):
+        calc._validate_inputs(np.zeros((1, 3)), np.array([0]), np.eye(3), np.array([False] * 3))
+    with pytest.raises(ValueError, match="Invalid atomic numbers"):
+        calc._validate_inputs(np.zeros((1, 3)), np.array([110]), np.eye(3), np.array([False] * 3))
+    with pytest.raises(ValueError, match="NaN"):
+        calc._validate_inputs(np.array([[np.nan, 0, 0]]), np.array([1]), np.eye(3), np.array([False] * 3))
+    with pytest.raises(ValueError, match="2\\*cutoff"):
+        calc._validate_inputs(np.zeros((1, 3)), np.array([29]), np.eye(3) * 3.58, np.array([True] * 3))
+    with pytest.raises(FileNotFoundError):
+        StudentForceFieldCalculator("/nonexistent/best_model.pt", device="cuda")
