@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Summarise .ncu-rep captures (ncu --set full) into a small text table for profiles/.
+Usage: python tools/ncu_summary.py gpurun_out/prof_*.ncu-rep > profiles/<name>.txt"""
+import csv
+import subprocess
+import sys
+
+WANT = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor.sum",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+    "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem",
+    "launch__occupancy_limit_registers", "lts__t_sector_hit_rate.pct",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
+]
+
+
+def main():
+    for path in sys.argv[1:]:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        if len(rows) < 3:
+            print(f"## {path}: no data")
+            continue
+        hdr, units = rows[0], rows[1]
+        for vals in rows[2:]:
+            name = vals[hdr.index("Kernel Name")]
+            print(f"## {path}\n   kernel: {name[:110]}")
+            for w in WANT:
+                if w in hdr:
+                    i = hdr.index(w)
+                    print(f"   {w:70s} {vals[i]:>16s} {units[i]}")
+            print()
+
+
+if __name__ == "__main__":
+    main()
