@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--variant", choices=sorted(VARIANT_FILES), default="original")
     ap.add_argument("--batch", type=int, default=1024, help="structures per GPU per step")
     ap.add_argument("--atoms", type=int, default=50)
+    ap.add_argument("--precision", choices=["fp32", "tc"], default="tc",
+                    help="fp32 = FFMA dense layers; tc = tcgen05 tensor cores with 2-term FP16 split (FP32-equivalent)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -59,7 +61,7 @@ def load_state(variant):
 def workload_config(args, world):
     return {"workload": f"C2: {args.batch} drug-like structures x {args.atoms} atoms per GPU per step, "
                         f"energy+forces, PaiNN student '{args.variant}'",
-            "variant": args.variant, "structures_per_gpu": args.batch, "atoms_per_structure": args.atoms,
+            "variant": args.variant, "precision": args.precision, "structures_per_gpu": args.batch, "atoms_per_structure": args.atoms,
             "global_batch": args.batch * world, "parallelism": f"structure-sharded x{world}, no collective",
             "l2_policy": "per-step working set (filter tables + features, >4 GB) exceeds the 126 MB L2; "
                          f"{POSITION_SETS} rotating perturbed input sets"}
@@ -255,7 +257,8 @@ def run_b200(args):
     rng = np.random.default_rng(1234 + rank)
     pos_sets64 = [pos64 + rng.normal(0.0, 0.01, pos64.shape) for _ in range(POSITION_SETS)]
 
-    calc = StudentForceFieldCalculator(ROOT / "tests" / "golden" / VARIANT_FILES[args.variant], device=str(dev))
+    calc = StudentForceFieldCalculator(ROOT / "tests" / "golden" / VARIANT_FILES[args.variant], device=str(dev),
+                                      precision=args.precision)
     model = calc.model
     eng = model.engine()
     cfg = model.config

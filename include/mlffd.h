@@ -36,10 +36,12 @@ enum {
 /* Arithmetic of the dense layers.  FP32 is the parity default (north-star tolerances 1e-5
  * eV/atom, 1e-4 eV/A); the others trade accuracy for tensor-core speed with looser bounds. */
 enum {
-    MLFFD_PREC_FP32 = 0,
-    MLFFD_PREC_TF32X3 = 1,
-    MLFFD_PREC_TF32 = 2,
-    MLFFD_PREC_BF16 = 3
+    MLFFD_PREC_FP32 = 0,      /* FP32 FFMA everywhere */
+    MLFFD_PREC_TC_FP16X2 = 1, /* tcgen05 tensor cores, operands split into two FP16 terms, three
+                                 products, FP32 accumulation in TMEM: FP32-equivalent (meets the
+                                 FP32 bounds).  H = 128 only; other sizes fall back to FFMA. */
+    MLFFD_PREC_TF32 = 2,      /* reserved: single-pass TF32, looser bounds */
+    MLFFD_PREC_BF16 = 3       /* reserved: single-pass BF16, looser bounds */
 };
 
 /* Hyper-parameters = the `config` dict of StudentForceField.save

@@ -17,7 +17,7 @@ from typing import List, Optional
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libmlffd.so"
 SOURCES = ["mlffd.cu"]
-HEADERS = ["common.cuh", "neighbor.cuh", "tile_gemm.cuh", "filter.cuh", "message.cuh",
+HEADERS = ["common.cuh", "neighbor.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "message.cuh",
            "update.cuh", "readout.cuh", "../../include/mlffd.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -32,7 +32,7 @@ EXPORTS = [
 NUM_STAGES = 10
 
 MLFFD_OK, MLFFD_EINVAL, MLFFD_ECUDA, MLFFD_ECAPACITY, MLFFD_ENOMEM = 0, -1, -2, -3, -4
-PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "bf16": 3}
+PRECISIONS = {"fp32": 0, "tc": 1}
 
 
 class MlffdConfig(ctypes.Structure):

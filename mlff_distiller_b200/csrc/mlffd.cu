@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "filter.cuh"
+#include "filter_umma.cuh"
 #include "message.cuh"
 #include "neighbor.cuh"
 #include "readout.cuh"
@@ -68,6 +69,8 @@ struct mlffd_ctx {
     bool debug_keep = false;
     std::string err;
     float* weights_d = nullptr;
+    uint8_t* w2_images_d = nullptr;   // per layer 3 x 64 KB swizzled fp16 hi/lo images (tensor-core path)
+    bool use_umma = false;
     const float *emb = nullptr, *centers = nullptr, *gammas = nullptr;
     LayerWeights layer[kMaxLayers];
     HeadWeights head{};
@@ -192,6 +195,18 @@ template <int H>
 int launch_filter(mlffd_ctx* ctx, int l, const float* dist, const int* num_pairs_ptr,
                   int num_pairs_arg, const DeviceStatus* status, float* filt, float* dfilt,
                   int64_t pair_bound, cudaStream_t st) {
+    if constexpr (H == 128) {
+        if (ctx->use_umma) {
+            const int grid = clamp_grid(ceil_div(std::max<int64_t>(pair_bound, 1), kUmmaPairs), kNumSMs);
+            filter_table_umma_kernel<<<grid, kUmmaThreads, UmmaSmem::total(ctx->K), st>>>(
+                dist, num_pairs_ptr, num_pairs_arg, status, ctx->centers, ctx->gammas, ctx->K,
+                ctx->cfg.cutoff, ctx->layer[l].filter,
+                ctx->w2_images_d + (size_t)l * 3 * kChunkImageBytes,
+                (l == 0 && status != nullptr) ? 1 : 0, filt, dfilt);
+            LAUNCHED(ctx, "filter_table_umma_kernel", MLFFD_STAGE_FILTER, st);
+            return MLFFD_OK;
+        }
+    }
     const int blocks_per_sm = (filter_smem_bytes<H>() <= 110 * 1024) ? 2 : 1;
     const int grid = clamp_grid(ceil_div(std::max<int64_t>(pair_bound, 1), kFilterPairs),
                                 kNumSMs * blocks_per_sm);
@@ -351,8 +366,8 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     if (L < 1 || L > kMaxLayers) return fail(nullptr, MLFFD_EINVAL, "num_interactions must be in 1..8");
     if (config->max_z < 1 || !(config->cutoff > 0.f))
         return fail(nullptr, MLFFD_EINVAL, "max_z and cutoff must be positive");
-    if (config->precision != MLFFD_PREC_FP32)
-        return fail(nullptr, MLFFD_EINVAL, "only MLFFD_PREC_FP32 is implemented in this build");
+    if (config->precision != MLFFD_PREC_FP32 && config->precision != MLFFD_PREC_TC_FP16X2)
+        return fail(nullptr, MLFFD_EINVAL, "precision must be MLFFD_PREC_FP32 or MLFFD_PREC_TC_FP16X2");
     const size_t per_layer = (size_t)H * K + H + 3 * H * H + 3 * H + 2 * H * H + H + 3 * H * H + 3 * H + 9;
     const size_t expect = (size_t)(config->max_z + 1) * H + 2 * K + L * per_layer +
                           (size_t)(H / 2) * H + H / 2 + (size_t)(H / 4) * (H / 2) + H / 4 + H / 4 + 1;
@@ -417,6 +432,7 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     auto bail = [&](int code, const std::string& msg) {
         g_create_error = msg;
         if (ctx->weights_d) cudaFree(ctx->weights_d);
+        if (ctx->w2_images_d) cudaFree(ctx->w2_images_d);
         if (ctx->status_d) cudaFree(ctx->status_d);
         delete ctx;
         return code;
@@ -428,6 +444,37 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     e = cudaMalloc(&ctx->status_d, sizeof(DeviceStatus));
     if (e != cudaSuccess) return bail(MLFFD_ENOMEM, cudaGetErrorString(e));
     cudaMemset(ctx->status_d, 0, sizeof(DeviceStatus));
+    if (config->precision == MLFFD_PREC_TC_FP16X2 && H == 128) {
+        // K-major SWIZZLE_128B images of W2 (torch [out=3H][in=H] is already K-major): per layer,
+        // per 128-row chunk: [hi kb0 | hi kb1 | lo kb0 | lo kb1], each 128 rows x 64 halves.
+        std::vector<__half> img((size_t)L * 3 * kChunkImageBytes / 2);
+        const float* q = weights_host + (size_t)(config->max_z + 1) * H + 2 * K;
+        for (int l = 0; l < L; ++l) {
+            const float* W2 = q + (size_t)H * K + H;   // skip W1, b1
+            for (int c = 0; c < 3; ++c)
+                for (int r = 0; r < 128; ++r)
+                    for (int k = 0; k < H; ++k) {
+                        const float x = W2[(size_t)(c * 128 + r) * H + k];
+                        const __half hi = __float2half_rn(x);
+                        const __half lo = __float2half_rn(x - __half2float(hi));
+                        const int kb = k / 64, kc = k % 64;
+                        const size_t off = (size_t)(r / 8) * 512 + (size_t)(r % 8) * 64 +
+                                           (size_t)(((kc / 8) ^ (r % 8)) * 8) + (size_t)(kc % 8);
+                        const size_t base = ((size_t)l * 3 + c) * (kChunkImageBytes / 2);
+                        img[base + (size_t)kb * (kKBlockBytes / 2) + off] = hi;
+                        img[base + (size_t)(2 + kb) * (kKBlockBytes / 2) + off] = lo;
+                    }
+            q += per_layer;
+        }
+        e = cudaMalloc(&ctx->w2_images_d, img.size() * sizeof(__half));
+        if (e != cudaSuccess) return bail(MLFFD_ENOMEM, cudaGetErrorString(e));
+        e = cudaMemcpy(ctx->w2_images_d, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
+        e = cudaFuncSetAttribute(filter_table_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)UmmaSmem::total(K));
+        if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
+        ctx->use_umma = true;
+    }
     const float* W = ctx->weights_d;
     ctx->emb = W + o_emb; ctx->centers = W + o_centers; ctx->gammas = W + o_gammas;
     for (int l = 0; l < L; ++l) {
@@ -450,6 +497,7 @@ extern "C" void mlffd_model_destroy(mlffd_ctx* ctx) {
     for (cudaEvent_t ev : ctx->event_pool) cudaEventDestroy(ev);
     if (ctx->ws.arena) cudaFree(ctx->ws.arena);
     if (ctx->weights_d) cudaFree(ctx->weights_d);
+    if (ctx->w2_images_d) cudaFree(ctx->w2_images_d);
     if (ctx->status_d) cudaFree(ctx->status_d);
     delete ctx;
 }

@@ -297,3 +297,53 @@ def test_edge_capacity_overflow_recovers(variant):
     z, pos, off = gold["drug50_numbers"], gold["drug50_positions"], gold["drug50_offsets"]
     e, f = _run(model, z, pos, off)
     assert abs(e[0] - gold["drug50_energy32"][0]) / 50 <= E_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core path (tcgen05, two-term FP16 split): must meet the SAME FP32 bounds
+# ---------------------------------------------------------------------------------------------
+def test_tensor_core_filter_table_matches_ffma_and_oracle():
+    model_tc, state, cfg = _model("original", precision="tc")
+    model_32, _, _ = _model("original")
+    rc = cfg["cutoff"]
+    d = torch.cat([torch.linspace(0.4, rc + 0.3, 4099), torch.tensor([rc, rc - 1e-6, 0.9572])]).float()
+    for l in range(cfg["num_interactions"]):
+        f_tc, df_tc = model_tc.engine().filter_table(l, d)
+        f_32, df_32 = model_32.engine().filter_table(l, d)
+        scale = max(float(f_32.abs().max()), 1.0)
+        dscale = max(float(df_32.abs().max()), 1.0)
+        assert float((f_tc - f_32).abs().max()) < 4e-6 * scale, l
+        assert float((df_tc - df_32).abs().max()) < 4e-6 * dscale, l
+
+
+def test_tensor_core_energy_forces_match_golden():
+    model, state, cfg = _model("original", precision="tc")
+    gold = load_golden("original")
+    report = {}
+    for case in golden_cases(gold):
+        z, pos, off = gold[f"{case}_numbers"], gold[f"{case}_positions"], gold[f"{case}_offsets"]
+        e, f = _run(model, z, pos, off)
+        natoms = np.diff(off)
+        de64 = float(np.max(np.abs(e - gold[f"{case}_energy64"]) / natoms))
+        df64 = float(np.max(np.abs(f - gold[f"{case}_forces64"])))
+        ref_noise = float(np.max(np.abs(gold[f"{case}_forces32"] - gold[f"{case}_forces64"])))
+        report[case] = {"dE64_per_atom": de64, "dF64": df64, "ref_fp32_vs_fp64_F": ref_noise}
+        assert de64 <= E_TOL, (case, de64)
+        if not case.endswith("_exact"):
+            assert df64 <= max(F_TOL, 2 * ref_noise), (case, df64)
+    OUT.mkdir(exist_ok=True)
+    (OUT / "parity_original_tc.json").write_text(json.dumps(report, indent=1))
+
+
+def test_tensor_core_batch_matches_oracle():
+    from mlff_distiller_b200 import synthetic
+    model, state, cfg = _model("original", precision="tc")
+    structs = synthetic.druglike_batch(130, first=700)   # 6500 atoms: several tiles per CTA incl. a ragged tail
+    z, pos, off = synthetic.concatenate(structs)
+    pos = pos.astype(np.float32)
+    e, f = _run(model, z, pos, off)
+    e2, f2 = _run(model, z, pos, off)
+    assert np.array_equal(e, e2) and np.array_equal(f, f2)
+    e_ref, f_ref = po.evaluate(state, cfg["cutoff"], z, pos, off, dtype=torch.float64, dense_graph=False)
+    assert np.max(np.abs(e - e_ref) / np.diff(off)) <= E_TOL
+    assert np.max(np.abs(f - f_ref)) <= F_TOL

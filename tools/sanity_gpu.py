@@ -17,11 +17,13 @@ from mlff_distiller_b200.student_model import StudentForceField  # noqa: E402
 
 
 def main():
-    variants = sys.argv[1:] or ["original", "tiny", "ultra_tiny"]
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    precision = "tc" if "--tc" in sys.argv else "fp32"
+    variants = args or ["original", "tiny", "ultra_tiny"]
     for variant in variants:
         state, cfg = load_weights(variant)
         gold = load_golden(variant)
-        model = StudentForceField.from_state(state, infer_config(state, cfg), "cuda:0")
+        model = StudentForceField.from_state(state, infer_config(state, cfg), "cuda:0", precision=precision)
         for case in ("h2o", "single_atom", "isolated", "drug50", "ragged", "chain300"):
             z = torch.from_numpy(gold[f"{case}_numbers"].astype(np.int32)).cuda()
             pos = torch.from_numpy(gold[f"{case}_positions"]).cuda()
