@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include "cell_list.cuh"
 #include "common.cuh"
 #include "filter.cuh"
 #include "filter_umma.cuh"
@@ -44,6 +45,11 @@ struct Workspace {
     int *col = nullptr, *edge_dst = nullptr, *rev = nullptr, *pair = nullptr;
     float4 *geo = nullptr, *edge_adj = nullptr;
     float* pair_dist = nullptr;
+    // cell list (large structures)
+    GridInfo* grids = nullptr;
+    int *ncells = nullptr, *total_cells = nullptr, *atom_cell = nullptr, *cell_count = nullptr,
+        *cell_start = nullptr, *cell_cursor = nullptr, *cell_atoms = nullptr;
+    int64_t cap_cells = 0;
     // per layer
     float* filt[kMaxLayers] = {};
     float* dfilt[kMaxLayers] = {};
@@ -67,6 +73,7 @@ struct mlffd_ctx {
     mlffd_config cfg{};
     int H = 0, K = 0, L = 0;
     bool debug_keep = false;
+    int neighbor_mode = 0;   // 0 auto, 1 sweep, 2 cells (env MLFFD_NEIGHBOR)
     std::string err;
     float* weights_d = nullptr;
     uint8_t* w2_images_d = nullptr;   // per layer 3 x 64 KB swizzled fp16 hi/lo images (tensor-core path)
@@ -313,11 +320,38 @@ int build_neighbors(mlffd_ctx* ctx, const float* pos, const int* offsets, int n_
     CUDA_TRY(ctx, cudaMemsetAsync(ws.deg + N, 0, sizeof(int), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ws.deg_low + N, 0, sizeof(int), st));
     const int sweep_grid = clamp_grid(ceil_div(N, 8), kNumSMs * 16);
-    neighbor_sweep_kernel<false><<<sweep_grid, 256, 0, st>>>(
-        pos, offsets, ws.atom_struct, cells, pbc, N, ctx->cfg.cutoff, ws.deg, ws.deg_low, nullptr,
-        nullptr, nullptr, nullptr, ctx->status_d);
-    LAUNCHED(ctx, "neighbor_sweep_kernel<count>", MLFFD_STAGE_NEIGHBOR, st);
-    size_t bytes = ws.cub_bytes;
+    const bool use_cells = ctx->neighbor_mode == 2 ||
+                           (ctx->neighbor_mode == 0 && n_atoms >= (int64_t)2048 * n_structs);
+    size_t bytes;
+    if (use_cells) {
+        const int C = (int)ws.cap_cells;
+        const int cap_per_struct = (int)std::max<int64_t>(8, 2 * (n_atoms / n_structs));
+        grid_setup_kernel<<<n_structs, 256, 0, st>>>(pos, offsets, cells, pbc, ctx->cfg.cutoff,
+                                                     cap_per_struct, ws.grids, ws.ncells);
+        LAUNCHED(ctx, "grid_setup_kernel", MLFFD_STAGE_NEIGHBOR, st);
+        grid_offsets_kernel<<<1, 32, 0, st>>>(ws.grids, ws.ncells, n_structs, ws.total_cells);
+        LAUNCHED(ctx, "grid_offsets_kernel", MLFFD_STAGE_NEIGHBOR, st);
+        CUDA_TRY(ctx, cudaMemsetAsync(ws.cell_count, 0, sizeof(int) * (C + 1), st));
+        CUDA_TRY(ctx, cudaMemsetAsync(ws.cell_cursor, 0, sizeof(int) * (C + 1), st));
+        const int atom_grid = clamp_grid(ceil_div(N, 256), kNumSMs * 8);
+        cell_count_kernel<<<atom_grid, 256, 0, st>>>(pos, ws.atom_struct, ws.grids, N, ws.atom_cell, ws.cell_count);
+        LAUNCHED(ctx, "cell_count_kernel", MLFFD_STAGE_NEIGHBOR, st);
+        bytes = ws.cub_bytes;
+        CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ws.cub_temp, bytes, ws.cell_count, ws.cell_start, C + 1, st));
+        mark(ctx, MLFFD_STAGE_NEIGHBOR, st, 2);
+        cell_fill_kernel<<<atom_grid, 256, 0, st>>>(ws.atom_cell, ws.cell_start, ws.cell_cursor, N, ws.cell_atoms);
+        LAUNCHED(ctx, "cell_fill_kernel", MLFFD_STAGE_NEIGHBOR, st);
+        neighbor_cells_kernel<false><<<sweep_grid, 256, 0, st>>>(
+            pos, ws.atom_struct, cells, ws.grids, ws.cell_start, ws.cell_atoms, N, ctx->cfg.cutoff,
+            ws.deg, ws.deg_low, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->status_d);
+        LAUNCHED(ctx, "neighbor_cells_kernel<count>", MLFFD_STAGE_NEIGHBOR, st);
+    } else {
+        neighbor_sweep_kernel<false><<<sweep_grid, 256, 0, st>>>(
+            pos, offsets, ws.atom_struct, cells, pbc, N, ctx->cfg.cutoff, ws.deg, ws.deg_low, nullptr,
+            nullptr, nullptr, nullptr, ctx->status_d);
+        LAUNCHED(ctx, "neighbor_sweep_kernel<count>", MLFFD_STAGE_NEIGHBOR, st);
+    }
+    bytes = ws.cub_bytes;
     CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ws.cub_temp, bytes, ws.deg, ws.rowptr, N + 1, st));
     bytes = ws.cub_bytes;
     CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ws.cub_temp, bytes, ws.deg_low, ws.lowptr, N + 1, st));
@@ -325,10 +359,18 @@ int build_neighbors(mlffd_ctx* ctx, const float* pos, const int* offsets, int n_
     neighbor_finalize_kernel<<<1, 32, 0, st>>>(ws.rowptr, ws.lowptr, N, (int)ws.cap_edges,
                                                ctx->status_d);
     LAUNCHED(ctx, "neighbor_finalize_kernel", MLFFD_STAGE_NEIGHBOR, st);
-    neighbor_sweep_kernel<true><<<sweep_grid, 256, 0, st>>>(
-        pos, offsets, ws.atom_struct, cells, pbc, N, ctx->cfg.cutoff, nullptr, nullptr, ws.rowptr,
-        ws.col, ws.edge_dst, ws.geo, ctx->status_d);
-    LAUNCHED(ctx, "neighbor_sweep_kernel<fill>", MLFFD_STAGE_NEIGHBOR, st);
+    if (use_cells) {
+        // scratch for the unsorted rows: `rev` and `edge_adj` are only written by later kernels
+        neighbor_cells_kernel<true><<<sweep_grid, 256, 0, st>>>(
+            pos, ws.atom_struct, cells, ws.grids, ws.cell_start, ws.cell_atoms, N, ctx->cfg.cutoff,
+            nullptr, nullptr, ws.rowptr, ws.rev, ws.edge_adj, ws.col, ws.edge_dst, ws.geo, ctx->status_d);
+        LAUNCHED(ctx, "neighbor_cells_kernel<fill>", MLFFD_STAGE_NEIGHBOR, st);
+    } else {
+        neighbor_sweep_kernel<true><<<sweep_grid, 256, 0, st>>>(
+            pos, offsets, ws.atom_struct, cells, pbc, N, ctx->cfg.cutoff, nullptr, nullptr, ws.rowptr,
+            ws.col, ws.edge_dst, ws.geo, ctx->status_d);
+        LAUNCHED(ctx, "neighbor_sweep_kernel<fill>", MLFFD_STAGE_NEIGHBOR, st);
+    }
     reverse_pair_kernel<<<clamp_grid(ceil_div(std::max<int64_t>(ws.cap_edges, 1), 256), kNumSMs * 8),
                           256, 0, st>>>(ws.rowptr, ws.lowptr, ws.col, ws.edge_dst, ws.geo, ws.rev,
                                         ws.pair, ws.pair_dist, ctx->status_d);
@@ -389,6 +431,8 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     ctx->H = H; ctx->K = K; ctx->L = L;
     const char* dbg = std::getenv("MLFFD_DEBUG_KEEP");
     ctx->debug_keep = dbg && dbg[0] == '1';
+    if (const char* nm = std::getenv("MLFFD_NEIGHBOR"))
+        ctx->neighbor_mode = (std::strcmp(nm, "sweep") == 0) ? 1 : (std::strcmp(nm, "cells") == 0) ? 2 : 0;
 
     // walk the blob in state_dict order and stage the device layout
     Stager st;
@@ -534,7 +578,20 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
     const size_t o_adj = plan.take(sizeof(float4) * E);
     const size_t o_pdist = plan.take(sizeof(float) * P);
     const size_t o_eps = plan.take(sizeof(float) * N);
+    const int64_t C = 2 * N + 8 * max_structures + 2;   // cell capacity (grid_setup caps cells per structure)
+    {
+        size_t cub_cells = 0;
+        CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(nullptr, cub_cells, (int*)nullptr, (int*)nullptr, (int)(C + 1)));
+        cub_bytes = std::max(cub_bytes, cub_cells);
+    }
     const size_t o_cub = plan.take(cub_bytes);
+    const size_t o_grids = plan.take(sizeof(GridInfo) * max_structures);
+    const size_t o_ncells = plan.take(sizeof(int) * (max_structures + 1));
+    const size_t o_atom_cell = plan.take(sizeof(int) * N);
+    const size_t o_cell_count = plan.take(sizeof(int) * (C + 1));
+    const size_t o_cell_start = plan.take(sizeof(int) * (C + 1));
+    const size_t o_cell_cursor = plan.take(sizeof(int) * (C + 1));
+    const size_t o_cell_atoms = plan.take(sizeof(int) * N);
     size_t o_filt[kMaxLayers], o_dfilt[kMaxLayers], o_s_in[kMaxLayers + 1], o_v_in[kMaxLayers],
         o_s_msg[kMaxLayers], o_v_msg[kMaxLayers], o_y1[kMaxLayers], o_gates[kMaxLayers],
         o_sbar[kMaxLayers], o_vbar[kMaxLayers];
@@ -574,6 +631,12 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
     ws.pair_dist = (float*)(base + o_pdist);
     ws.eps = (float*)(base + o_eps);
     ws.cub_temp = base + o_cub; ws.cub_bytes = cub_bytes;
+    ws.grids = (GridInfo*)(base + o_grids);
+    ws.ncells = (int*)(base + o_ncells); ws.total_cells = ws.ncells + max_structures;
+    ws.atom_cell = (int*)(base + o_atom_cell);
+    ws.cell_count = (int*)(base + o_cell_count); ws.cell_start = (int*)(base + o_cell_start);
+    ws.cell_cursor = (int*)(base + o_cell_cursor); ws.cell_atoms = (int*)(base + o_cell_atoms);
+    ws.cap_cells = C;
     for (int l = 0; l < L; ++l) {
         ws.filt[l] = (float*)(base + o_filt[l]); ws.dfilt[l] = (float*)(base + o_dfilt[l]);
         ws.s_in[l] = (float*)(base + o_s_in[l]);

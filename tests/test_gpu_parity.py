@@ -347,3 +347,66 @@ def test_tensor_core_batch_matches_oracle():
     e_ref, f_ref = po.evaluate(state, cfg["cutoff"], z, pos, off, dtype=torch.float64, dense_graph=False)
     assert np.max(np.abs(e - e_ref) / np.diff(off)) <= E_TOL
     assert np.max(np.abs(f - f_ref)) <= F_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# cell-list candidate generator (large structures): same edges, bit for bit
+# ---------------------------------------------------------------------------------------------
+def _with_neighbor_mode(mode, variant="ultra_tiny"):
+    os.environ["MLFFD_NEIGHBOR"] = mode
+    try:
+        return _model(variant)
+    finally:
+        os.environ.pop("MLFFD_NEIGHBOR", None)
+
+
+def test_cell_list_edges_bit_exact_small_and_batched():
+    from mlff_distiller_b200.student_model import radius_graph
+    model, state, cfg = _with_neighbor_mode("cells")
+    gold = load_golden("ultra_tiny")
+    for case in golden_cases(gold):
+        pos, off = gold[f"{case}_positions"], gold[f"{case}_offsets"]
+        ei = radius_graph(torch.from_numpy(pos), cfg["cutoff"], po.batch_from_offsets(off).cuda(),
+                          engine=model.engine()).cpu().numpy()
+        assert np.array_equal(ei, gold[f"{case}_edge_index"]), case
+    rng = np.random.default_rng(21)
+    n, L = 700, 16.0
+    pos = rng.uniform(-5.0, L + 5.0, size=(n, 3)).astype(np.float32)
+    cell = np.array([[L, 0, 0], [2.0, L, 0], [1.0, -1.5, L + 3]], dtype=np.float64)
+    for pbc in ([True, True, True], [True, False, True], [False, False, True]):
+        ei_ref, _ = po.neighbor_list(pos, [0, n], cfg["cutoff"], cell[None], np.array([pbc]))
+        ei = radius_graph(torch.from_numpy(pos), cfg["cutoff"], None, engine=model.engine(),
+                          cell=torch.from_numpy(cell), pbc=torch.tensor(pbc)).cpu().numpy()
+        assert np.array_equal(ei, ei_ref), pbc
+
+
+def test_cell_list_water_box_10k_atoms():
+    """BASELINE config C4: 9 999-atom periodic water box, automatic path selection (cells)."""
+    from mlff_distiller_b200 import synthetic
+    from mlff_distiller_b200.student_model import radius_graph
+    model, state, cfg = _model("ultra_tiny")
+    box = synthetic.water_box()
+    pos = box.positions.astype(np.float32)
+    ei = radius_graph(torch.from_numpy(pos), cfg["cutoff"], None, engine=model.engine(),
+                      cell=torch.from_numpy(box.cell), pbc=torch.from_numpy(box.pbc)).cpu().numpy()
+    ei_ref, _ = po.neighbor_list(pos, [0, len(pos)], cfg["cutoff"], box.cell[None], box.pbc[None])
+    assert ei.shape[1] > 400_000
+    assert np.array_equal(ei, ei_ref)
+    # open-boundary blob of the same size: cells vs the reference semantics
+    blob = (np.random.default_rng(3).uniform(0, 60.0, size=(6000, 3))).astype(np.float32)
+    ei2 = radius_graph(torch.from_numpy(blob), cfg["cutoff"], None, engine=model.engine()).cpu().numpy()
+    ei2_ref, _ = po.neighbor_list(blob, [0, 6000], cfg["cutoff"])
+    assert np.array_equal(ei2, ei2_ref)
+
+
+def test_cell_list_energy_forces_periodic_1500_atoms():
+    from mlff_distiller_b200 import synthetic
+    model, state, cfg = _with_neighbor_mode("cells", "tiny")
+    box = synthetic.water_box(n_mol=500, seed=3002)
+    z, pos = box.numbers, box.positions.astype(np.float32)
+    off = [0, len(z)]
+    e, f = _run(model, z, pos, off, box.cell[None], box.pbc[None])
+    e_ref, f_ref = po.evaluate(state, cfg["cutoff"], z, pos, off, box.cell[None], box.pbc[None],
+                               dtype=torch.float64)
+    assert abs(e[0] - e_ref[0]) / len(z) <= E_TOL
+    assert np.max(np.abs(f - f_ref)) <= max(F_TOL, 2e-6 * float(np.abs(f_ref).max()))
