@@ -33,6 +33,14 @@ __device__ __forceinline__ float silu_gradf_(float x) {
 __device__ __forceinline__ float4 ldg4(const float* p) {
     return __ldg(reinterpret_cast<const float4*>(p));
 }
+// Streaming (evict-first) 16-byte load/store for data that is touched once per kernel -- the
+// filter-table rows -- so it does not push the gathered per-atom feature rows out of L2.
+__device__ __forceinline__ float4 ldcs4(const float* p) {
+    return __ldcs(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void stcs4(float* p, const float4& v) {
+    __stcs(reinterpret_cast<float4*>(p), v);
+}
 __device__ __forceinline__ void st4(float* p, const float4& v) {
     *reinterpret_cast<float4*>(p) = v;
 }

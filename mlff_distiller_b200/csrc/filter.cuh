@@ -129,9 +129,9 @@ filter_table_kernel(const float* __restrict__ pair_dist, const int* __restrict__
                     for (int q = 0; q < T::VW; ++q)
                         v[q] = acc[r][g * T::VW + q] + (tangent ? 0.f : __ldg(w.b2 + nc * H + col + q));
                     if constexpr (T::VW == 4)
-                        st4(out + col, make_float4(v[0], v[1], v[2], v[3]));
+                        stcs4(out + col, make_float4(v[0], v[1], v[2], v[3]));
                     else
-                        *reinterpret_cast<float2*>(out + col) = make_float2(v[0], v[1]);
+                        __stcs(reinterpret_cast<float2*>(out + col), make_float2(v[0], v[1]));
                 }
             }
             __syncthreads();

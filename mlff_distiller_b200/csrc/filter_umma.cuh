@@ -318,7 +318,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                 float* o = out + nc * 128;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (row0 + j < P) o[(size_t)j * (3 * H)] = __uint_as_float(r[j]) + b;
+                    if (row0 + j < P) __stcs(o + (size_t)j * (3 * H), __uint_as_float(r[j]) + b);
             }
             // all MMAs of tile `it` are complete (last chunk waited): the activation tile is free
             if (it + 1 < my_tiles) publish_tile();
