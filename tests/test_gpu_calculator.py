@@ -1,0 +1,145 @@
+"""Calculator semantics on the GPU, mirroring the reference's
+tests/integration/test_ase_calculator.py (which needs ASE + a trained checkpoint and cannot run
+here): result types, n_calls, ASE-style caching, validation errors, calculate_batch, timing,
+PBC handling, reset/repr, short NVE runs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden
+from mlff_distiller_b200 import md, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def calc():
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+    return StudentForceFieldCalculator(GOLDEN / "weights_original.npz", device="cuda", enable_timing=True,
+                                       use_compile=True, use_fp16=True, use_torch_cluster=False,
+                                       use_analytical_forces=True, batch_size=8)  # reference kwargs accepted
+
+
+def test_energy_forces_types_and_golden(calc):
+    gold = load_golden("original")
+    atoms = synthetic.water()
+    atoms.calc = calc
+    n0 = calc.n_calls
+    e = atoms.get_potential_energy()
+    f = atoms.get_forces()
+    assert isinstance(e, float) and np.isfinite(e)
+    assert f.shape == (3, 3) and f.dtype == np.float32 and np.isfinite(f).all()
+    assert abs(e - float(gold["h2o_energy32"][0])) < 3e-5
+    assert np.abs(f - gold["h2o_forces32"]).max() < 1e-4
+    assert calc.n_calls == n0 + 1  # the forces came from the cache
+
+
+def test_cache_and_n_calls(calc):
+    atoms = synthetic.benzene()
+    atoms.calc = calc
+    n0 = calc.n_calls
+    atoms.get_potential_energy(); atoms.get_forces(); atoms.get_potential_energy()
+    assert calc.n_calls == n0 + 1
+    atoms.set_positions(atoms.get_positions() + 0.01)
+    atoms.get_forces()
+    assert calc.n_calls == n0 + 2
+    stats = calc.get_timing_stats()
+    for key in ("n_calls", "total_time", "avg_time", "min_time", "max_time", "median_time"):
+        assert key in stats
+    assert calc.avg_time > 0
+
+
+def test_validation_errors(calc):
+    with pytest.raises(ValueError, match="empty structure"):
+        calc.calculate(synthetic.Structure([], np.zeros((0, 3))))
+    bad = synthetic.water()
+    bad.positions[0, 0] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        calc.calculate(bad)
+    with pytest.raises(ValueError, match="Invalid atomic numbers"):
+        calc.calculate(synthetic.Structure([0, 1], [[0, 0, 0], [1, 0, 0]]))
+    with pytest.raises(ValueError, match="Invalid atomic numbers"):
+        calc.calculate(synthetic.Structure([105], [[0, 0, 0]]))  # beyond the trained embedding (max_z = 100)
+
+
+def test_calculate_batch_matches_single(calc):
+    assert calc.calculate_batch([]) == []
+    structs = [synthetic.water(), synthetic.benzene()] + synthetic.druglike_batch(3, first=50, ragged=True)
+    res = calc.calculate_batch(structs)
+    assert len(res) == len(structs)
+    for s, r in zip(structs, res):
+        assert isinstance(r["energy"], float) and r["forces"].shape == (len(s), 3)
+        calc.calculate(s.copy())
+        assert abs(r["energy"] - calc.results["energy"]) < 1e-4 * max(1.0, abs(r["energy"]) * 1e-2)
+        assert np.abs(r["forces"] - calc.results["forces"]).max() < 1e-4
+    one = calc.calculate_batch([synthetic.water()])
+    assert len(one) == 1 and one[0]["forces"].shape == (3, 3) and one[0]["stress"] is None
+    only_e = calc.calculate_batch(structs[:2], properties=["energy"])
+    assert "forces" not in only_e[0]
+
+
+def test_pbc_inputs(calc):
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+    # reference behaviour (tests/integration/test_ase_calculator.py:255-278): PBC given, ignored
+    cu = synthetic.Structure([29], [[0, 0, 0]], cell=np.array([[0, 1.79, 1.79], [1.79, 0, 1.79], [1.79, 1.79, 0]]),
+                             pbc=[True, True, True])
+    calc.calculate(cu)
+    assert np.isfinite(calc.results["energy"]) and np.isfinite(calc.results["forces"]).all()
+    pbc_calc = StudentForceFieldCalculator(GOLDEN / "weights_ultra_tiny.npz", device="cuda", pbc_mode="minimum_image")
+    with pytest.raises(ValueError, match="2\\*cutoff"):
+        pbc_calc.calculate(cu)
+    box = synthetic.water_box(n_mol=64, seed=5)
+    pbc_calc.calculate(box)
+    e_pbc = pbc_calc.results["energy"]
+    ign = StudentForceFieldCalculator(GOLDEN / "weights_ultra_tiny.npz", device="cuda")
+    ign.calculate(box)
+    assert abs(e_pbc - ign.results["energy"]) > 1e-3  # periodic images do contribute
+    assert pbc_calc.implemented_properties == ["energy", "forces"]
+    assert "stress" in StudentForceFieldCalculator(GOLDEN / "weights_ultra_tiny.npz", device="cuda",
+                                                    enable_stress=True).implemented_properties
+
+
+def test_reset_and_repr(calc):
+    calc.calculate(synthetic.water())
+    calc.reset()
+    assert calc.results == {}
+    assert "StudentForceFieldCalculator" in repr(calc) and "weights_original.npz" in repr(calc)
+
+
+def test_descent_lowers_energy_and_short_nve(calc):
+    atoms = synthetic.druglike(4321, 24)
+    x = atoms.get_positions()
+    work = atoms.copy()
+
+    def ef(pos):
+        work.set_positions(pos)
+        calc.calculate(work)
+        return calc.results["energy"], calc.results["forces"].astype(np.float64)
+
+    e0, f = ef(x)
+    for _ in range(20):
+        x = x + 0.002 * f
+        e1, f = ef(x)
+    assert e1 < e0
+    # reference test: 10-step NVE drift < 10 %
+    m = atoms.get_masses()
+    v0 = md.maxwell_boltzmann(m, 300.0, np.random.default_rng(0))
+    out = md.velocity_verlet(ef, x, v0, m, steps=10, dt_fs=0.5)
+    assert abs(out["drift_percent"]) < 10.0
+
+
+def test_h2o_nve_1000_steps_drift_within_reference_bar(calc):
+    """BASELINE config C1: 1000 velocity-Verlet steps at 0.5 fs, T0 = 300 K, seed 42;
+    |drift| <= 0.14 % (README.md:82 of the reference)."""
+    atoms = synthetic.water()
+    work = atoms.copy()
+
+    def ef(pos):
+        work.set_positions(pos)
+        calc.calculate(work)
+        return calc.results["energy"], calc.results["forces"]
+
+    m = atoms.get_masses()
+    v0 = md.maxwell_boltzmann(m, 300.0, np.random.default_rng(42), atoms.get_positions(), zero_rotation=True)
+    out = md.velocity_verlet(ef, atoms.get_positions(), v0, m, steps=1000, dt_fs=0.5)
+    assert abs(out["drift_percent"]) <= 0.14
