@@ -63,6 +63,8 @@ typedef struct mlffd_status {
     int64_t edge_capacity;
     int32_t overflow;    /* 1: edges exceeded capacity, outputs invalid -> reserve and retry */
     int32_t max_degree;
+    int64_t overflow_events; /* sticky count of overflowed builds since mlffd_model_create (lets a
+                                caller that enqueues many steps, e.g. on-device MD, detect one) */
 } mlffd_status;
 
 typedef struct mlffd_ctx mlffd_ctx;
@@ -182,6 +184,22 @@ typedef struct mlffd_profile {
 int mlffd_profile_enable(mlffd_ctx* ctx, int32_t enable);
 int mlffd_profile_read(mlffd_ctx* ctx, mlffd_profile* out);
 const char* mlffd_stage_name(int32_t stage);
+
+/*
+ * On-device velocity Verlet (replaces the host-side ASE VelocityVerlet loop the reference drives
+ * through src/mlff_distiller/testing/nve_harness.py:214-235; one step = kick_drift,
+ * mlffd_energy_forces on pos32_d, kick_energy).  Integrator state is FP64 (as ASE's), the model
+ * sees FP32 positions (as inference/ase_calculator.py:497-500).  ASE units: eV, Angstrom, amu;
+ * dt in ASE time units (fs * 0.0982269...).  The three calls are graph-capturable.
+ *   kick_drift : v += dt/2 F/m ; x += dt v ; pos32 = float(x)
+ *   kick_energy: v += dt/2 F/m ; series[*counter] = (sum_b E_b, sum m v^2/2) ; ++*counter
+ */
+int mlffd_md_kick_drift(int64_t num_atoms, double* pos_d, double* vel_d, const float* forces_d,
+                        const double* inv_mass_d, double dt, float* pos32_d, void* stream);
+int mlffd_md_kick_energy(int64_t num_atoms, double* vel_d, const float* forces_d,
+                         const double* inv_mass_d, double dt, const float* energy_d,
+                         int32_t num_structures, double* series_d, int32_t* counter_d,
+                         int32_t capacity, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,8 @@ struct DeviceStatus {
     int num_pairs;
     int overflow;
     int max_degree;
+    int overflow_events;   // sticky: number of neighbour builds that overflowed since creation
+    int reserved_;
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "filter.cuh"
 #include "filter_umma.cuh"
+#include "md.cuh"
 #include "message.cuh"
 #include "neighbor.cuh"
 #include "readout.cuh"
@@ -715,6 +716,7 @@ extern "C" int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out) {
     out->edge_capacity = ctx->ws.cap_edges;
     out->overflow = h.overflow;
     out->max_degree = h.max_degree;
+    out->overflow_events = h.overflow_events;
     return MLFFD_OK;
 }
 
@@ -804,4 +806,29 @@ extern "C" const char* mlffd_stage_name(int32_t stage) {
         "neighbor", "embedding", "filter", "message_fwd", "update_fwd", "readout", "energy_sum",
         "update_bwd", "message_bwd", "force"};
     return (stage >= 0 && stage < MLFFD_NUM_STAGES) ? names[stage] : "";
+}
+
+// ---- on-device velocity Verlet (stateless helpers; any stream) -------------------------------
+extern "C" int mlffd_md_kick_drift(int64_t num_atoms, double* pos_d, double* vel_d,
+                                   const float* forces_d, const double* inv_mass_d, double dt,
+                                   float* pos32_d, void* stream) {
+    if (num_atoms < 1 || !pos_d || !vel_d || !forces_d || !inv_mass_d || !pos32_d) return MLFFD_EINVAL;
+    const long long n3 = 3 * (long long)num_atoms;
+    md_kick_drift_kernel<<<clamp_grid(ceil_div(n3, 256), kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(
+        n3, pos_d, vel_d, forces_d, inv_mass_d, dt, pos32_d);
+    return cudaGetLastError() == cudaSuccess ? MLFFD_OK : MLFFD_ECUDA;
+}
+
+extern "C" int mlffd_md_kick_energy(int64_t num_atoms, double* vel_d, const float* forces_d,
+                                    const double* inv_mass_d, double dt, const float* energy_d,
+                                    int32_t num_structures, double* series_d, int32_t* counter_d,
+                                    int32_t capacity, void* stream) {
+    if (num_atoms < 1 || !vel_d || !forces_d || !inv_mass_d || !energy_d || !series_d || !counter_d)
+        return MLFFD_EINVAL;
+    const long long n3 = 3 * (long long)num_atoms;
+    cudaStream_t st = (cudaStream_t)stream;
+    md_kick_kernel<<<clamp_grid(ceil_div(n3, 256), kNumSMs * 8), 256, 0, st>>>(n3, vel_d, forces_d, inv_mass_d, dt);
+    md_energy_kernel<<<1, 1024, 0, st>>>(n3, vel_d, inv_mass_d, energy_d, num_structures, series_d,
+                                         counter_d, capacity);
+    return cudaGetLastError() == cudaSuccess ? MLFFD_OK : MLFFD_ECUDA;
 }

@@ -102,6 +102,7 @@ __global__ void neighbor_finalize_kernel(const int* __restrict__ rowptr,
         status->num_edges = e;
         status->num_pairs = lowptr[num_atoms];
         status->overflow = (e > edge_capacity) ? 1 : 0;
+        if (e > edge_capacity) status->overflow_events += 1;
         status->max_degree = 0;
     }
 }

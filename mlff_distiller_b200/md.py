@@ -100,3 +100,124 @@ def velocity_verlet(force_fn: Callable[[np.ndarray], Tuple[float, np.ndarray]],
 def ns_per_day(steps_per_second: float, dt_fs: float = 0.5) -> float:
     """ns/day = steps/s * dt[fs] * 86400 * 1e-6."""
     return steps_per_second * dt_fs * 86400.0 * 1e-6
+
+
+class DeviceMD:
+    """NVE trajectory with positions, velocities and forces resident on the GPU.
+
+    One step = ``mlffd_md_kick_drift`` -> ``mlffd_energy_forces`` -> ``mlffd_md_kick_energy``
+    (include/mlffd.h), optionally captured once into a CUDA graph and replayed, so a step costs one
+    graph launch and no host<->device copy; the (PE, KE) series is read back after ``run``.
+    Integrator state is FP64 on the device; the model sees FP32 positions, like the reference's
+    calculator does every step.  ``structures`` may hold several independent systems (offsets).
+    """
+
+    def __init__(self, model, numbers, positions, velocities, masses, dt_fs: float = 0.5,
+                 offsets=None, cell=None, pbc=None, use_graph: bool = True, capacity: int = 1 << 20):
+        import ctypes
+        import torch
+        self.torch, self.ctypes = torch, ctypes
+        self.model, self.eng = model, model.engine()
+        self.lib = self.eng.lib
+        dev = self.eng.device
+        n = len(numbers)
+        self.n, self.dt = n, float(dt_fs) * FS
+        offsets = np.array([0, n], dtype=np.int32) if offsets is None else np.asarray(offsets, dtype=np.int32)
+        self.nb = len(offsets) - 1
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.z = torch.from_numpy(np.ascontiguousarray(numbers, dtype=np.int32)).to(dev)
+        self.off = torch.from_numpy(offsets).to(dev)
+        self.pos = torch.tensor(np.asarray(positions, dtype=np.float64).reshape(n, 3), **f64)
+        self.vel = torch.tensor(np.asarray(velocities, dtype=np.float64).reshape(n, 3), **f64)
+        self.inv_mass = torch.tensor(1.0 / np.asarray(masses, dtype=np.float64), **f64)
+        self.pos32 = self.pos.to(torch.float32)
+        self.energy = torch.zeros(self.nb, dtype=torch.float32, device=dev)
+        self.forces = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+        self.capacity = int(capacity)
+        self.series = torch.zeros((self.capacity, 2), **f64)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.cells = self.pbc = None
+        if cell is not None and pbc is not None and bool(np.any(pbc)):
+            self.cells, self.pbc = model.pack_cells(torch.as_tensor(np.asarray(cell)), torch.as_tensor(np.asarray(pbc)),
+                                                    self.nb, dev)
+        self.use_graph, self.graph, self._graph_caps = use_graph, None, None
+        # forces at t = 0 (sizes the workspace; 1.5x edge head-room for density fluctuations)
+        for _ in range(3):
+            self.eng.ensure(n, self.nb)
+            self._forces()
+            st = self.eng.status()
+            if not st.overflow:
+                self.eng.reserve(n, int(st.num_edges * 1.5) + 64, self.nb)
+                break
+            self.eng.reserve(n, int(st.num_edges * 1.5) + 64, self.nb)
+        self._forces()
+        self._events0 = int(self.eng.status().overflow_events)
+        self._record(0.0)  # series[0] = (PE, KE) at t = 0
+
+    def _ptr(self, t):
+        return None if t is None else t.data_ptr()
+
+    def _forces(self):
+        self.eng.energy_forces_async(self.z, self.pos32, self.off, self.nb, self.energy, self.forces,
+                                     self.cells, self.pbc)
+
+    def _record(self, dt):
+        rc = self.lib.mlffd_md_kick_energy(self.n, self.vel.data_ptr(), self.forces.data_ptr(),
+                                           self.inv_mass.data_ptr(), dt, self.energy.data_ptr(), self.nb,
+                                           self.series.data_ptr(), self.counter.data_ptr(), self.capacity,
+                                           self.eng._stream())
+        if rc:
+            raise RuntimeError(f"mlffd_md_kick_energy failed ({rc})")
+
+    def _step(self):
+        rc = self.lib.mlffd_md_kick_drift(self.n, self.pos.data_ptr(), self.vel.data_ptr(), self.forces.data_ptr(),
+                                          self.inv_mass.data_ptr(), self.dt, self.pos32.data_ptr(), self.eng._stream())
+        if rc:
+            raise RuntimeError(f"mlffd_md_kick_drift failed ({rc})")
+        self._forces()
+        self._record(self.dt)
+
+    def run(self, steps: int) -> Dict[str, np.ndarray]:
+        """Advance ``steps`` steps; returns the energy series so far (step 0 included)."""
+        torch = self.torch
+        caps = (self.eng.cap_atoms, self.eng.cap_edges, self.eng.cap_structs)
+        if self.use_graph and (self.graph is None or self._graph_caps != caps):
+            side = torch.cuda.Stream(device=self.eng.device)
+            side.wait_stream(torch.cuda.current_stream(self.eng.device))
+            with torch.cuda.stream(side):  # warm-up outside capture, then capture one step
+                state = (self.pos.clone(), self.vel.clone(), self.forces.clone(), self.energy.clone(),
+                         self.counter.clone())
+                self._step()
+                side.synchronize()
+                for dst, src in zip((self.pos, self.vel, self.forces, self.energy, self.counter), state):
+                    dst.copy_(src)
+                self.pos32.copy_(self.pos.to(torch.float32))
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=side):
+                    self._step()
+                for dst, src in zip((self.pos, self.vel, self.forces, self.energy, self.counter), state):
+                    dst.copy_(src)  # the capture run itself must not advance the trajectory
+                self.pos32.copy_(self.pos.to(torch.float32))
+            torch.cuda.current_stream(self.eng.device).wait_stream(side)
+            self._graph_caps = caps
+        for _ in range(int(steps)):
+            if self.use_graph:
+                self.graph.replay()
+            else:
+                self._step()
+        torch.cuda.synchronize(self.eng.device)
+        st = self.eng.status()
+        if int(st.overflow_events) != self._events0:
+            raise RuntimeError("edge workspace overflowed during the on-device trajectory; "
+                               "reserve more edges (Engine.reserve) and restart from the last state")
+        return self.energies()
+
+    def energies(self) -> Dict[str, np.ndarray]:
+        k = min(int(self.counter.item()), self.capacity)
+        ser = self.series[:k].cpu().numpy()
+        total = ser[:, 0] + ser[:, 1]
+        return {"potential": ser[:, 0], "kinetic": ser[:, 1], "total": total,
+                "drift_percent": energy_drift_percent(total) if k > 1 else 0.0}
+
+    def state(self):
+        return self.pos.cpu().numpy(), self.vel.cpu().numpy()

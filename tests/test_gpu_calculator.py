@@ -143,3 +143,40 @@ def test_h2o_nve_1000_steps_drift_within_reference_bar(calc):
     v0 = md.maxwell_boltzmann(m, 300.0, np.random.default_rng(42), atoms.get_positions(), zero_rotation=True)
     out = md.velocity_verlet(ef, atoms.get_positions(), v0, m, steps=1000, dt_fs=0.5)
     assert abs(out["drift_percent"]) <= 0.14
+
+
+def test_device_md_matches_host_verlet(calc):
+    """On-device velocity Verlet (graph replay) against the host float64 integrator driving the
+    calculator: same initial state, same energy series."""
+    atoms = synthetic.benzene()
+    m = atoms.get_masses()
+    v0 = md.maxwell_boltzmann(m, 300.0, np.random.default_rng(7), atoms.get_positions(), zero_rotation=True)
+    work = atoms.copy()
+
+    def ef(pos):
+        work.set_positions(pos)
+        calc.calculate(work)
+        return calc.results["energy"], calc.results["forces"]
+
+    host = md.velocity_verlet(ef, atoms.get_positions(), v0, m, steps=200, dt_fs=0.5)
+    for use_graph in (False, True):
+        dev = md.DeviceMD(calc.model, atoms.numbers, atoms.get_positions(), v0, m, dt_fs=0.5, use_graph=use_graph)
+        out = dev.run(120)
+        out = dev.run(80)          # a second call continues the same trajectory
+        assert len(out["total"]) == 201
+        assert np.abs(out["total"] - host["total"]).max() < 2e-4
+        assert np.abs(out["potential"][:5] - host["potential"][:5]).max() < 5e-5
+        x, v = dev.state()
+        assert np.abs(x - host["positions"]).max() < 1e-4
+    assert abs(out["drift_percent"]) < 0.14
+
+
+def test_device_md_batch_of_independent_trajectories(calc):
+    structs = [synthetic.water(), synthetic.benzene(), synthetic.druglike(5, 30)]
+    z, pos, off = synthetic.concatenate(structs)
+    m = md.ATOMIC_MASSES[z]
+    v0 = md.maxwell_boltzmann(m, 300.0, np.random.default_rng(1))
+    dev = md.DeviceMD(calc.model, z, pos, v0, m, dt_fs=0.5, offsets=off)
+    out = dev.run(100)
+    assert len(out["total"]) == 101 and np.isfinite(out["total"]).all()
+    assert abs(out["drift_percent"]) < 0.5

@@ -22,11 +22,15 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--batch", type=int, default=1024)
     args = ap.parse_args()
+    ap.add_argument("--precision", default="tc")
+    args = ap.parse_args()
     model = StudentForceField.load(ROOT / "tests" / "golden" / f"weights_{args.variant}.npz", device="cuda:0",
-                                   pbc_mode="minimum_image")
+                                   pbc_mode="minimum_image", precision=args.precision)
     cells = pbc = None
     if args.workload == "c2":
         structs = synthetic.druglike_batch(args.batch)
+    elif args.workload == "c1":
+        structs = [synthetic.water()]
     elif args.workload == "c3":
         structs = [synthetic.alkane_chain(100)]
     else:
@@ -40,9 +44,18 @@ def main():
     st = model.engine().status()
     print(f"N={len(z)} E={st.num_edges} P={st.num_pairs} maxdeg={st.max_degree} E0={float(e[0]):.4f}")
     eng = model.engine()
+    eng.profile_enable(True)
     for _ in range(args.steps):
         eng.energy_forces_async(z_d, p_d, o_d, len(structs), e, f, cells, pbc)
     torch.cuda.synchronize()
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    tot = 0.0
+    for k, v in prof["stages"].items():
+        if v["launches"]:
+            print(f"  {k:12s} {1e3 * v['ms'] / args.steps:9.1f} us/step  ({v['launches'] // args.steps} launches)")
+            tot += 1e3 * v["ms"] / args.steps
+    print(f"  total        {tot:9.1f} us/step (device time between events)")
     print("done")
 
 

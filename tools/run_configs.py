@@ -60,6 +60,23 @@ def nve(calc, atoms, steps, temperature, seed, dt_fs=0.5):
             "max_abs_dE_total": float(np.abs(out["total"] - out["total"][0]).max())}
 
 
+def nve_device(calc, atoms, steps, temperature, seed, dt_fs=0.5, cell=None, pbc=None):
+    """Same trajectory with the integrator on the GPU (CUDA-graph replay, no per-step copies)."""
+    rng = np.random.default_rng(seed)
+    masses = atoms.get_masses()
+    v0 = md.maxwell_boltzmann(masses, temperature, rng, atoms.get_positions(), zero_rotation=True)
+    dev = md.DeviceMD(calc.model, atoms.numbers, atoms.get_positions(), v0, masses, dt_fs, cell=cell, pbc=pbc)
+    dev.run(20)  # graph capture + warm-up (these steps are part of the trajectory)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = dev.run(steps - 20)
+    dt = time.perf_counter() - t0
+    sps = (steps - 20) / dt
+    return {"steps": steps, "steps_per_s": sps, "us_per_step": 1e6 / sps, "ns_per_day": md.ns_per_day(sps, dt_fs),
+            "drift_percent": out["drift_percent"], "E_total_first": float(out["total"][0]),
+            "E_total_last": float(out["total"][-1])}
+
+
 def cpu_steps(variant, atoms, steps, cells=None, pbc=None):
     state, cfg = load_state(variant)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -89,6 +106,9 @@ def main():
     if want("c1"):
         calc = StudentForceFieldCalculator(W / "weights_original.npz", device="cuda:0", precision=args.precision)
         r = nve(calc, synthetic.water(), 200 if args.quick else 1000, 300.0, 42)
+        r["device_md"] = nve_device(calc, synthetic.water(), 200 if args.quick else 1000, 300.0, 42)
+        r["device_md_10ps"] = nve_device(calc, synthetic.water(), 2000 if args.quick else 20000, 300.0, 42)
+        r["benzene_device_md_10ps"] = nve_device(calc, synthetic.benzene(), 2000 if args.quick else 20000, 300.0, 42)
         r["cpu_reference"] = cpu_steps("original", synthetic.water(), 50 if args.quick else 200)
         report["C1_h2o_nve"] = r
         print("C1", json.dumps(r), flush=True)
@@ -98,6 +118,7 @@ def main():
         chain = synthetic.alkane_chain(100)
         chain.positions = chain.positions + np.random.default_rng(8).normal(0.0, 0.02, chain.positions.shape)
         r = nve(calc, chain, 2000 if args.quick else 20000, 300.0, 42)
+        r["device_md"] = nve_device(calc, chain, 2000 if args.quick else 20000, 300.0, 42)
         r["cpu_reference"] = cpu_steps("original", chain, 5 if args.quick else 30)
         report["C3_chain300_nve"] = r
         print("C3", json.dumps(r), flush=True)
@@ -128,6 +149,7 @@ def main():
              "ms_neighbor": stages.get("neighbor"), "ms_forward": fwd, "ms_reverse": rev, "stages_ms": stages,
              "steps_per_s": steps / dt, "ns_per_day": md.ns_per_day(steps / dt),
              "energy_eV": calc.results["energy"], "max_force": float(np.abs(calc.results["forces"]).max())}
+        r["device_md"] = nve_device(calc, box, 120 if args.quick else 520, 300.0, 42, cell=box.cell, pbc=box.pbc)
         if not args.quick:
             r["cpu_reference"] = cpu_steps("original", box, 1, box.cell[None], box.pbc[None])
         report["C4_water_box_10k"] = r
