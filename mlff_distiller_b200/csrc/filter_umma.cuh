@@ -106,9 +106,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
 }
 
+// Power-of-two pre-scaling keeps the low FP16 term out of the subnormal range (an unscaled term
+// below 6e-5 would be quantised to 2^-24 absolute): activations are split as 2^3 x, weights as
+// 2^8 w, and the epilogue multiplies the FP32 accumulator by 2^-11 (all exact).
+constexpr float kActScale = 8.0f;
+constexpr float kWeightScale = 256.0f;
+constexpr float kAccUnscale = 1.0f / (kActScale * kWeightScale);
+
 // fp16 two-term split of 8 consecutive channels, packed for one 16-byte swizzle chunk
-__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+__device__ __forceinline__ void split8(const float (&xin)[8], uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = xin[i] * kActScale;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const __half h0 = __float2half_rn(x[2 * i]), h1 = __float2half_rn(x[2 * i + 1]);
@@ -206,9 +216,12 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                 const uint64_t w_desc = w_desc0 + (uint64_t)(buf ? (kChunkImageBytes >> 4) : 0);
                 uint32_t acc = 0;
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {   // W_hi*act_hi, W_hi*act_lo, W_lo*act_hi
-                    const uint64_t act_base = (pass == 1) ? act_desc_lo : act_desc_hi;
-                    const uint64_t w_base = w_desc + (uint64_t)((pass == 2) ? ((2 * kKBlockBytes) >> 4) : 0);
+                // The tensor core accumulates with truncation, a bias that grows with the number of
+                // additions into a LARGE accumulator: the two small correction products go first
+                // (accumulator still ~2^-11 of its final size), the 8 main MMAs last.
+                for (int pass = 0; pass < 3; ++pass) {   // W_hi*act_lo, W_lo*act_hi, W_hi*act_hi
+                    const uint64_t act_base = (pass == 0) ? act_desc_lo : act_desc_hi;
+                    const uint64_t w_base = w_desc + (uint64_t)((pass == 1) ? ((2 * kKBlockBytes) >> 4) : 0);
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
@@ -318,7 +331,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                 float* o = out + nc * 128;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (row0 + j < P) __stcs(o + (size_t)j * (3 * H), __uint_as_float(r[j]) + b);
+                    if (row0 + j < P) __stcs(o + (size_t)j * (3 * H), fmaf(__uint_as_float(r[j]), kAccUnscale, b));
             }
             // all MMAs of tile `it` are complete (last chunk waited): the activation tile is free
             if (it + 1 < my_tiles) publish_tile();

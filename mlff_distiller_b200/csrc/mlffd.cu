@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "filter.cuh"
 #include "filter_umma.cuh"
+#include "umma_rows.cuh"
 #include "md.cuh"
 #include "message.cuh"
 #include "neighbor.cuh"
@@ -77,8 +78,9 @@ struct mlffd_ctx {
     int neighbor_mode = 0;   // 0 auto, 1 sweep, 2 cells (env MLFFD_NEIGHBOR)
     std::string err;
     float* weights_d = nullptr;
-    uint8_t* w2_images_d = nullptr;   // per layer 3 x 64 KB swizzled fp16 hi/lo images (tensor-core path)
+    uint8_t* w2_images_d = nullptr;   // swizzled fp16 hi/lo 64 KB weight images (tensor-core path)
     bool use_umma = false;
+    struct ImageOffsets { size_t filter, upd_f1, upd_f2, upd_b1, upd_b2; } img[kMaxLayers] = {};
     const float *emb = nullptr, *centers = nullptr, *gammas = nullptr;
     LayerWeights layer[kMaxLayers];
     HeadWeights head{};
@@ -209,7 +211,7 @@ int launch_filter(mlffd_ctx* ctx, int l, const float* dist, const int* num_pairs
             filter_table_umma_kernel<<<grid, kUmmaThreads, UmmaSmem::total(ctx->K), st>>>(
                 dist, num_pairs_ptr, num_pairs_arg, status, ctx->centers, ctx->gammas, ctx->K,
                 ctx->cfg.cutoff, ctx->layer[l].filter,
-                ctx->w2_images_d + (size_t)l * 3 * kChunkImageBytes,
+                ctx->w2_images_d + ctx->img[l].filter,
                 (l == 0 && status != nullptr) ? 1 : 0, filt, dfilt);
             LAUNCHED(ctx, "filter_table_umma_kernel", MLFFD_STAGE_FILTER, st);
             return MLFFD_OK;
@@ -255,7 +257,28 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
                 ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], ws.v_in[l], ws.s_msg[l],
                 ws.v_msg[l], N, status);
         LAUNCHED(ctx, "message_forward_kernel", MLFFD_STAGE_MESSAGE_FWD, st);
-        if (l == L - 1)
+        bool upd_done = false;
+        if constexpr (H == 128) {
+            if (ctx->use_umma) {
+                const UpdateWeights& uw = ctx->layer[l].update;
+                const int rows_grid = clamp_grid(ceil_div(N, 128), kNumSMs);
+                umma_rows_kernel<UpdateFwd1Op><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                    UpdateFwd1Op{ws.s_msg[l], ws.v_msg[l], uw.m1, ws.y1[l]}, N,
+                    ctx->w2_images_d + ctx->img[l].upd_f1, status);
+                LAUNCHED(ctx, "umma_rows_kernel<UpdateFwd1Op>", MLFFD_STAGE_UPDATE_FWD, st);
+                if (l == L - 1)
+                    umma_rows_kernel<UpdateFwd2Op<true>><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                        UpdateFwd2Op<true>{ws.y1[l], ws.s_msg[l], ws.v_msg[l], uw.m2, uw.U, ws.s_in[l + 1], nullptr, nullptr},
+                        N, ctx->w2_images_d + ctx->img[l].upd_f2, status);
+                else
+                    umma_rows_kernel<UpdateFwd2Op<false>><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                        UpdateFwd2Op<false>{ws.y1[l], ws.s_msg[l], ws.v_msg[l], uw.m2, uw.U, ws.s_in[l + 1], ws.v_in[l + 1], ws.gates[l]},
+                        N, ctx->w2_images_d + ctx->img[l].upd_f2, status);
+                upd_done = true;
+            }
+        }
+        if (upd_done) {
+        } else if (l == L - 1)
             update_forward_kernel<H, true><<<upd_fwd_grid, kGemmThreads, update_fwd_smem_bytes<H>(), st>>>(
                 ws.s_msg[l], ws.v_msg[l], ctx->layer[l].update, ws.s_in[l + 1], nullptr, ws.y1[l],
                 nullptr, N, status);
@@ -279,7 +302,29 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     for (int l = L - 1; l >= 0; --l) {
         float* sb = ws.sbar[adj(l)];
         float* vb = ws.vbar[adj(l)];
-        if (l == L - 1)
+        bool bwd_done = false;
+        if constexpr (H == 128) {
+            if (ctx->use_umma) {
+                const UpdateWeights& uw = ctx->layer[l].update;
+                const int rows_grid = clamp_grid(ceil_div(N, 128), kNumSMs);
+                if (l == L - 1) {
+                    umma_rows_kernel<UpdateBwd1Op<true>><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                        UpdateBwd1Op<true>{sb, vb, ws.v_msg[l], uw.U, ws.y1[l]}, N, ctx->w2_images_d + ctx->img[l].upd_b1, status);
+                    LAUNCHED(ctx, "umma_rows_kernel<UpdateBwd1Op>", MLFFD_STAGE_UPDATE_BWD, st);
+                    umma_rows_kernel<UpdateBwd2Op<true>><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                        UpdateBwd2Op<true>{ws.y1[l], ws.v_msg[l], nullptr, uw.U, sb, vb}, N, ctx->w2_images_d + ctx->img[l].upd_b2, status);
+                } else {
+                    umma_rows_kernel<UpdateBwd1Op<false>><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                        UpdateBwd1Op<false>{sb, vb, ws.v_msg[l], uw.U, ws.y1[l]}, N, ctx->w2_images_d + ctx->img[l].upd_b1, status);
+                    LAUNCHED(ctx, "umma_rows_kernel<UpdateBwd1Op>", MLFFD_STAGE_UPDATE_BWD, st);
+                    umma_rows_kernel<UpdateBwd2Op<false>><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                        UpdateBwd2Op<false>{ws.y1[l], ws.v_msg[l], ws.gates[l], uw.U, sb, vb}, N, ctx->w2_images_d + ctx->img[l].upd_b2, status);
+                }
+                bwd_done = true;
+            }
+        }
+        if (bwd_done) {
+        } else if (l == L - 1)
             update_backward_kernel<H, true><<<upd_bwd_grid, kGemmThreads, update_bwd_smem_bytes<H>(), st>>>(
                 ws.v_msg[l], ws.y1[l], nullptr, ctx->layer[l].update, sb, vb, N, status);
         else
@@ -490,25 +535,45 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     if (e != cudaSuccess) return bail(MLFFD_ENOMEM, cudaGetErrorString(e));
     cudaMemset(ctx->status_d, 0, sizeof(DeviceStatus));
     if (config->precision == MLFFD_PREC_TC_FP16X2 && H == 128) {
-        // K-major SWIZZLE_128B images of W2 (torch [out=3H][in=H] is already K-major): per layer,
-        // per 128-row chunk: [hi kb0 | hi kb1 | lo kb0 | lo kb1], each 128 rows x 64 halves.
-        std::vector<__half> img((size_t)L * 3 * kChunkImageBytes / 2);
+        // 64 KB K-major SWIZZLE_128B images of 128x128 blocks of an [out][in] matrix:
+        // [hi kb0 | hi kb1 | lo kb0 | lo kb1], each 128 rows x 64 halves (see filter_umma.cuh).
+        std::vector<__half> img;
+        auto add_image = [&](const float* Wm, int ld, int r0, int c0) {
+            const size_t base = img.size();
+            img.resize(base + kChunkImageBytes / 2);
+            for (int r = 0; r < 128; ++r)
+                for (int k = 0; k < 128; ++k) {
+                    const float x = Wm[(size_t)(r0 + r) * ld + c0 + k] * kWeightScale;
+                    const __half hi = __float2half_rn(x);
+                    const __half lo = __float2half_rn(x - __half2float(hi));
+                    const int kb = k / 64, kc = k % 64;
+                    const size_t off = (size_t)(r / 8) * 512 + (size_t)(r % 8) * 64 +
+                                       (size_t)(((kc / 8) ^ (r % 8)) * 8) + (size_t)(kc % 8);
+                    img[base + (size_t)kb * (kKBlockBytes / 2) + off] = hi;
+                    img[base + (size_t)(2 + kb) * (kKBlockBytes / 2) + off] = lo;
+                }
+            return base * sizeof(__half);
+        };
         const float* q = weights_host + (size_t)(config->max_z + 1) * H + 2 * K;
+        std::vector<float> M1T((size_t)2 * H * H), M2T((size_t)H * 3 * H);
         for (int l = 0; l < L; ++l) {
-            const float* W2 = q + (size_t)H * K + H;   // skip W1, b1
-            for (int c = 0; c < 3; ++c)
-                for (int r = 0; r < 128; ++r)
-                    for (int k = 0; k < H; ++k) {
-                        const float x = W2[(size_t)(c * 128 + r) * H + k];
-                        const __half hi = __float2half_rn(x);
-                        const __half lo = __float2half_rn(x - __half2float(hi));
-                        const int kb = k / 64, kc = k % 64;
-                        const size_t off = (size_t)(r / 8) * 512 + (size_t)(r % 8) * 64 +
-                                           (size_t)(((kc / 8) ^ (r % 8)) * 8) + (size_t)(kc % 8);
-                        const size_t base = ((size_t)l * 3 + c) * (kChunkImageBytes / 2);
-                        img[base + (size_t)kb * (kKBlockBytes / 2) + off] = hi;
-                        img[base + (size_t)(2 + kb) * (kKBlockBytes / 2) + off] = lo;
-                    }
+            const float* W2 = q + (size_t)H * K + H;                       // filter layer 2 [3H][H]
+            const float* M1 = W2 + (size_t)3 * H * H + 3 * H;              // update_mlp.0 [H][2H]
+            const float* M2 = M1 + (size_t)H * 2 * H + H;                  // update_mlp.2 [3H][H]
+            for (int r = 0; r < H; ++r)
+                for (int c = 0; c < 2 * H; ++c) M1T[(size_t)c * H + r] = M1[(size_t)r * 2 * H + c];
+            for (int r = 0; r < 3 * H; ++r)
+                for (int c = 0; c < H; ++c) M2T[(size_t)c * 3 * H + r] = M2[(size_t)r * H + c];
+            ctx->img[l].filter = add_image(W2, H, 0, 0);
+            add_image(W2, H, 128, 0); add_image(W2, H, 256, 0);
+            ctx->img[l].upd_f1 = add_image(M1, 2 * H, 0, 0);               // [ks][c]: W = M1 [H][2H]
+            add_image(M1, 2 * H, 0, 128);
+            ctx->img[l].upd_f2 = add_image(M2, H, 0, 0);                   // W = M2 [3H][H]
+            add_image(M2, H, 128, 0); add_image(M2, H, 256, 0);
+            ctx->img[l].upd_b1 = add_image(M2T.data(), 3 * H, 0, 0);       // W = M2^T [H][3H]
+            add_image(M2T.data(), 3 * H, 0, 128); add_image(M2T.data(), 3 * H, 0, 256);
+            ctx->img[l].upd_b2 = add_image(M1T.data(), H, 0, 0);           // W = M1^T [2H][H]
+            add_image(M1T.data(), H, 128, 0);
             q += per_layer;
         }
         e = cudaMalloc(&ctx->w2_images_d, img.size() * sizeof(__half));
@@ -518,6 +583,14 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
         e = cudaFuncSetAttribute(filter_table_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)UmmaSmem::total(K));
         if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
+#define SET_ROWS_ATTR(OP)                                                                            \
+        e = cudaFuncSetAttribute(umma_rows_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)UmmaRowsSmem::TOTAL);                                          \
+        if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
+        SET_ROWS_ATTR(UpdateFwd1Op) SET_ROWS_ATTR(UpdateFwd2Op<false>) SET_ROWS_ATTR(UpdateFwd2Op<true>)
+        SET_ROWS_ATTR(UpdateBwd1Op<false>) SET_ROWS_ATTR(UpdateBwd1Op<true>)
+        SET_ROWS_ATTR(UpdateBwd2Op<false>) SET_ROWS_ATTR(UpdateBwd2Op<true>)
+#undef SET_ROWS_ATTR
         ctx->use_umma = true;
     }
     const float* W = ctx->weights_d;

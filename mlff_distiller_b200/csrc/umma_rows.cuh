@@ -1,0 +1,371 @@
+// Generic "rows x dense layer" kernel on tcgen05 tensor cores (H = 128), used by the PaiNN update
+// block forward and reverse.  Same arithmetic contract as filter_umma.cuh: both operands are split
+// into two FP16 terms, three products (W_hi x_hi + W_hi x_lo + W_lo x_hi) accumulate in FP32 in
+// tensor memory -> FP32-equivalent results.
+//
+//   D[channel][row] = sum_k W[channel][k] * x[row][k]      (transposed product: a TMEM lane is an
+//                                                           output channel, a column is a row)
+// Rows come in tiles of 128 (atoms); K is walked in super-blocks of 128 (KS of them) and the
+// output in chunks of 128 channels (NC of them), all NC accumulators (<= 384 columns) stay in
+// TMEM across the K loop.  An `Op` supplies
+//   produce(row, ks, k0, x[16])   : 16 consecutive inputs of super-block ks for one row
+//   store(chunk, lane_ch, row0, r, prev) : epilogue for 32 rows x 1 channel per thread
+// so norms, SiLU, gates, the 3x3 spatial mixing and residuals are fused around the GEMM and the
+// only HBM traffic is the per-atom feature rows.
+//
+// Roles: 16 compute/epilogue warps + 1 issuer warp (bulk-copies the pre-swizzled 64 KB weight
+// images [ks][chunk] through a 2-deep ring and issues 24 MMAs per image).
+#pragma once
+#include "filter_umma.cuh"
+
+namespace mlffd {
+
+struct UmmaRowsSmem {
+    static constexpr uint32_t A_HI = 0;
+    static constexpr uint32_t A_LO = 32768;
+    static constexpr uint32_t B0 = 65536;
+    static constexpr uint32_t B1 = 131072;
+    static constexpr uint32_t BARS = 196608;   // a_full, act_free, b_full[2], b_free[2], d_full[3], tmem base
+    static constexpr uint32_t TOTAL = BARS + 128 + 1024 /*align*/;
+};
+
+template <class Op>
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
+                 const DeviceStatus* __restrict__ status) {
+    constexpr int KS = Op::KS, NC = Op::NC;
+    constexpr bool SPLIT = KS > 1;   // separate TMEM accumulator for the correction products
+    static_assert(!SPLIT || 2 * NC * 128 <= (int)kTmemCols, "not enough tensor memory columns");
+    if (status != nullptr && status->overflow) return;
+    const int num_tiles = (num_rows + 127) / 128;
+    if ((int)blockIdx.x >= num_tiles) return;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = (uint64_t*)(smem + UmmaRowsSmem::BARS);
+    uint64_t* bar_a_full = bars;
+    uint64_t* bar_act_free = bars + 1;
+    uint64_t* bar_b_full = bars + 2;
+    uint64_t* bar_b_free = bars + 4;
+    uint64_t* bar_d_full = bars + 6;
+    uint32_t* tmem_base_s = (uint32_t*)(bars + 9);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == kUmmaComputeWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (lane == 0) {
+            for (int i = 0; i < 9; ++i) mbar_init(bars + i, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == kUmmaComputeWarps) {
+        // =============================== issuer ===============================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t b_buf[2] = {smem_u32(smem + UmmaRowsSmem::B0), smem_u32(smem + UmmaRowsSmem::B1)};
+            const uint64_t act_desc_hi = umma_desc_sw128(smem_u32(smem + UmmaRowsSmem::A_HI));
+            const uint64_t act_desc_lo = umma_desc_sw128(smem_u32(smem + UmmaRowsSmem::A_LO));
+            const uint64_t w_desc0 = umma_desc_sw128(b_buf[0]);
+            constexpr int PER_TILE = KS * NC;
+            const int total = my_tiles * PER_TILE;
+            auto issue_load = [&](int g) {
+                const int buf = g & 1;
+                mbar_expect_tx(&bar_b_full[buf], kChunkImageBytes);
+                const uint8_t* src = images + (size_t)(g % PER_TILE) * kChunkImageBytes;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq)
+                    bulk_g2s(b_buf[buf] + qq * kKBlockBytes, src + qq * kKBlockBytes, kKBlockBytes, &bar_b_full[buf]);
+            };
+            issue_load(0);
+            if (total > 1) issue_load(1);
+            int g = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int pc = it * KS + ks;
+                    mbar_wait(bar_a_full, pc & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int c = 0; c < NC; ++c, ++g) {
+                        const int buf = g & 1;
+                        mbar_wait(&bar_b_full[buf], (g >> 1) & 1);
+                        const uint32_t d_main = tmem_base + (uint32_t)c * 128;
+                        // Truncating accumulation biases long sums into a large accumulator, so
+                        // the small correction products (W_hi x_lo, W_lo x_hi) are kept apart:
+                        // issued first when there is one K super-block, or accumulated in their
+                        // own TMEM columns (added in the epilogue) when K spans several.
+                        const uint32_t d_corr = SPLIT ? tmem_base + (uint32_t)(NC + c) * 128 : d_main;
+                        const uint64_t w_desc = w_desc0 + (uint64_t)(buf ? (kChunkImageBytes >> 4) : 0);
+                        uint32_t acc_corr = (ks > 0) ? 1u : 0u;
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass) {   // W_hi*x_lo, W_lo*x_hi
+                            const uint64_t act_base = (pass == 0) ? act_desc_lo : act_desc_hi;
+                            const uint64_t w_base = w_desc + (uint64_t)((pass == 1) ? ((2 * kKBlockBytes) >> 4) : 0);
+#pragma unroll
+                            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t off = (uint64_t)((kb * kKBlockBytes + k * 32) >> 4);
+                                    umma_f16(d_corr, w_base + off, act_base + off, idesc, acc_corr);
+                                    acc_corr = 1;
+                                }
+                        }
+                        uint32_t acc_main = SPLIT ? ((ks > 0) ? 1u : 0u) : 1u;
+#pragma unroll
+                        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {       // W_hi*x_hi
+                                const uint64_t off = (uint64_t)((kb * kKBlockBytes + k * 32) >> 4);
+                                umma_f16(d_main, w_desc + off, act_desc_hi + off, idesc, acc_main);
+                                acc_main = 1;
+                            }
+                        umma_commit(&bar_b_free[buf]);
+                        if (ks == KS - 1) umma_commit(&bar_d_full[c]);
+                        if (g >= 1 && g + 1 < total) {   // ring refill behind the previous image
+                            mbar_wait(&bar_b_free[(g - 1) & 1], ((g - 1) >> 1) & 1);
+                            issue_load(g + 1);
+                        }
+                    }
+                    umma_commit(bar_act_free);
+                }
+            }
+        }
+    } else {
+        // ========================= compute / epilogue =========================
+        const int row_in_tile = tid & 127, kgrp = tid >> 7;   // 32 K-values per thread
+        const int q = warp & 3, cs = warp >> 2;               // channel quarter (lanes), row segment
+        for (int it = 0; it < my_tiles; ++it) {
+            const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * 128;
+            for (int ks = 0; ks < KS; ++ks) {
+                const int pc = it * KS + ks;
+                float x[2][16];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) op.produce(row0 + row_in_tile, num_rows, ks, kgrp * 32 + half * 16, x[half]);
+                if (pc > 0) mbar_wait(bar_act_free, (pc - 1) & 1);   // previous MMAs finished reading the tile
+                const int kb = kgrp >> 1;
+                uint8_t* a_hi = smem + UmmaRowsSmem::A_HI + kb * kKBlockBytes;
+                uint8_t* a_lo = smem + UmmaRowsSmem::A_LO + kb * kKBlockBytes;
+#pragma unroll
+                for (int half = 0; half < 2; ++half)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float v8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v8[i] = x[half][8 * j + i];
+                        uint4 hi, lo;
+                        split8(v8, hi, lo);
+                        const uint32_t o = sw128_offset(row_in_tile, (kgrp & 1) * 4 + half * 2 + j);
+                        *reinterpret_cast<uint4*>(a_hi + o) = hi;
+                        *reinterpret_cast<uint4*>(a_lo + o) = lo;
+                    }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                if (tid == 0) mbar_arrive(bar_a_full);
+            }
+            // ---- epilogue: D[chunk][channel = lane][row = column] ----
+            uint32_t prev[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) prev[j] = 0u;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                mbar_wait(&bar_d_full[c], it & 1);
+                __syncwarp();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 128 + cs * 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if constexpr (SPLIT) {
+                    uint32_t rc[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((NC + c) * 128 + cs * 32), rc);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * kAccUnscale);
+                op.store(c, q * 32 + lane, row0 + cs * 32, num_rows, r, prev);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) prev[j] = r[j];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    if (warp == kUmmaComputeWarps) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// =================================== update block ops =========================================
+// Restating PaiNNUpdate.forward (reference src/mlff_distiller/models/student_model.py:434-470)
+// and its reverse, H = 128.  Weight "images" are [ks][chunk] 64 KB blocks of
+// the [out][in] matrix named at each op.
+
+__device__ __forceinline__ void load16(const float* p, float (&x)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 v = ldg4(p + 4 * i);
+        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void zero16(float (&x)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = 0.f;
+}
+
+// y1 = M1 [s'; |v'|] + m1          W = update_mlp.0.weight [H][2H]: KS = 2, NC = 1
+struct UpdateFwd1Op {
+    static constexpr int KS = 2, NC = 1;
+    const float* s_msg; const float* v_msg; const float* m1; float* y1;
+    __device__ __forceinline__ void produce(int row, int n, int ks, int k0, float (&x)[16]) const {
+        if (row >= n) { zero16(x); return; }
+        if (ks == 0) { load16(s_msg + (size_t)row * 128 + k0, x); return; }
+        float vx[16], vy[16], vz[16];
+        const float* vp = v_msg + (size_t)row * 384 + k0;
+        load16(vp, vx); load16(vp + 128, vy); load16(vp + 256, vz);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = sqrtf(vx[i] * vx[i] + vy[i] * vy[i] + vz[i] * vz[i]);
+    }
+    __device__ __forceinline__ void store(int, int ch, int row0, int n, const uint32_t (&r)[32], const uint32_t (&)[32]) const {
+        const float b = __ldg(m1 + ch);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (row0 + j < n) y1[(size_t)(row0 + j) * 128 + ch] = __uint_as_float(r[j]) + b;
+    }
+};
+
+// (ds | g1 | g2) = M2 SiLU(y1) + m2 ; s'' = s' + ds ; v'' = v' g1 + (U v') g2
+//                                   W = update_mlp.2.weight [3H][H]: KS = 1, NC = 3 (1 when LAST)
+template <bool LAST>
+struct UpdateFwd2Op {
+    static constexpr int KS = 1, NC = LAST ? 1 : 3;
+    const float* y1; const float* s_msg; const float* v_msg; const float* m2; const float* U;
+    float* s_out; float* v_out; float* gates;
+    __device__ __forceinline__ void produce(int row, int n, int, int k0, float (&x)[16]) const {
+        if (row >= n) { zero16(x); return; }
+        load16(y1 + (size_t)row * 128 + k0, x);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = siluf_(x[i]);
+    }
+    __device__ __forceinline__ void store(int c, int ch, int row0, int n, const uint32_t (&r)[32], const uint32_t (&prev)[32]) const {
+        if (c == 0) {
+            const float b = __ldg(m2 + ch);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (row0 + j < n) {
+                    const size_t o = (size_t)(row0 + j) * 128 + ch;
+                    s_out[o] = __ldg(s_msg + o) + __uint_as_float(r[j]) + b;
+                }
+        } else if (c == 2) {   // prev = g1 accumulators (chunk 1), r = g2
+            const float b1 = __ldg(m2 + 128 + ch), b2 = __ldg(m2 + 256 + ch);
+            float u[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) u[k] = __ldg(U + k);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (row0 + j < n) {
+                    const size_t row = (size_t)(row0 + j);
+                    const float g1 = __uint_as_float(prev[j]) + b1, g2 = __uint_as_float(r[j]) + b2;
+                    const float* vp = v_msg + row * 384 + ch;
+                    const float vx = __ldg(vp), vy = __ldg(vp + 128), vz = __ldg(vp + 256);
+                    gates[row * 256 + ch] = g1;
+                    gates[row * 256 + 128 + ch] = g2;
+                    float* vo = v_out + row * 384 + ch;
+                    vo[0] = vx * g1 + (u[0] * vx + u[1] * vy + u[2] * vz) * g2;
+                    vo[128] = vy * g1 + (u[3] * vx + u[4] * vy + u[5] * vz) * g2;
+                    vo[256] = vz * g1 + (u[6] * vx + u[7] * vy + u[8] * vz) * g2;
+                }
+        }
+    }
+};
+
+// hid_bar = M2^T [s_bar; g1_bar; g2_bar] ; y1_bar = hid_bar * SiLU'(y1)   (written over y1)
+//                                   W = M2^T [H][3H]: KS = 3 (1 when LAST: g_bar = 0), NC = 1
+template <bool LAST>
+struct UpdateBwd1Op {
+    static constexpr int KS = LAST ? 1 : 3, NC = 1;
+    const float* sbar; const float* vbar; const float* v_msg; const float* U; float* y1;
+    __device__ __forceinline__ void produce(int row, int n, int ks, int k0, float (&x)[16]) const {
+        if (row >= n) { zero16(x); return; }
+        if (ks == 0) { load16(sbar + (size_t)row * 128 + k0, x); return; }
+        float vx[16], vy[16], vz[16], bx[16], by[16], bz[16];
+        const float* vp = v_msg + (size_t)row * 384 + k0;
+        const float* bp = vbar + (size_t)row * 384 + k0;
+        load16(vp, vx); load16(vp + 128, vy); load16(vp + 256, vz);
+        load16(bp, bx); load16(bp + 128, by); load16(bp + 256, bz);
+        if (ks == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = bx[i] * vx[i] + by[i] * vy[i] + bz[i] * vz[i];
+        } else {
+            float u[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) u[k] = __ldg(U + k);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                x[i] = bx[i] * (u[0] * vx[i] + u[1] * vy[i] + u[2] * vz[i]) +
+                       by[i] * (u[3] * vx[i] + u[4] * vy[i] + u[5] * vz[i]) +
+                       bz[i] * (u[6] * vx[i] + u[7] * vy[i] + u[8] * vz[i]);
+        }
+    }
+    __device__ __forceinline__ void store(int, int ch, int row0, int n, const uint32_t (&r)[32], const uint32_t (&)[32]) const {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (row0 + j < n) {
+                const size_t o = (size_t)(row0 + j) * 128 + ch;
+                y1[o] = __uint_as_float(r[j]) * silu_gradf_(y1[o]);
+            }
+    }
+};
+
+// [ps_bar | n_bar] = M1^T y1_bar ; s_bar += ps_bar ;
+// v_bar <- v_bar g1 + U^T (v_bar g2) + n_bar v'/|v'|      W = M1^T [2H][H]: KS = 1, NC = 2
+template <bool LAST>
+struct UpdateBwd2Op {
+    static constexpr int KS = 1, NC = 2;
+    const float* ybar; const float* v_msg; const float* gates; const float* U; float* sbar; float* vbar;
+    __device__ __forceinline__ void produce(int row, int n, int, int k0, float (&x)[16]) const {
+        if (row >= n) { zero16(x); return; }
+        load16(ybar + (size_t)row * 128 + k0, x);
+    }
+    __device__ __forceinline__ void store(int c, int ch, int row0, int n, const uint32_t (&r)[32], const uint32_t (&)[32]) const {
+        if (c == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (row0 + j < n) sbar[(size_t)(row0 + j) * 128 + ch] += __uint_as_float(r[j]);
+            return;
+        }
+        float u[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) u[k] = __ldg(U + k);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (row0 + j < n) {
+                const size_t row = (size_t)(row0 + j);
+                const float* vp = v_msg + row * 384 + ch;
+                float* bp = vbar + row * 384 + ch;
+                const float vx = __ldg(vp), vy = __ldg(vp + 128), vz = __ldg(vp + 256);
+                const float nrm = sqrtf(vx * vx + vy * vy + vz * vz);
+                const float sc = (nrm > 0.f) ? __uint_as_float(r[j]) / nrm : 0.f;
+                float ox = sc * vx, oy = sc * vy, oz = sc * vz;
+                if (!LAST) {
+                    const float g1 = __ldg(gates + row * 256 + ch), g2 = __ldg(gates + row * 256 + 128 + ch);
+                    const float bx = bp[0], by = bp[128], bz = bp[256];
+                    const float gx = bx * g2, gy = by * g2, gz = bz * g2;
+                    ox += bx * g1 + (u[0] * gx + u[3] * gy + u[6] * gz);
+                    oy += by * g1 + (u[1] * gx + u[4] * gy + u[7] * gz);
+                    oz += bz * g1 + (u[2] * gx + u[5] * gy + u[8] * gz);
+                }
+                bp[0] = ox; bp[128] = oy; bp[256] = oz;
+            }
+    }
+};
+
+}  // namespace mlffd

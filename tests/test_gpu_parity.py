@@ -113,9 +113,17 @@ def _oracle_stages(state, cfg, z, pos, off):
 
 
 def test_stage_intermediates_and_adjoints(variant):
+    _stage_check(variant, "fp32")
+
+
+def test_stage_intermediates_and_adjoints_tensor_core():
+    _stage_check("original", "tc")
+
+
+def _stage_check(variant, precision):
     os.environ["MLFFD_DEBUG_KEEP"] = "1"
     try:
-        model, state, cfg = _model(variant)
+        model, state, cfg = _model(variant, precision=precision)
         gold = load_golden(variant)
         case = "ragged"
         z, pos, off = gold[f"{case}_numbers"], gold[f"{case}_positions"], gold[f"{case}_offsets"]
@@ -147,7 +155,8 @@ def test_stage_intermediates_and_adjoints(variant):
             check(f"filter{l}", filt, ref, 2e-5)
             check(f"s_msg{l}", eng.debug_buffer("s_msg", l), keep[f"s_msg{l}"].detach(), 2e-5)
             check(f"v_msg{l}", eng.debug_buffer("v_msg", l), keep[f"v_msg{l}"].detach(), 2e-5)
-            check(f"y1_{l}", eng.debug_buffer("y1", l), keep[f"y1_{l}"].detach(), 2e-5)
+            if precision == "fp32":  # the tensor-core reverse pass reuses y1 for its adjoint
+                check(f"y1_{l}", eng.debug_buffer("y1", l), keep[f"y1_{l}"].detach(), 2e-5)
             if l < L - 1:
                 g = eng.debug_buffer("gates", l).reshape(-1, 2 * H)
                 check(f"g1_{l}", g[:, :H], keep[f"g1_{l}"].detach(), 2e-5)
@@ -165,7 +174,7 @@ def test_stage_intermediates_and_adjoints(variant):
         # oracle directly; forces cover it.
         check("forces", torch.from_numpy(f), f64, 2e-5)
         OUT.mkdir(exist_ok=True)
-        (OUT / f"stages_{variant}.json").write_text(json.dumps(report, indent=1))
+        (OUT / f"stages_{variant}_{precision}.json").write_text(json.dumps(report, indent=1))
         bad = {k: v for k, v in report.items() if not v["ok"]}
         assert not bad, bad
     finally:
