@@ -38,7 +38,7 @@ REFERENCE_CHUNK = 32     # structures per reference call: un-chunked needs a 31 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--variant", choices=sorted(VARIANT_FILES), default="original")
@@ -92,10 +92,13 @@ def algorithmic_work(N, E, P, H, K, L):
     for l in range(L):
         nf = (2 if l == 0 else 3) * H * 4
         gather = (1 if l == 0 else 4) * H * 4
-        mf_b += E * (nf + gather + 24) + N * (4 * H * 4 + gather)
+        # compulsory HBM bytes: every filter-table row once per PAIR (both directed edges share it),
+        # per-edge indices/geometry, per-atom feature rows in and out once; the edge-granular
+        # gathers of neighbour rows (E * `gather` bytes) are L2 traffic and not counted here
+        mf_b += P * nf + E * 24 + N * (4 * H * 4 + gather)
         mf_f += E * 2 * H * (1 + (0 if l == 0 else 3) + 3)
-        mb_b += E * (2 * nf + H * 4 + (0 if l == 0 else 7 * H * 4) + 24 + 16 + (0 if l == L - 1 else 16)) \
-            + N * (4 * H * 4 + (0 if l == 0 else 4 * H * 4))
+        mb_b += P * 2 * nf + E * (24 + 16 + (0 if l == L - 1 else 16)) \
+            + N * (gather + 4 * H * 4 + (0 if l == 0 else 4 * H * 4))
         mb_f += E * 2 * H * (2 + 6 + 3 + (0 if l == 0 else 3 + 2 + 4))
     w["message_fwd"] = {"flops": mf_f, "bytes": mf_b}
     w["message_bwd"] = {"flops": mb_f, "bytes": mb_b}
@@ -136,7 +139,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -314,8 +317,8 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t.item())
-    h2d = 4 * N + 12 * N + 4 * (B + 1)
-    d2h = 4 * B + 12 * N
+    h2d = world * (4 * N + 12 * N + 4 * (B + 1))   # numbers i32 + positions f32 + offsets i32, all ranks
+    d2h = world * (4 * B + 12 * N)                 # energies f32 + forces f32, all ranks
 
     if rank != 0:
         if world > 1:
@@ -341,16 +344,21 @@ def run_b200(args):
         achieved, peak, unit, bound = stages[top]["TFLOPs"], peaks["bf16_tflops"], "TFLOP/s", "tensor"
     else:
         achieved, peak, unit, bound = stages[top]["GBps"], peaks["hbm_gbs"], "GB/s", "hbm"
+    traffic = None   # dram bytes per launch of the same kernel from the committed ncu --set full capture
+    tfile = ROOT / "profiles" / "ncu_traffic.json"
+    if tfile.exists():
+        traffic = json.loads(tfile.read_text()).get(args.precision, {}).get(top)
     roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak if achieved else None, "traffic": None,
+                "frac": achieved / peak if achieved else None, "traffic": traffic,
                 "peak_source": peaks["source"],
                 "share_of_step": stages[top]["ms_per_step"] / (elapsed_ms / args.steps)}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, world),
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "f32 (dense layers: 2-term f16 split products on tcgen05, f32 accumulate)",
+        "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": prof["launches"], "clocks": clocks, "roofline": roofline,
         "stages": stages, "graph": {"atoms": N, "edges": E, "pairs": P},
