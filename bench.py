@@ -273,7 +273,7 @@ def run_b200(args):
     forces_d = torch.empty((N, 3), dtype=torch.float32, device=dev)
 
     # sizing call (grows the edge workspace if the first guess overflows)
-    model.energy_and_forces_packed(z_d, pos_d[0], off_d, B)
+    model.energy_and_forces_packed(z_d, pos_d[0], off_d, B, max_atoms=int(counts.max()))
     st = eng.status()
     E, P = int(st.num_edges), int(st.num_pairs)
 

@@ -65,6 +65,9 @@ typedef struct mlffd_status {
     int32_t max_degree;
     int64_t overflow_events; /* sticky count of overflowed builds since mlffd_model_create (lets a
                                 caller that enqueues many steps, e.g. on-device MD, detect one) */
+    int32_t hint_violation;  /* 1: a structure was larger than mlffd_set_structure_hint promised;
+                                outputs invalid -> clear the hint (0) and call again */
+    int32_t reserved;
 } mlffd_status;
 
 typedef struct mlffd_ctx mlffd_ctx;
@@ -132,6 +135,16 @@ int mlffd_energy_forces(mlffd_ctx* ctx, const int32_t* z_d, const float* pos_d,
                         float* forces_d, void* stream);
 
 int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out);
+
+/*
+ * Optional promise that no structure of the coming calls has more than this many atoms (0 =
+ * unknown, the default).  With small structures (<= 113 atoms at H = 128) the message kernels
+ * switch to a structure-per-block variant that stages the structure's feature rows in shared
+ * memory (results are bit-identical).  The batched-structure interface of the reference
+ * (inference/ase_calculator.py:647-706) knows the atom counts on the host, so the calculator
+ * passes max(counts).  A violated promise is detected on the device (mlffd_status.hint_violation).
+ */
+int mlffd_set_structure_hint(mlffd_ctx* ctx, int32_t max_atoms_per_structure);
 
 /*
  * Stage entry point (parity tests, ncu): evaluate the per-layer radial filter and its

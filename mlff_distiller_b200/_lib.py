@@ -17,7 +17,7 @@ from typing import List, Optional
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libmlffd.so"
 SOURCES = ["mlffd.cu"]
-HEADERS = ["common.cuh", "neighbor.cuh", "cell_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh",
+HEADERS = ["common.cuh", "neighbor.cuh", "cell_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh", "message_staged.cuh",
            "update.cuh", "readout.cuh", "md.cuh", "../../include/mlffd.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -28,7 +28,7 @@ EXPORTS = [
     "mlffd_workspace_reserve", "mlffd_neighbor_list", "mlffd_export_edges",
     "mlffd_energy_forces", "mlffd_get_status", "mlffd_filter_table", "mlffd_debug_buffer",
     "mlffd_profile_enable", "mlffd_profile_read", "mlffd_stage_name",
-    "mlffd_md_kick_drift", "mlffd_md_kick_energy",
+    "mlffd_md_kick_drift", "mlffd_md_kick_energy", "mlffd_set_structure_hint",
 ]
 NUM_STAGES = 10
 
@@ -46,7 +46,8 @@ class MlffdStatus(ctypes.Structure):
     _fields_ = [("num_atoms", ctypes.c_int64), ("num_edges", ctypes.c_int64),
                 ("num_pairs", ctypes.c_int64), ("edge_capacity", ctypes.c_int64),
                 ("overflow", ctypes.c_int32), ("max_degree", ctypes.c_int32),
-                ("overflow_events", ctypes.c_int64)]
+                ("overflow_events", ctypes.c_int64), ("hint_violation", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
 
 
 class MlffdProfile(ctypes.Structure):
@@ -135,6 +136,8 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     lib.mlffd_profile_read.argtypes = [vp, ctypes.POINTER(MlffdProfile)]
     lib.mlffd_stage_name.restype = ctypes.c_char_p
     lib.mlffd_stage_name.argtypes = [i32]
+    lib.mlffd_set_structure_hint.restype = ctypes.c_int
+    lib.mlffd_set_structure_hint.argtypes = [vp, i32]
     f64 = ctypes.c_double
     lib.mlffd_md_kick_drift.restype = ctypes.c_int
     lib.mlffd_md_kick_drift.argtypes = [i64, vp, vp, vp, vp, f64, vp, vp]

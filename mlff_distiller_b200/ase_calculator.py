@@ -287,7 +287,8 @@ class StudentForceFieldCalculator(_AseCalculator):
             cells_d, pbc_d = StudentForceField.pack_cells(torch.from_numpy(np.asarray(cells)),
                                                           torch.from_numpy(np.asarray(pbcs)), nb, dev)
         try:
-            e_d, f_d = self.model.energy_and_forces_packed(z_d, pos_d, off_d, nb, cells_d, pbc_d)
+            e_d, f_d = self.model.energy_and_forces_packed(z_d, pos_d, off_d, nb, cells_d, pbc_d,
+                                                           max_atoms=int(counts.max()))
             st["e_h"][:nb].copy_(e_d, non_blocking=True)
             st["f_h"][:n].copy_(f_d, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()

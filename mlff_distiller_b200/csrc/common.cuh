@@ -18,7 +18,7 @@ struct DeviceStatus {
     int overflow;
     int max_degree;
     int overflow_events;   // sticky: number of neighbour builds that overflowed since creation
-    int reserved_;
+    int hint_violation;    // a structure exceeded mlffd_set_structure_hint: staged kernels skipped it
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -47,7 +47,7 @@ struct UmmaSmem {
     static constexpr uint32_t PHI = 196608;                                   // [64][33] f32
     static constexpr uint32_t DPHI = PHI + kUmmaPairs * kPhiStride * 4;       // [64][33] f32
     static constexpr uint32_t W1T = DPHI + kUmmaPairs * kPhiStride * 4;       // [K][128] f32
-    static constexpr uint32_t total(int K) { return W1T + (uint32_t)K * 128 * 4 + 512 /*b1*/ + 64 /*mbarriers, tmem base*/ + 1024 /*align*/; }
+    static constexpr uint32_t total(int K) { return W1T + (uint32_t)K * 128 * 4 + 512 /*b1*/ + 64 /*mbarriers, tmem base*/ + 512 /*cutoff per pair*/ + 1024 /*align*/; }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -162,6 +162,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
     uint64_t* bar_b_full = bars + 1;
     uint64_t* bar_d_full = bars + 3;
     uint32_t* tmem_base_s = (uint32_t*)(bars + 6);
+    float2* cut_s = (float2*)(bars + 8);             // [64] cutoff value and derivative per pair
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunks = skip_vector_gate ? 2 : 3;
@@ -255,13 +256,30 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
 
         auto first_layer = [&](int it) {
             const int p0 = ((int)blockIdx.x + it * (int)gridDim.x) * kUmmaPairs;
+            // cutoff value/derivative once per pair (not per basis function): lanes with the same
+            // pair recompute it at most ceil(K / (threads per pair)) times instead of K times
             for (int idx = tid; idx < kUmmaPairs * K; idx += kUmmaComputeThreads) {
                 const int pp = idx / K, k = idx - pp * K;
                 const float d = (p0 + pp < P) ? __ldg(pair_dist + p0 + pp) : rc;
-                float v, dv;
-                rbf_cutoff(d, __ldg(centers + k), __ldg(gammas + k), rc, v, dv);
-                phi_s[pp * kPhiStride + k] = v;
-                dphi_s[pp * kPhiStride + k] = dv;
+                if (k == 0) {
+                    const float kPi = 3.14159274101257324f;
+                    const float arg = (kPi * d) / rc;
+                    const bool inside = d < rc;
+                    cut_s[pp] = make_float2(inside ? 0.5f * (cosf(arg) + 1.0f) : 0.0f,
+                                            inside ? -0.5f * (kPi / rc) * sinf(arg) : 0.0f);
+                }
+                const float diff = d - __ldg(centers + k), gamma = __ldg(gammas + k);
+                const float phi = expf(-gamma * (diff * diff));
+                phi_s[pp * kPhiStride + k] = phi;                            // plain Gaussian for now
+                dphi_s[pp * kPhiStride + k] = -2.0f * gamma * diff * phi;
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            for (int idx = tid; idx < kUmmaPairs * K; idx += kUmmaComputeThreads) {
+                const int pp = idx / K, k = idx - pp * K;
+                const float2 c = cut_s[pp];
+                const float phi = phi_s[pp * kPhiStride + k], dphi = dphi_s[pp * kPhiStride + k];
+                phi_s[pp * kPhiStride + k] = phi * c.x;                      // same products as rbf_cutoff
+                dphi_s[pp * kPhiStride + k] = dphi * c.x + phi * c.y;
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
 #pragma unroll

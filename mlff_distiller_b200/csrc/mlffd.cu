@@ -23,6 +23,7 @@
 #include "umma_rows.cuh"
 #include "md.cuh"
 #include "message.cuh"
+#include "message_staged.cuh"
 #include "neighbor.cuh"
 #include "readout.cuh"
 #include "update.cuh"
@@ -76,6 +77,8 @@ struct mlffd_ctx {
     int H = 0, K = 0, L = 0;
     bool debug_keep = false;
     int neighbor_mode = 0;   // 0 auto, 1 sweep, 2 cells (env MLFFD_NEIGHBOR)
+    int struct_hint = 0;     // max atoms per structure promised by the caller (0 = unknown)
+    bool enable_staging = false;     // env MLFFD_STAGING=1
     std::string err;
     float* weights_d = nullptr;
     uint8_t* w2_images_d = nullptr;   // swizzled fp16 hi/lo 64 KB weight images (tensor-core path)
@@ -197,6 +200,14 @@ int set_kernel_attributes(mlffd_ctx* ctx) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(update_backward_kernel<H, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)update_bwd_smem_bytes<H>()));
+    constexpr int kMaxSmem = 227 * 1024;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(message_forward_staged_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(message_forward_staged_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(message_backward_edges_staged_kernel<H, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(message_backward_edges_staged_kernel<H, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(message_backward_edges_staged_kernel<H, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(message_backward_edges_staged_kernel<H, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(message_backward_atoms_staged_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     return MLFFD_OK;
 }
 
@@ -239,6 +250,15 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     const int upd_fwd_grid = clamp_grid(tiles, kNumSMs * (update_fwd_smem_bytes<H>() <= 110 * 1024 ? 2 : 1));
     const int upd_bwd_grid = clamp_grid(tiles, kNumSMs * (update_bwd_smem_bytes<H>() <= 110 * 1024 ? 2 : 1));
     const int warp_grid = clamp_grid(ceil_div(N, 8), kNumSMs * 8);
+    // structure-blocked kernels with smem-staged features when the caller promised small structures
+    const int hint = ctx->struct_hint;
+    const size_t staged_smem = staged_smem_bytes<H>(hint);
+    // Measured on C2 (B200): the staged variant is SLOWER than the generic kernels (message fwd
+    // 1.00 vs 0.77 ms, reverse 2.11 vs 1.98 ms per step) -- the neighbour gathers already hit
+    // L1/L2 and the kernels are bound by streaming the filter-table rows -- so it is opt-in
+    // (MLFFD_STAGING=1) and kept for bit-identity tests and for future tuning.
+    const bool staged = ctx->enable_staging && hint > 0 && staged_smem <= 227 * 1024;
+    const int staged_grid = staged ? clamp_grid(n_structs, kNumSMs * (int)std::min<size_t>(8, (227 * 1024) / staged_smem)) : 1;
 
     embedding_kernel<H><<<clamp_grid(ceil_div((int64_t)N * (H / 4), 256), kNumSMs * 8), 256, 0, st>>>(
         z, ctx->emb, ctx->cfg.max_z, ws.s_in[0], N);
@@ -248,7 +268,15 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
         int rc = launch_filter<H>(ctx, l, ws.pair_dist, &ctx->status_d->num_pairs, 0, status,
                                   ws.filt[l], ws.dfilt[l], ws.cap_pairs, st);
         if (rc) return rc;
-        if (l == 0)
+        if (staged && l == 0)
+            message_forward_staged_kernel<H, true><<<staged_grid, kStagedThreads, staged_smem, st>>>(
+                offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], nullptr,
+                ws.s_msg[l], ws.v_msg[l], ctx->status_d);
+        else if (staged)
+            message_forward_staged_kernel<H, false><<<staged_grid, kStagedThreads, staged_smem, st>>>(
+                offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], ws.v_in[l],
+                ws.s_msg[l], ws.v_msg[l], ctx->status_d);
+        else if (l == 0)
             message_forward_kernel<H, true><<<msg_grid, 256, 0, st>>>(
                 ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], nullptr, ws.s_msg[l],
                 ws.v_msg[l], N, status);
@@ -338,8 +366,22 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     message_backward_kernel<H, LAYER0, ACC><<<msg_grid, 256, 0, st>>>(                           \
         ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.dfilt[l], ws.s_in[l], ws.v_in[l], sb, \
         vb, sb_in, vb_in, ws.edge_adj, N, status)
-        if (l == 0) { if (first) MSG_BWD(true, false); else MSG_BWD(true, true); }
+#define MSG_BWD_EDGES(LAYER0, ACC)                                                                         \
+    message_backward_edges_staged_kernel<H, LAYER0, ACC><<<staged_grid, kStagedThreads, staged_smem, st>>>(             \
+        offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.dfilt[l], ws.s_in[l],   \
+        ws.v_in[l], sb, vb, ws.edge_adj, ctx->status_d)
+        if (staged) {
+            if (l == 0) { if (first) MSG_BWD_EDGES(true, false); else MSG_BWD_EDGES(true, true); }
+            else        { if (first) MSG_BWD_EDGES(false, false); else MSG_BWD_EDGES(false, true); }
+            if (l > 0) {
+                LAUNCHED(ctx, "message_backward_edges_staged_kernel", MLFFD_STAGE_MESSAGE_BWD, st);
+                message_backward_atoms_staged_kernel<H><<<staged_grid, kStagedThreads, staged_smem, st>>>(
+                    offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.filt[l], sb, vb, sb_in, vb_in,
+                    ctx->status_d);
+            }
+        } else if (l == 0) { if (first) MSG_BWD(true, false); else MSG_BWD(true, true); }
         else        { if (first) MSG_BWD(false, false); else MSG_BWD(false, true); }
+#undef MSG_BWD_EDGES
 #undef MSG_BWD
         LAUNCHED(ctx, "message_backward_kernel", MLFFD_STAGE_MESSAGE_BWD, st);
     }
@@ -477,6 +519,7 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     ctx->H = H; ctx->K = K; ctx->L = L;
     const char* dbg = std::getenv("MLFFD_DEBUG_KEEP");
     ctx->debug_keep = dbg && dbg[0] == '1';
+    if (const char* ns = std::getenv("MLFFD_STAGING")) ctx->enable_staging = ns[0] == '1';
     if (const char* nm = std::getenv("MLFFD_NEIGHBOR"))
         ctx->neighbor_mode = (std::strcmp(nm, "sweep") == 0) ? 1 : (std::strcmp(nm, "cells") == 0) ? 2 : 0;
 
@@ -790,6 +833,8 @@ extern "C" int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out) {
     out->overflow = h.overflow;
     out->max_degree = h.max_degree;
     out->overflow_events = h.overflow_events;
+    out->hint_violation = h.hint_violation;
+    out->reserved = 0;
     return MLFFD_OK;
 }
 
@@ -904,4 +949,10 @@ extern "C" int mlffd_md_kick_energy(int64_t num_atoms, double* vel_d, const floa
     md_energy_kernel<<<1, 1024, 0, st>>>(n3, vel_d, inv_mass_d, energy_d, num_structures, series_d,
                                          counter_d, capacity);
     return cudaGetLastError() == cudaSuccess ? MLFFD_OK : MLFFD_ECUDA;
+}
+
+extern "C" int mlffd_set_structure_hint(mlffd_ctx* ctx, int32_t max_atoms_per_structure) {
+    if (!ctx || max_atoms_per_structure < 0) return MLFFD_EINVAL;
+    ctx->struct_hint = max_atoms_per_structure;
+    return MLFFD_OK;
 }

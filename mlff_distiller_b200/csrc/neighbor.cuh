@@ -104,6 +104,7 @@ __global__ void neighbor_finalize_kernel(const int* __restrict__ rowptr,
         status->overflow = (e > edge_capacity) ? 1 : 0;
         if (e > edge_capacity) status->overflow_events += 1;
         status->max_degree = 0;
+        status->hint_violation = 0;
     }
 }
 

@@ -111,6 +111,12 @@ class Engine:
             self._ctx, _ptr(pos), _ptr(offsets), int(n_structs), int(pos.shape[0]), _ptr(cells),
             _ptr(pbc), self._stream()))
 
+    def set_structure_hint(self, max_atoms_per_structure: int):
+        """Promise an upper bound on atoms per structure (0 = unknown) -> smem-staged kernels."""
+        if int(max_atoms_per_structure) != getattr(self, "_hint", 0):
+            self._check(self.lib.mlffd_set_structure_hint(self._ctx, int(max_atoms_per_structure)))
+            self._hint = int(max_atoms_per_structure)
+
     def status(self) -> _lib.MlffdStatus:
         """Synchronises the last call's stream and returns its counters."""
         s = _lib.MlffdStatus()

@@ -200,16 +200,22 @@ class StudentForceField(nn.Module):
             self._engine_key = key
         return self._engine
 
-    def _run(self, z, pos, offsets, nb, cells, pbc, want_forces: bool):
-        """One evaluation through the C ABI; retries once with a larger edge workspace."""
+    def _run(self, z, pos, offsets, nb, cells, pbc, want_forces: bool, max_atoms: int = 0):
+        """One evaluation through the C ABI; retries once with a larger edge workspace.
+        ``max_atoms`` (host-known largest structure, 0 = unknown) enables the smem-staged kernels."""
         eng = self.engine()
         n = pos.shape[0]
+        # structure-per-block kernels pay off only when there are enough structures to fill the GPU
+        eng.set_structure_hint(max_atoms if nb >= 32 else 0)
         energy = torch.empty(nb, dtype=torch.float32, device=pos.device)
         forces = torch.empty((n, 3), dtype=torch.float32, device=pos.device) if want_forces else None
         eng.ensure(n, nb, self._edges_per_atom)
         for _ in range(3):
             eng.energy_forces_async(z, pos, offsets, nb, energy, forces, cells, pbc)
             st = eng.status()
+            if st.hint_violation:   # the promise was wrong: fall back to the generic kernels
+                eng.set_structure_hint(0)
+                continue
             if not st.overflow:
                 return energy, forces
             eng.reserve(n, int(st.num_edges * 1.25) + 64, nb)
@@ -283,10 +289,11 @@ class StudentForceField(nn.Module):
     def energy_and_forces_packed(self, z_i32: torch.Tensor, pos_f32: torch.Tensor,
                                  offsets_i32: torch.Tensor, n_structs: int,
                                  cells: Optional[torch.Tensor] = None,
-                                 pbc: Optional[torch.Tensor] = None):
+                                 pbc: Optional[torch.Tensor] = None, max_atoms: int = 0):
         """Batched fast path: inputs already in the C-ABI layout, no host sync besides the
-        status check.  Returns (E [B], F [N,3])."""
-        return self._run(z_i32, pos_f32, offsets_i32, n_structs, cells, pbc, True)
+        status check.  ``max_atoms`` = size of the largest structure if the caller knows it.
+        Returns (E [B], F [N,3])."""
+        return self._run(z_i32, pos_f32, offsets_i32, n_structs, cells, pbc, True, max_atoms)
 
     # ---- checkpoints ----------------------------------------------------------------------
     def save(self, path: Union[str, Path]):

@@ -38,7 +38,7 @@ def test_version_and_stage_names(lib):
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.MlffdConfig) == 24
-    assert ctypes.sizeof(_lib.MlffdStatus) == 48
+    assert ctypes.sizeof(_lib.MlffdStatus) == 56
     assert ctypes.sizeof(_lib.MlffdProfile) == 8 + 8 * _lib.NUM_STAGES * 2
 
 

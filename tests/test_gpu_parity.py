@@ -364,7 +364,9 @@ def test_tensor_core_batch_matches_oracle():
 def _with_neighbor_mode(mode, variant="ultra_tiny"):
     os.environ["MLFFD_NEIGHBOR"] = mode
     try:
-        return _model(variant)
+        bundle = _model(variant)
+        bundle[0].engine()   # the context reads MLFFD_NEIGHBOR when it is created
+        return bundle
     finally:
         os.environ.pop("MLFFD_NEIGHBOR", None)
 
@@ -419,3 +421,43 @@ def test_cell_list_energy_forces_periodic_1500_atoms():
                                dtype=torch.float64)
     assert abs(e[0] - e_ref[0]) / len(z) <= E_TOL
     assert np.max(np.abs(f - f_ref)) <= max(F_TOL, 2e-6 * float(np.abs(f_ref).max()))
+
+
+# ---------------------------------------------------------------------------------------------
+# structure-blocked (smem-staged) message kernels: bit-identical to the generic kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant_name", ["original", "tiny", "ultra_tiny"])
+def test_staged_message_kernels_bit_identical(variant_name):
+    from mlff_distiller_b200 import synthetic
+    structs = synthetic.druglike_batch(70, first=900, ragged=True) + [synthetic.water(), synthetic.Structure([6], [[0, 0, 0]])]
+    z, pos, off = synthetic.concatenate(structs)
+    counts = np.diff(off)
+    pos = pos.astype(np.float32)
+    dev = "cuda:0"
+    z_d = torch.from_numpy(z.astype(np.int32)).to(dev)
+    p_d = torch.from_numpy(pos).to(dev)
+    o_d = torch.from_numpy(off.astype(np.int32)).to(dev)
+    out = {}
+    for mode in ("staged", "generic"):
+        if mode == "staged":
+            os.environ["MLFFD_STAGING"] = "1"
+        try:
+            model, state, cfg = _model(variant_name)
+            model.engine()   # the context reads MLFFD_STAGING when it is created
+        finally:
+            os.environ.pop("MLFFD_STAGING", None)
+        e, f = model.energy_and_forces_packed(z_d, p_d, o_d, len(structs), max_atoms=int(counts.max()))
+        assert model.engine()._hint == int(counts.max())
+        out[mode] = (e.cpu().numpy(), f.cpu().numpy())
+    assert np.array_equal(out["staged"][0], out["generic"][0])
+    assert np.array_equal(out["staged"][1], out["generic"][1])
+    # a wrong promise is detected on the device and the call falls back to the generic kernels
+    os.environ["MLFFD_STAGING"] = "1"
+    try:
+        model, state, cfg = _model(variant_name)
+        model.engine()
+    finally:
+        os.environ.pop("MLFFD_STAGING", None)
+    e, f = model.energy_and_forces_packed(z_d, p_d, o_d, len(structs), max_atoms=25)
+    assert model.engine()._hint == 0
+    assert np.array_equal(e.cpu().numpy(), out["generic"][0]) and np.array_equal(f.cpu().numpy(), out["generic"][1])
