@@ -81,7 +81,7 @@ class StudentForceFieldCalculator(_AseCalculator):
                  batch_size: Optional[int] = None, enable_timing: bool = False,
                  use_compile: bool = False, use_fp16: bool = False, use_jit: bool = False,
                  jit_path: Optional[Union[str, Path]] = None, use_torch_cluster: bool = True,
-                 use_analytical_forces: bool = False, *, precision: str = "fp32",
+                 use_analytical_forces: bool = False, *, precision: str = "tc",
                  pbc_mode: str = "ignore", **kwargs):
         super().__init__(**kwargs)
         self.checkpoint_path = Path(checkpoint_path)

@@ -115,7 +115,7 @@ class StudentForceField(nn.Module):
 
     def __init__(self, hidden_dim: int = 128, num_interactions: int = 3, num_rbf: int = 20,
                  cutoff: float = 5.0, max_z: int = 118, learnable_rbf: bool = False,
-                 use_torch_cluster: bool = True, *, precision: str = "fp32",
+                 use_torch_cluster: bool = True, *, precision: str = "tc",
                  pbc_mode: str = "ignore"):
         super().__init__()
         if pbc_mode not in ("ignore", "minimum_image"):
