@@ -131,6 +131,22 @@ __device__ __forceinline__ void split8(const float (&xin)[8], uint4& hi, uint4& 
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// same split for 4 consecutive channels (half a swizzle chunk, 8 bytes per term)
+__device__ __forceinline__ void split4(const float4& xin, uint2& hi, uint2& lo) {
+    const float x[4] = {xin.x * kActScale, xin.y * kActScale, xin.z * kActScale, xin.w * kActScale};
+    uint32_t h[2], l[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const __half h0 = __float2half_rn(x[2 * i]), h1 = __float2half_rn(x[2 * i + 1]);
+        const __half l0 = __float2half_rn(x[2 * i] - __half2float(h0));
+        const __half l1 = __float2half_rn(x[2 * i + 1] - __half2float(h1));
+        h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    hi = make_uint2(h[0], h[1]);
+    lo = make_uint2(l[0], l[1]);
+}
+
 // byte offset of 16-byte chunk `chunk` (0..7) of row `r` inside a K-block image
 __device__ __forceinline__ uint32_t sw128_offset(int r, int chunk) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));

@@ -8,7 +8,7 @@
 // Rows come in tiles of 128 (atoms); K is walked in super-blocks of 128 (KS of them) and the
 // output in chunks of 128 channels (NC of them), all NC accumulators (<= 384 columns) stay in
 // TMEM across the K loop.  An `Op` supplies
-//   produce(row, ks, k0, x[16])   : 16 consecutive inputs of super-block ks for one row
+//   produce(row, n, ks, k0) -> float4 : 4 consecutive inputs of super-block ks for one row
 //   store(chunk, lane_ch, row0, r, prev) : epilogue for 32 rows x 1 channel per thread
 // so norms, SiLU, gates, the 3x3 spatial mixing and residuals are fused around the GEMM and the
 // only HBM traffic is the per-atom feature rows.
@@ -138,32 +138,29 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
         }
     } else {
         // ========================= compute / epilogue =========================
-        const int row_in_tile = tid & 127, kgrp = tid >> 7;   // 32 K-values per thread
+        // Producer mapping: a warp owns 8 rows of the tile, a lane owns 4 consecutive K values, so
+        // every global read of a feature row is one coalesced 512-byte request.
         const int q = warp & 3, cs = warp >> 2;               // channel quarter (lanes), row segment
+        const int kb = lane >> 4;                             // K block (64 values) of this lane
+        const int chunk = (lane & 15) >> 1, half8 = (lane & 1) * 8;
         for (int it = 0; it < my_tiles; ++it) {
             const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * 128;
             for (int ks = 0; ks < KS; ++ks) {
                 const int pc = it * KS + ks;
-                float x[2][16];
+                float4 x[8];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) op.produce(row0 + row_in_tile, num_rows, ks, kgrp * 32 + half * 16, x[half]);
+                for (int rr = 0; rr < 8; ++rr) x[rr] = op.produce(row0 + warp * 8 + rr, num_rows, ks, 4 * lane);
                 if (pc > 0) mbar_wait(bar_act_free, (pc - 1) & 1);   // previous MMAs finished reading the tile
-                const int kb = kgrp >> 1;
                 uint8_t* a_hi = smem + UmmaRowsSmem::A_HI + kb * kKBlockBytes;
                 uint8_t* a_lo = smem + UmmaRowsSmem::A_LO + kb * kKBlockBytes;
 #pragma unroll
-                for (int half = 0; half < 2; ++half)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        float v8[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v8[i] = x[half][8 * j + i];
-                        uint4 hi, lo;
-                        split8(v8, hi, lo);
-                        const uint32_t o = sw128_offset(row_in_tile, (kgrp & 1) * 4 + half * 2 + j);
-                        *reinterpret_cast<uint4*>(a_hi + o) = hi;
-                        *reinterpret_cast<uint4*>(a_lo + o) = lo;
-                    }
+                for (int rr = 0; rr < 8; ++rr) {
+                    uint2 hi, lo;
+                    split4(x[rr], hi, lo);
+                    const uint32_t o = sw128_offset(warp * 8 + rr, chunk) + half8;
+                    *reinterpret_cast<uint2*>(a_hi + o) = hi;
+                    *reinterpret_cast<uint2*>(a_lo + o) = lo;
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -209,30 +206,17 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
 // and its reverse, H = 128.  Weight "images" are [ks][chunk] 64 KB blocks of
 // the [out][in] matrix named at each op.
 
-__device__ __forceinline__ void load16(const float* p, float (&x)[16]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 v = ldg4(p + 4 * i);
-        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
-    }
-}
-__device__ __forceinline__ void zero16(float (&x)[16]) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = 0.f;
-}
-
 // y1 = M1 [s'; |v'|] + m1          W = update_mlp.0.weight [H][2H]: KS = 2, NC = 1
 struct UpdateFwd1Op {
     static constexpr int KS = 2, NC = 1;
     const float* s_msg; const float* v_msg; const float* m1; float* y1;
-    __device__ __forceinline__ void produce(int row, int n, int ks, int k0, float (&x)[16]) const {
-        if (row >= n) { zero16(x); return; }
-        if (ks == 0) { load16(s_msg + (size_t)row * 128 + k0, x); return; }
-        float vx[16], vy[16], vz[16];
+    __device__ __forceinline__ float4 produce(int row, int n, int ks, int k0) const {
+        if (row >= n) return make4(0.f);
+        if (ks == 0) return ldg4(s_msg + (size_t)row * 128 + k0);
         const float* vp = v_msg + (size_t)row * 384 + k0;
-        load16(vp, vx); load16(vp + 128, vy); load16(vp + 256, vz);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = sqrtf(vx[i] * vx[i] + vy[i] * vy[i] + vz[i] * vz[i]);
+        const float4 vx = ldg4(vp), vy = ldg4(vp + 128), vz = ldg4(vp + 256);
+        return make_float4(sqrtf(vx.x * vx.x + vy.x * vy.x + vz.x * vz.x), sqrtf(vx.y * vx.y + vy.y * vy.y + vz.y * vz.y),
+                           sqrtf(vx.z * vx.z + vy.z * vy.z + vz.z * vz.z), sqrtf(vx.w * vx.w + vy.w * vy.w + vz.w * vz.w));
     }
     __device__ __forceinline__ void store(int, int ch, int row0, int n, const uint32_t (&r)[32], const uint32_t (&)[32]) const {
         const float b = __ldg(m1 + ch);
@@ -249,40 +233,54 @@ struct UpdateFwd2Op {
     static constexpr int KS = 1, NC = LAST ? 1 : 3;
     const float* y1; const float* s_msg; const float* v_msg; const float* m2; const float* U;
     float* s_out; float* v_out; float* gates;
-    __device__ __forceinline__ void produce(int row, int n, int, int k0, float (&x)[16]) const {
-        if (row >= n) { zero16(x); return; }
-        load16(y1 + (size_t)row * 128 + k0, x);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = siluf_(x[i]);
+    __device__ __forceinline__ float4 produce(int row, int n, int, int k0) const {
+        if (row >= n) return make4(0.f);
+        const float4 y = ldg4(y1 + (size_t)row * 128 + k0);
+        return make_float4(siluf_(y.x), siluf_(y.y), siluf_(y.z), siluf_(y.w));
     }
     __device__ __forceinline__ void store(int c, int ch, int row0, int n, const uint32_t (&r)[32], const uint32_t (&prev)[32]) const {
         if (c == 0) {
             const float b = __ldg(m2 + ch);
+            // loads of a batch of rows are issued together, then the stores: a load placed after a
+            // store through another pointer cannot be hoisted by the compiler (possible alias)
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (row0 + j < n) {
-                    const size_t o = (size_t)(row0 + j) * 128 + ch;
-                    s_out[o] = __ldg(s_msg + o) + __uint_as_float(r[j]) + b;
-                }
+            for (int jb = 0; jb < 32; jb += 8) {
+                float sv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    sv[j] = (row0 + jb + j < n) ? __ldg(s_msg + (size_t)(row0 + jb + j) * 128 + ch) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (row0 + jb + j < n)
+                        s_out[(size_t)(row0 + jb + j) * 128 + ch] = sv[j] + __uint_as_float(r[jb + j]) + b;
+            }
         } else if (c == 2) {   // prev = g1 accumulators (chunk 1), r = g2
             const float b1 = __ldg(m2 + 128 + ch), b2 = __ldg(m2 + 256 + ch);
             float u[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) u[k] = __ldg(U + k);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (row0 + j < n) {
-                    const size_t row = (size_t)(row0 + j);
-                    const float g1 = __uint_as_float(prev[j]) + b1, g2 = __uint_as_float(r[j]) + b2;
-                    const float* vp = v_msg + row * 384 + ch;
-                    const float vx = __ldg(vp), vy = __ldg(vp + 128), vz = __ldg(vp + 256);
-                    gates[row * 256 + ch] = g1;
-                    gates[row * 256 + 128 + ch] = g2;
-                    float* vo = v_out + row * 384 + ch;
-                    vo[0] = vx * g1 + (u[0] * vx + u[1] * vy + u[2] * vz) * g2;
-                    vo[128] = vy * g1 + (u[3] * vx + u[4] * vy + u[5] * vz) * g2;
-                    vo[256] = vz * g1 + (u[6] * vx + u[7] * vy + u[8] * vz) * g2;
+            for (int jb = 0; jb < 32; jb += 8) {
+                float vx[8], vy[8], vz[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool ok = row0 + jb + j < n;
+                    const float* vp = v_msg + (size_t)(row0 + jb + j) * 384 + ch;
+                    vx[j] = ok ? __ldg(vp) : 0.f; vy[j] = ok ? __ldg(vp + 128) : 0.f; vz[j] = ok ? __ldg(vp + 256) : 0.f;
                 }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (row0 + jb + j < n) {
+                        const size_t row = (size_t)(row0 + jb + j);
+                        const float g1 = __uint_as_float(prev[jb + j]) + b1, g2 = __uint_as_float(r[jb + j]) + b2;
+                        gates[row * 256 + ch] = g1;
+                        gates[row * 256 + 128 + ch] = g2;
+                        float* vo = v_out + row * 384 + ch;
+                        vo[0] = vx[j] * g1 + (u[0] * vx[j] + u[1] * vy[j] + u[2] * vz[j]) * g2;
+                        vo[128] = vy[j] * g1 + (u[3] * vx[j] + u[4] * vy[j] + u[5] * vz[j]) * g2;
+                        vo[256] = vz[j] * g1 + (u[6] * vx[j] + u[7] * vy[j] + u[8] * vz[j]) * g2;
+                    }
+            }
         }
     }
 };
@@ -293,35 +291,37 @@ template <bool LAST>
 struct UpdateBwd1Op {
     static constexpr int KS = LAST ? 1 : 3, NC = 1;
     const float* sbar; const float* vbar; const float* v_msg; const float* U; float* y1;
-    __device__ __forceinline__ void produce(int row, int n, int ks, int k0, float (&x)[16]) const {
-        if (row >= n) { zero16(x); return; }
-        if (ks == 0) { load16(sbar + (size_t)row * 128 + k0, x); return; }
-        float vx[16], vy[16], vz[16], bx[16], by[16], bz[16];
+    __device__ __forceinline__ float4 produce(int row, int n, int ks, int k0) const {
+        if (row >= n) return make4(0.f);
+        if (ks == 0) return ldg4(sbar + (size_t)row * 128 + k0);
         const float* vp = v_msg + (size_t)row * 384 + k0;
         const float* bp = vbar + (size_t)row * 384 + k0;
-        load16(vp, vx); load16(vp + 128, vy); load16(vp + 256, vz);
-        load16(bp, bx); load16(bp + 128, by); load16(bp + 256, bz);
-        if (ks == 1) {
+        const float4 vx = ldg4(vp), vy = ldg4(vp + 128), vz = ldg4(vp + 256);
+        const float4 bx = ldg4(bp), by = ldg4(bp + 128), bz = ldg4(bp + 256);
+        if (ks == 1)
+            return make_float4(bx.x * vx.x + by.x * vy.x + bz.x * vz.x, bx.y * vx.y + by.y * vy.y + bz.y * vz.y,
+                               bx.z * vx.z + by.z * vy.z + bz.z * vz.z, bx.w * vx.w + by.w * vy.w + bz.w * vz.w);
+        float u[9];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) x[i] = bx[i] * vx[i] + by[i] * vy[i] + bz[i] * vz[i];
-        } else {
-            float u[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) u[k] = __ldg(U + k);
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                x[i] = bx[i] * (u[0] * vx[i] + u[1] * vy[i] + u[2] * vz[i]) +
-                       by[i] * (u[3] * vx[i] + u[4] * vy[i] + u[5] * vz[i]) +
-                       bz[i] * (u[6] * vx[i] + u[7] * vy[i] + u[8] * vz[i]);
-        }
+        for (int k = 0; k < 9; ++k) u[k] = __ldg(U + k);
+        auto mix = [&](float b0, float b1, float b2, float v0, float v1, float v2) {
+            return b0 * (u[0] * v0 + u[1] * v1 + u[2] * v2) + b1 * (u[3] * v0 + u[4] * v1 + u[5] * v2) +
+                   b2 * (u[6] * v0 + u[7] * v1 + u[8] * v2);
+        };
+        return make_float4(mix(bx.x, by.x, bz.x, vx.x, vy.x, vz.x), mix(bx.y, by.y, bz.y, vx.y, vy.y, vz.y),
+                           mix(bx.z, by.z, bz.z, vx.z, vy.z, vz.z), mix(bx.w, by.w, bz.w, vx.w, vy.w, vz.w));
     }
     __device__ __forceinline__ void store(int, int ch, int row0, int n, const uint32_t (&r)[32], const uint32_t (&)[32]) const {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (row0 + j < n) {
-                const size_t o = (size_t)(row0 + j) * 128 + ch;
-                y1[o] = __uint_as_float(r[j]) * silu_gradf_(y1[o]);
-            }
+        for (int jb = 0; jb < 32; jb += 8) {
+            float yv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) yv[j] = (row0 + jb + j < n) ? y1[(size_t)(row0 + jb + j) * 128 + ch] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (row0 + jb + j < n)
+                    y1[(size_t)(row0 + jb + j) * 128 + ch] = __uint_as_float(r[jb + j]) * silu_gradf_(yv[j]);
+        }
     }
 };
 
@@ -331,40 +331,58 @@ template <bool LAST>
 struct UpdateBwd2Op {
     static constexpr int KS = 1, NC = 2;
     const float* ybar; const float* v_msg; const float* gates; const float* U; float* sbar; float* vbar;
-    __device__ __forceinline__ void produce(int row, int n, int, int k0, float (&x)[16]) const {
-        if (row >= n) { zero16(x); return; }
-        load16(ybar + (size_t)row * 128 + k0, x);
+    __device__ __forceinline__ float4 produce(int row, int n, int, int k0) const {
+        if (row >= n) return make4(0.f);
+        return ldg4(ybar + (size_t)row * 128 + k0);
     }
     __device__ __forceinline__ void store(int c, int ch, int row0, int n, const uint32_t (&r)[32], const uint32_t (&)[32]) const {
         if (c == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (row0 + j < n) sbar[(size_t)(row0 + j) * 128 + ch] += __uint_as_float(r[j]);
+            for (int jb = 0; jb < 32; jb += 8) {
+                float sv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sv[j] = (row0 + jb + j < n) ? sbar[(size_t)(row0 + jb + j) * 128 + ch] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (row0 + jb + j < n) sbar[(size_t)(row0 + jb + j) * 128 + ch] = sv[j] + __uint_as_float(r[jb + j]);
+            }
             return;
         }
         float u[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) u[k] = __ldg(U + k);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (row0 + j < n) {
-                const size_t row = (size_t)(row0 + j);
+        for (int jb = 0; jb < 32; jb += 4) {
+            float vx[4], vy[4], vz[4], bx[4], by[4], bz[4], g1[4], g2[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool ok = row0 + jb + j < n;
+                const size_t row = (size_t)(row0 + jb + j);
                 const float* vp = v_msg + row * 384 + ch;
-                float* bp = vbar + row * 384 + ch;
-                const float vx = __ldg(vp), vy = __ldg(vp + 128), vz = __ldg(vp + 256);
-                const float nrm = sqrtf(vx * vx + vy * vy + vz * vz);
-                const float sc = (nrm > 0.f) ? __uint_as_float(r[j]) / nrm : 0.f;
-                float ox = sc * vx, oy = sc * vy, oz = sc * vz;
-                if (!LAST) {
-                    const float g1 = __ldg(gates + row * 256 + ch), g2 = __ldg(gates + row * 256 + 128 + ch);
-                    const float bx = bp[0], by = bp[128], bz = bp[256];
-                    const float gx = bx * g2, gy = by * g2, gz = bz * g2;
-                    ox += bx * g1 + (u[0] * gx + u[3] * gy + u[6] * gz);
-                    oy += by * g1 + (u[1] * gx + u[4] * gy + u[7] * gz);
-                    oz += bz * g1 + (u[2] * gx + u[5] * gy + u[8] * gz);
+                vx[j] = ok ? __ldg(vp) : 0.f; vy[j] = ok ? __ldg(vp + 128) : 0.f; vz[j] = ok ? __ldg(vp + 256) : 0.f;
+                bx[j] = by[j] = bz[j] = g1[j] = g2[j] = 0.f;
+                if (!LAST && ok) {
+                    const float* bp = vbar + row * 384 + ch;
+                    bx[j] = bp[0]; by[j] = bp[128]; bz[j] = bp[256];
+                    g1[j] = __ldg(gates + row * 256 + ch); g2[j] = __ldg(gates + row * 256 + 128 + ch);
                 }
-                bp[0] = ox; bp[128] = oy; bp[256] = oz;
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (row0 + jb + j < n) {
+                    const float nrm = sqrtf(vx[j] * vx[j] + vy[j] * vy[j] + vz[j] * vz[j]);
+                    const float sc = (nrm > 0.f) ? __uint_as_float(r[jb + j]) / nrm : 0.f;
+                    float ox = sc * vx[j], oy = sc * vy[j], oz = sc * vz[j];
+                    if (!LAST) {
+                        const float gx = bx[j] * g2[j], gy = by[j] * g2[j], gz = bz[j] * g2[j];
+                        ox += bx[j] * g1[j] + (u[0] * gx + u[3] * gy + u[6] * gz);
+                        oy += by[j] * g1[j] + (u[1] * gx + u[4] * gy + u[7] * gz);
+                        oz += bz[j] * g1[j] + (u[2] * gx + u[5] * gy + u[8] * gz);
+                    }
+                    float* bp = vbar + (size_t)(row0 + jb + j) * 384 + ch;
+                    bp[0] = ox; bp[128] = oy; bp[256] = oz;
+                }
+        }
     }
 };
 
