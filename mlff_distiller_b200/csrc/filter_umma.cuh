@@ -186,12 +186,23 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
 
     // ---- one-time setup ----
     if (warp == kUmmaComputeWarps) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         if (lane == 0) {
             for (int i = 0; i < 6; ++i) mbar_init(bars + i, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // start streaming the first two weight chunks before anything else (latency path)
+            const int total0 = my_tiles * nchunks;
+            for (int g = 0; g < 2 && g < total0; ++g) {
+                mbar_expect_tx(&bar_b_full[g], kChunkImageBytes);
+                const int cid = skip_vector_gate ? (g % nchunks) * 2 : (g % nchunks);
+                const uint8_t* src = w2_images + (size_t)cid * kChunkImageBytes;
+                const uint32_t dst = smem_u32(smem + (g ? UmmaSmem::B1 : UmmaSmem::B0));
+                for (int qq = 0; qq < 4; ++qq)
+                    bulk_g2s(dst + qq * kKBlockBytes, src + qq * kKBlockBytes, kKBlockBytes, &bar_b_full[g]);
+            }
         }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     } else {
         for (int idx = tid; idx < K * H / 4; idx += kUmmaComputeThreads) st4(w1t_s + 4 * idx, ldg4(w.W1t + 4 * idx));
         for (int idx = tid; idx < H; idx += kUmmaComputeThreads) b1_s[idx] = __ldg(w.b1 + idx);
@@ -220,9 +231,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                 for (int qq = 0; qq < 4; ++qq)
                     bulk_g2s(b_buf[buf] + qq * kKBlockBytes, src + qq * kKBlockBytes, kKBlockBytes, &bar_b_full[buf]);
             };
-            issue_load(0);
-            if (total_chunks > 1) issue_load(1);
-            for (int g = 0; g < total_chunks; ++g) {
+            for (int g = 0; g < total_chunks; ++g) {   // chunks 0 and 1 were requested during set-up
                 const int it = g / nchunks, ci = g - it * nchunks, nc = chunk_id(g), buf = g & 1;
                 if (ci == 0) {  // activation tile `it` written; previous accumulators drained
                     mbar_wait(bar_a_full, it & 1);

@@ -319,7 +319,7 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
 
     const bool want_forces = forces != nullptr;
     auto adj = [&](int l) { return ctx->debug_keep ? l : (l & 1); };
-    readout_kernel<H><<<warp_grid, 256, 0, st>>>(ws.s_in[L], ctx->head, ws.eps,
+    readout_kernel<H><<<clamp_grid(ceil_div(N, 8 * 4), kNumSMs * 8), 256, 0, st>>>(ws.s_in[L], ctx->head, ws.eps,
                                                  want_forces ? ws.sbar[adj(L - 1)] : nullptr, N, status);
     LAUNCHED(ctx, "readout_kernel", MLFFD_STAGE_READOUT, st);
     structure_energy_kernel<<<clamp_grid(ceil_div(n_structs, 8), kNumSMs * 8), 256, 0, st>>>(
@@ -439,14 +439,20 @@ int build_neighbors(mlffd_ctx* ctx, const float* pos, const int* offsets, int n_
             nullptr, nullptr, nullptr, ctx->status_d);
         LAUNCHED(ctx, "neighbor_sweep_kernel<count>", MLFFD_STAGE_NEIGHBOR, st);
     }
-    bytes = ws.cub_bytes;
-    CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ws.cub_temp, bytes, ws.deg, ws.rowptr, N + 1, st));
-    bytes = ws.cub_bytes;
-    CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ws.cub_temp, bytes, ws.deg_low, ws.lowptr, N + 1, st));
-    mark(ctx, MLFFD_STAGE_NEIGHBOR, st, 4);  // two CUB scans = 2 x (init + scan) kernels
-    neighbor_finalize_kernel<<<1, 32, 0, st>>>(ws.rowptr, ws.lowptr, N, (int)ws.cap_edges,
-                                               ctx->status_d);
-    LAUNCHED(ctx, "neighbor_finalize_kernel", MLFFD_STAGE_NEIGHBOR, st);
+    if (N <= 32768) {   // latency path: one launch instead of five
+        neighbor_scan_small_kernel<<<1, 1024, 0, st>>>(ws.deg, ws.deg_low, ws.rowptr, ws.lowptr, N,
+                                                       (int)ws.cap_edges, ctx->status_d);
+        LAUNCHED(ctx, "neighbor_scan_small_kernel", MLFFD_STAGE_NEIGHBOR, st);
+    } else {
+        bytes = ws.cub_bytes;
+        CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ws.cub_temp, bytes, ws.deg, ws.rowptr, N + 1, st));
+        bytes = ws.cub_bytes;
+        CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ws.cub_temp, bytes, ws.deg_low, ws.lowptr, N + 1, st));
+        mark(ctx, MLFFD_STAGE_NEIGHBOR, st, 4);  // two CUB scans = 2 x (init + scan) kernels
+        neighbor_finalize_kernel<<<1, 32, 0, st>>>(ws.rowptr, ws.lowptr, N, (int)ws.cap_edges,
+                                                   ctx->status_d);
+        LAUNCHED(ctx, "neighbor_finalize_kernel", MLFFD_STAGE_NEIGHBOR, st);
+    }
     if (use_cells) {
         // scratch for the unsorted rows: `rev` and `edge_adj` are only written by later kernels
         neighbor_cells_kernel<true><<<sweep_grid, 256, 0, st>>>(

@@ -108,6 +108,55 @@ __global__ void neighbor_finalize_kernel(const int* __restrict__ rowptr,
     }
 }
 
+// Small systems (latency path): both exclusive scans and the finalize step in ONE single-block
+// launch instead of five (2 x CUB init + scan, finalize).  Each thread scans a contiguous chunk.
+__global__ void __launch_bounds__(1024)
+neighbor_scan_small_kernel(const int* __restrict__ deg, const int* __restrict__ deg_low,
+                           int* __restrict__ rowptr, int* __restrict__ lowptr, int num_atoms,
+                           int edge_capacity, DeviceStatus* __restrict__ status) {
+    __shared__ int warp_a[32], warp_b[32];
+    const int n = num_atoms + 1;   // deg[num_atoms] == 0 closes the CSR
+    const int chunk = (n + 1023) / 1024;
+    const int lo = min(threadIdx.x * chunk, n), hi = min(lo + chunk, n);
+    int sa = 0, sb = 0;
+    for (int i = lo; i < hi; ++i) { sa += deg[i]; sb += deg_low[i]; }
+    // exclusive scan of the 1024 per-thread sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int ia = sa, ib = sb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ta; ib += tb; }
+    }
+    if (lane == 31) { warp_a[warp] = ia; warp_b[warp] = ib; }
+    __syncthreads();
+    if (warp == 0) {
+        int wa = warp_a[lane], wb = warp_b[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ta = __shfl_up_sync(0xffffffffu, wa, o), tb = __shfl_up_sync(0xffffffffu, wb, o);
+            if (lane >= o) { wa += ta; wb += tb; }
+        }
+        warp_a[lane] = wa; warp_b[lane] = wb;   // inclusive over warps
+    }
+    __syncthreads();
+    int pa = ia - sa + (warp ? warp_a[warp - 1] : 0);   // exclusive prefix of this thread's chunk
+    int pb = ib - sb + (warp ? warp_b[warp - 1] : 0);
+    for (int i = lo; i < hi; ++i) {
+        rowptr[i] = pa; lowptr[i] = pb;
+        pa += deg[i]; pb += deg_low[i];
+    }
+    if (threadIdx.x == 1023) {
+        const int e = warp_a[31];
+        status->num_edges = e;
+        status->num_pairs = warp_b[31];
+        status->overflow = (e > edge_capacity) ? 1 : 0;
+        if (e > edge_capacity) status->overflow_events += 1;
+        status->max_degree = 0;
+        status->hint_violation = 0;
+    }
+}
+
 // Per edge e = (i -> j): rev[e] = position of (j -> i) (binary search in row i), pair id, and the
 // compact per-pair distance list the filter-table kernel consumes.  Lower edges (i < j) come
 // first in a row because sources ascend, so pair ids need no extra sort.

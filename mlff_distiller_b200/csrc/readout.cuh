@@ -42,56 +42,100 @@ embedding_kernel(const int* __restrict__ z, const float* __restrict__ emb, int m
     }
 }
 
-// One warp per atom (grid-stride).  Writes eps[atom] and, if sbar != nullptr, d eps / d s.
+// A warp evaluates the head for AT = 4 atoms at a time (grid-stride), so every weight fetched
+// from L1 feeds four FMAs: with one atom per warp the kernel was bound by L1 bandwidth (one
+// 4-byte weight load per FMA).  Writes eps[atom] and, if sbar != nullptr, d eps / d s.
 template <int H>
 __global__ void __launch_bounds__(256)
 readout_kernel(const float* __restrict__ s, HeadWeights w, float* __restrict__ eps,
                float* __restrict__ sbar, int num_atoms, const DeviceStatus* __restrict__ status) {
     constexpr int H2 = H / 2, H4 = H / 4;
-    constexpr int WARPS = 8;
+    constexpr int WARPS = 8, AT = 4;
     if (status->overflow) return;
-    __shared__ float s_sh[WARPS][H];
-    __shared__ float y1_sh[WARPS][H2];   // pre-activations, then adjoints
-    __shared__ float h1_sh[WARPS][H2];
-    __shared__ float y2_sh[WARPS][H4];
+    __shared__ float s_sh[WARPS][AT][H];
+    __shared__ float y1_sh[WARPS][AT][H2];   // pre-activations
+    __shared__ float h1_sh[WARPS][AT][H2];   // activations, then adjoints of y1
+    __shared__ float y2_sh[WARPS][AT][H4];   // adjoints of the layer-2 pre-activations
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = blockIdx.x * WARPS + wib;
     const int num_warps = gridDim.x * WARPS;
-    for (int atom = warp; atom < num_atoms; atom += num_warps) {
-        for (int c = lane; c < H; c += 32) s_sh[wib][c] = __ldg(s + (size_t)atom * H + c);
+    for (int atom0 = warp * AT; atom0 < num_atoms; atom0 += num_warps * AT) {
+#pragma unroll
+        for (int a = 0; a < AT; ++a)
+            for (int c = lane; c < H; c += 32)
+                s_sh[wib][a][c] = (atom0 + a < num_atoms) ? __ldg(s + (size_t)(atom0 + a) * H + c) : 0.f;
         __syncwarp();
         // layer 1: H -> H/2
         for (int o = lane; o < H2; o += 32) {
-            float y = __ldg(w.a1 + o);
-            for (int k = 0; k < H; ++k) y = fmaf(s_sh[wib][k], __ldg(w.A1t + k * H2 + o), y);
-            y1_sh[wib][o] = y;
-            h1_sh[wib][o] = siluf_(y);
+            float y[AT];
+#pragma unroll
+            for (int a = 0; a < AT; ++a) y[a] = __ldg(w.a1 + o);
+#pragma unroll 4
+            for (int k = 0; k < H; ++k) {
+                const float wv = __ldg(w.A1t + k * H2 + o);
+#pragma unroll
+                for (int a = 0; a < AT; ++a) y[a] = fmaf(s_sh[wib][a][k], wv, y[a]);
+            }
+#pragma unroll
+            for (int a = 0; a < AT; ++a) { y1_sh[wib][a][o] = y[a]; h1_sh[wib][a][o] = siluf_(y[a]); }
         }
         __syncwarp();
         // layer 2: H/2 -> H/4, layer 3: H/4 -> 1
-        float part = 0.f;
+        float part[AT];
+#pragma unroll
+        for (int a = 0; a < AT; ++a) part[a] = 0.f;
         for (int o = lane; o < H4; o += 32) {
-            float y = __ldg(w.a2 + o);
-            for (int k = 0; k < H2; ++k) y = fmaf(h1_sh[wib][k], __ldg(w.A2t + k * H4 + o), y);
+            float y[AT];
+#pragma unroll
+            for (int a = 0; a < AT; ++a) y[a] = __ldg(w.a2 + o);
+#pragma unroll 4
+            for (int k = 0; k < H2; ++k) {
+                const float wv = __ldg(w.A2t + k * H4 + o);
+#pragma unroll
+                for (int a = 0; a < AT; ++a) y[a] = fmaf(h1_sh[wib][a][k], wv, y[a]);
+            }
             const float a3 = __ldg(w.A3 + o);
-            part = fmaf(siluf_(y), a3, part);
-            y2_sh[wib][o] = a3 * silu_gradf_(y);   // adjoint of the layer-2 pre-activation
+#pragma unroll
+            for (int a = 0; a < AT; ++a) {
+                part[a] = fmaf(siluf_(y[a]), a3, part[a]);
+                y2_sh[wib][a][o] = a3 * silu_gradf_(y[a]);   // adjoint of the layer-2 pre-activation
+            }
         }
-        part = group_sum<32>(part);
-        if (lane == 0) eps[atom] = part + __ldg(w.a3);
+#pragma unroll
+        for (int a = 0; a < AT; ++a) {
+            part[a] = group_sum<32>(part[a]);
+            if (lane == 0 && atom0 + a < num_atoms) eps[atom0 + a] = part[a] + __ldg(w.a3);
+        }
         __syncwarp();
         if (sbar != nullptr) {
             // y1_bar = (A2^T y2_bar) * SiLU'(y1)
             for (int k = lane; k < H2; k += 32) {
-                float hb = 0.f;
-                for (int o = 0; o < H4; ++o) hb = fmaf(y2_sh[wib][o], __ldg(w.A2 + o * H2 + k), hb);
-                h1_sh[wib][k] = hb * silu_gradf_(y1_sh[wib][k]);
+                float hb[AT];
+#pragma unroll
+                for (int a = 0; a < AT; ++a) hb[a] = 0.f;
+#pragma unroll 4
+                for (int o = 0; o < H4; ++o) {
+                    const float wv = __ldg(w.A2 + o * H2 + k);
+#pragma unroll
+                    for (int a = 0; a < AT; ++a) hb[a] = fmaf(y2_sh[wib][a][o], wv, hb[a]);
+                }
+#pragma unroll
+                for (int a = 0; a < AT; ++a) h1_sh[wib][a][k] = hb[a] * silu_gradf_(y1_sh[wib][a][k]);
             }
             __syncwarp();
             for (int c = lane; c < H; c += 32) {
-                float sb = 0.f;
-                for (int k = 0; k < H2; ++k) sb = fmaf(h1_sh[wib][k], __ldg(w.A1 + k * H + c), sb);
-                sbar[(size_t)atom * H + c] = sb;
+                float sb[AT];
+#pragma unroll
+                for (int a = 0; a < AT; ++a) sb[a] = 0.f;
+#pragma unroll 4
+                for (int k = 0; k < H2; ++k) {
+                    const float wv = __ldg(w.A1 + k * H + c);
+#pragma unroll
+                    for (int a = 0; a < AT; ++a) sb[a] = fmaf(h1_sh[wib][a][k], wv, sb[a]);
+                }
+#pragma unroll
+                for (int a = 0; a < AT; ++a)
+                    if (atom0 + a < num_atoms) sbar[(size_t)(atom0 + a) * H + c] = sb[a];
             }
         }
         __syncwarp();

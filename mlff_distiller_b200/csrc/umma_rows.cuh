@@ -53,13 +53,24 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
+    constexpr int PER_TILE = KS * NC;
     if (warp == kUmmaComputeWarps) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         if (lane == 0) {
             for (int i = 0; i < 9; ++i) mbar_init(bars + i, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // start streaming the first two weight images before anything else (latency path)
+            const int total0 = my_tiles * PER_TILE;
+            for (int g = 0; g < 2 && g < total0; ++g) {
+                mbar_expect_tx(&bar_b_full[g], kChunkImageBytes);
+                const uint8_t* src = images + (size_t)(g % PER_TILE) * kChunkImageBytes;
+                const uint32_t dst = smem_u32(smem + (g ? UmmaRowsSmem::B1 : UmmaRowsSmem::B0));
+                for (int qq = 0; qq < 4; ++qq)
+                    bulk_g2s(dst + qq * kKBlockBytes, src + qq * kKBlockBytes, kKBlockBytes, &bar_b_full[g]);
+            }
         }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -74,7 +85,6 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
             const uint64_t act_desc_hi = umma_desc_sw128(smem_u32(smem + UmmaRowsSmem::A_HI));
             const uint64_t act_desc_lo = umma_desc_sw128(smem_u32(smem + UmmaRowsSmem::A_LO));
             const uint64_t w_desc0 = umma_desc_sw128(b_buf[0]);
-            constexpr int PER_TILE = KS * NC;
             const int total = my_tiles * PER_TILE;
             auto issue_load = [&](int g) {
                 const int buf = g & 1;
@@ -84,9 +94,7 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
                 for (int qq = 0; qq < 4; ++qq)
                     bulk_g2s(b_buf[buf] + qq * kKBlockBytes, src + qq * kKBlockBytes, kKBlockBytes, &bar_b_full[buf]);
             };
-            issue_load(0);
-            if (total > 1) issue_load(1);
-            int g = 0;
+            int g = 0;   // images 0 and 1 were requested during set-up
             for (int it = 0; it < my_tiles; ++it) {
                 for (int ks = 0; ks < KS; ++ks) {
                     const int pc = it * KS + ks;
