@@ -98,6 +98,7 @@ class StudentForceFieldCalculator(_AseCalculator):
         self.use_analytical_forces = use_analytical_forces
         self.precision = precision
         self.pbc_mode = pbc_mode
+        self.max_atoms_per_call = 262144   # micro-batch bound of the batched interface (~30 GB workspace)
         self.implemented_properties = ["energy", "forces"]
         if self.enable_stress:
             self.implemented_properties.append("stress")
@@ -269,6 +270,19 @@ class StudentForceFieldCalculator(_AseCalculator):
             raise ValueError(f"Invalid atomic numbers: must be 1-{min(118, self.model.max_z)}")
         if not np.isfinite(positions).all():
             raise ValueError("Positions contain NaN or Inf values")
+        if len(numbers) > self.max_atoms_per_call and len(counts) > 1:
+            # micro-batches that fit the workspace (a 100 k-structure sweep does not fit in one call)
+            from .sharding import chunk_by_budget
+            offs = np.concatenate([[0], np.cumsum(counts)])
+            e_parts, f_parts = [], []
+            for a, b in chunk_by_budget(counts, self.max_atoms_per_call, 1 << 20):
+                sl = slice(int(offs[a]), int(offs[b]))
+                e, f = self.evaluate_arrays(numbers[sl], positions[sl], counts[a:b],
+                                            None if cells is None else cells[a:b],
+                                            None if pbcs is None else pbcs[a:b])
+                e_parts.append(e)
+                f_parts.append(f)
+            return np.concatenate(e_parts), np.concatenate(f_parts)
         dev = self.device
         nb, n = len(counts), len(numbers)
         st = self._batch_staging(n, nb)

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""BASELINE config C5: screening sweep of ragged synthetic structures, sharded over the GPUs of
+one box (one process per GPU, contiguous shards balanced by atoms, NO collective on the data
+path; per-structure energies are gathered on the host at the end).
+
+    python tools/sweep.py --structures 100000 --variant tiny                       # 1 GPU
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/sweep.py ...
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from mlff_distiller_b200 import sharding, synthetic  # noqa: E402
+from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--structures", type=int, default=100000)
+    ap.add_argument("--variant", default="original")
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # every rank derives the same global size list (cheap), generates only its own shard
+    sizes = np.array([int(np.random.default_rng(500000 + s).integers(20, 81)) for s in range(args.structures)])
+    a, b = sharding.shard_slice(sizes, rank, world)
+    structs = synthetic.druglike_batch(b - a, first=a, ragged=True)
+    numbers, pos, offsets = synthetic.concatenate(structs)
+    counts = np.diff(offsets)
+    calc = StudentForceFieldCalculator(ROOT / "tests" / "golden" / f"weights_{args.variant}.npz", device=f"cuda:{local}")
+    calc.evaluate_arrays(numbers[: offsets[64]], pos[: offsets[64]], counts[:64])   # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e, f = calc.evaluate_arrays(numbers, pos, counts)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e_all, _ = sharding.gather_in_order(e, np.zeros((0, 3), dtype=np.float32))
+    else:
+        e_all = e
+    if rank == 0:
+        out = {"config": "C5 ragged sweep", "variant": args.variant, "structures": args.structures,
+               "atoms": int(sizes.sum()), "n_gpus": world, "seconds": float(dt.item()),
+               "structures_per_s": args.structures / float(dt.item()),
+               "energy_checksum": float(np.asarray(e_all, dtype=np.float64).sum()),
+               "shard_atoms_rank0": int(counts.sum())}
+        print(json.dumps(out))
+        if args.out:
+            Path(args.out).write_text(json.dumps(out, indent=1))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
