@@ -180,3 +180,20 @@ def test_device_md_batch_of_independent_trajectories(calc):
     out = dev.run(100)
     assert len(out["total"]) == 101 and np.isfinite(out["total"]).all()
     assert abs(out["drift_percent"]) < 0.5
+
+
+def test_batched_interface_micro_batches_large_requests(calc):
+    """A request larger than the per-call atom budget is split into micro-batches (C5 sweeps);
+    results must not depend on where the cuts fall."""
+    structs = synthetic.druglike_batch(40, first=2000, ragged=True)
+    z, pos, off = synthetic.concatenate(structs)
+    counts = np.diff(off)
+    e_ref, f_ref = calc.evaluate_arrays(z, pos, counts)
+    old = calc.max_atoms_per_call
+    try:
+        calc.max_atoms_per_call = 300
+        e, f = calc.evaluate_arrays(z, pos, counts)
+    finally:
+        calc.max_atoms_per_call = old
+    assert e.shape == e_ref.shape and f.shape == f_ref.shape
+    assert np.abs(e - e_ref).max() < 2e-4 and np.abs(f - f_ref).max() < 2e-5
