@@ -340,7 +340,10 @@ def run_b200(args):
                         "GBps": wk["bytes"] / (per_step_ms * 1e-3) / 1e9 if per_step_ms > 0 else None,
                         "TFLOPs": wk["flops"] / (per_step_ms * 1e-3) / 1e12 if per_step_ms > 0 else None}
     top = max(stages, key=lambda k: stages[k]["ms_per_step"])
-    if top in COMPUTE_BOUND:
+    # the roofline that bounds the kernel is the SLOWER of (FLOPs / tensor peak) and (bytes / HBM peak)
+    t_tensor = work[top]["flops"] / (peaks["bf16_tflops"] * 1e12)
+    t_hbm = work[top]["bytes"] / (peaks["hbm_gbs"] * 1e9)
+    if top in COMPUTE_BOUND and t_tensor >= t_hbm:
         achieved, peak, unit, bound = stages[top]["TFLOPs"], peaks["bf16_tflops"], "TFLOP/s", "tensor"
     else:
         achieved, peak, unit, bound = stages[top]["GBps"], peaks["hbm_gbs"], "GB/s", "hbm"
@@ -351,6 +354,7 @@ def run_b200(args):
     roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
                 "frac": achieved / peak if achieved else None, "traffic": traffic,
                 "peak_source": peaks["source"],
+                "tensor_TFLOPs": stages[top]["TFLOPs"], "tensor_frac": (stages[top]["TFLOPs"] or 0) / peaks["bf16_tflops"],
                 "share_of_step": stages[top]["ms_per_step"] / (elapsed_ms / args.steps)}
 
     out = {

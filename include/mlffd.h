@@ -39,7 +39,8 @@ enum {
     MLFFD_PREC_FP32 = 0,      /* FP32 FFMA everywhere */
     MLFFD_PREC_TC_FP16X2 = 1, /* tcgen05 tensor cores, operands split into two FP16 terms, three
                                  products, FP32 accumulation in TMEM: FP32-equivalent (meets the
-                                 FP32 bounds).  H = 128 only; other sizes fall back to FFMA. */
+                                 FP32 bounds).  Filter table for H = 128 / 64 / 32, update block
+                                 for H = 128 (FFMA otherwise). */
     MLFFD_PREC_TF32 = 2,      /* reserved: single-pass TF32, looser bounds */
     MLFFD_PREC_BF16 = 3       /* reserved: single-pass BF16, looser bounds */
 };

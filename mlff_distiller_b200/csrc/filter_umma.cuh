@@ -36,18 +36,31 @@ constexpr int kUmmaComputeWarps = 16;
 constexpr int kUmmaComputeThreads = 32 * kUmmaComputeWarps;   // compute / epilogue warps
 constexpr int kUmmaThreads = kUmmaComputeThreads + 32;        // + 1 issuer warp
 constexpr uint32_t kKBlockBytes = 16384;       // 128 rows x 64 halves
-constexpr uint32_t kChunkImageBytes = 65536;   // hi kb0 | hi kb1 | lo kb0 | lo kb1
+constexpr uint32_t kChunkImageBytes = 65536;   // H = 128 image: hi kb0 | hi kb1 | lo kb0 | lo kb1
 constexpr uint32_t kTmemCols = 512;
 
-struct UmmaSmem {
+// Geometry of the tensor-core filter kernel for hidden size H (128, 64 or 32).
+//   KBLK   64-wide K blocks of the activation / weight tiles (H = 32 is zero-padded to 64)
+//   KSTEPS MMA K-steps (16 each) issued per K block
+//   NCH    128-channel output chunks covering the 3H filter channels (padded with zero rows)
+template <int H>
+struct UmmaGeom {
+    static constexpr int KBLK = (H > 64) ? H / 64 : 1;
+    static constexpr int KSTEPS = (H >= 64) ? 4 : H / 16;
+    static constexpr int NCH = (3 * H + 127) / 128;
+    static constexpr uint32_t TILE = KBLK * kKBlockBytes;          // one FP16 term of a 128-row tile
+    static constexpr uint32_t IMAGE = 2 * TILE;                    // hi | lo
+    static constexpr uint32_t TMEM_COLS = (NCH * 128 > 256) ? 512 : (NCH * 128 > 128 ? 256 : 128);
     static constexpr uint32_t A_HI = 0;
-    static constexpr uint32_t A_LO = 32768;
-    static constexpr uint32_t B0 = 65536;
-    static constexpr uint32_t B1 = 131072;
-    static constexpr uint32_t PHI = 196608;                                   // [64][33] f32
-    static constexpr uint32_t DPHI = PHI + kUmmaPairs * kPhiStride * 4;       // [64][33] f32
-    static constexpr uint32_t W1T = DPHI + kUmmaPairs * kPhiStride * 4;       // [K][128] f32
-    static constexpr uint32_t total(int K) { return W1T + (uint32_t)K * 128 * 4 + 512 /*b1*/ + 64 /*mbarriers, tmem base*/ + 512 /*cutoff per pair*/ + 1024 /*align*/; }
+    static constexpr uint32_t A_LO = TILE;
+    static constexpr uint32_t B0 = 2 * TILE;
+    static constexpr uint32_t B1 = B0 + IMAGE;
+    static constexpr uint32_t PHI = B1 + IMAGE;                                // [64][33] f32
+    static constexpr uint32_t DPHI = PHI + kUmmaPairs * kPhiStride * 4;        // [64][33] f32
+    static constexpr uint32_t W1T = DPHI + kUmmaPairs * kPhiStride * 4;        // [K][H] f32
+    static constexpr uint32_t total(int K) {
+        return W1T + (uint32_t)K * H * 4 + H * 4 /*b1*/ + 64 /*mbarriers, tmem base*/ + 512 /*cutoff per pair*/ + 1024 /*align*/;
+    }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -152,14 +165,15 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int chunk) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
 }
 
+template <int H>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restrict__ num_pairs_ptr,
                          int num_pairs_arg, const DeviceStatus* __restrict__ status,
                          const float* __restrict__ centers, const float* __restrict__ gammas, int K,
                          float rc, FilterWeights w, const uint8_t* __restrict__ w2_images,
                          int skip_vector_gate, float* __restrict__ filt, float* __restrict__ dfilt) {
-    constexpr int H = 128;
-    constexpr int CPT = H / (kUmmaComputeThreads / kUmmaPairs);   // channels per thread (16)
+    using G = UmmaGeom<H>;
+    constexpr int CPT = H / (kUmmaComputeThreads / kUmmaPairs);   // channels per thread (16 / 8 / 4)
     if (status != nullptr && status->overflow) return;
     const int P = (num_pairs_ptr != nullptr) ? *num_pairs_ptr : num_pairs_arg;
     const int num_tiles = (P + kUmmaPairs - 1) / kUmmaPairs;
@@ -169,9 +183,9 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
     // computed in the shared address space and every access below stays an LDS/STS.
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* phi_s = (float*)(smem + UmmaSmem::PHI);
-    float* dphi_s = (float*)(smem + UmmaSmem::DPHI);
-    float* w1t_s = (float*)(smem + UmmaSmem::W1T);
+    float* phi_s = (float*)(smem + G::PHI);
+    float* dphi_s = (float*)(smem + G::DPHI);
+    float* w1t_s = (float*)(smem + G::W1T);
     float* b1_s = w1t_s + K * H;
     uint64_t* bars = (uint64_t*)(b1_s + H);          // a_full, b_full[2], d_full[3]
     uint64_t* bar_a_full = bars;
@@ -181,7 +195,10 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
     float2* cut_s = (float2*)(bars + 8);             // [64] cutoff value and derivative per pair
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nchunks = skip_vector_gate ? 2 : 3;
+    // layer 0 never reads the b gate (v_in = 0): for H = 128 that is exactly chunk 1, skipped
+    // entirely; for smaller H the chunks mix gates, so only the stores are skipped.
+    const bool skip_chunk1 = skip_vector_gate && H == 128;
+    const int nchunks = skip_chunk1 ? 2 : G::NCH;
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     // ---- one-time setup ----
@@ -192,16 +209,16 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
             // start streaming the first two weight chunks before anything else (latency path)
             const int total0 = my_tiles * nchunks;
             for (int g = 0; g < 2 && g < total0; ++g) {
-                mbar_expect_tx(&bar_b_full[g], kChunkImageBytes);
-                const int cid = skip_vector_gate ? (g % nchunks) * 2 : (g % nchunks);
-                const uint8_t* src = w2_images + (size_t)cid * kChunkImageBytes;
-                const uint32_t dst = smem_u32(smem + (g ? UmmaSmem::B1 : UmmaSmem::B0));
-                for (int qq = 0; qq < 4; ++qq)
-                    bulk_g2s(dst + qq * kKBlockBytes, src + qq * kKBlockBytes, kKBlockBytes, &bar_b_full[g]);
+                mbar_expect_tx(&bar_b_full[g], G::IMAGE);
+                const int cid = skip_chunk1 ? (g % nchunks) * 2 : (g % nchunks);
+                const uint8_t* src = w2_images + (size_t)cid * G::IMAGE;
+                const uint32_t dst = smem_u32(smem + (g ? G::B1 : G::B0));
+                for (uint32_t off = 0; off < G::IMAGE; off += kKBlockBytes)
+                    bulk_g2s(dst + off, src + off, kKBlockBytes, &bar_b_full[g]);
             }
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(kTmemCols));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(G::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     } else {
         for (int idx = tid; idx < K * H / 4; idx += kUmmaComputeThreads) st4(w1t_s + 4 * idx, ldg4(w.W1t + 4 * idx));
@@ -216,20 +233,19 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
         // =============================== issuer ===============================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t b_buf[2] = {smem_u32(smem + UmmaSmem::B0), smem_u32(smem + UmmaSmem::B1)};
+            const uint32_t b_buf[2] = {smem_u32(smem + G::B0), smem_u32(smem + G::B1)};
             // every operand descriptor is a constant plus a small offset in the 16-byte address field
-            const uint64_t act_desc_hi = umma_desc_sw128(smem_u32(smem + UmmaSmem::A_HI));
-            const uint64_t act_desc_lo = umma_desc_sw128(smem_u32(smem + UmmaSmem::A_LO));
+            const uint64_t act_desc_hi = umma_desc_sw128(smem_u32(smem + G::A_HI));
+            const uint64_t act_desc_lo = umma_desc_sw128(smem_u32(smem + G::A_LO));
             const uint64_t w_desc0 = umma_desc_sw128(b_buf[0]);
             const int total_chunks = my_tiles * nchunks;
-            auto chunk_id = [&](int g) { const int ci = g % nchunks; return skip_vector_gate ? ci * 2 : ci; };
+            auto chunk_id = [&](int g) { const int ci = g % nchunks; return skip_chunk1 ? ci * 2 : ci; };
             auto issue_load = [&](int g) {
                 const int buf = g & 1;
-                mbar_expect_tx(&bar_b_full[buf], kChunkImageBytes);
-                const uint8_t* src = w2_images + (size_t)chunk_id(g) * kChunkImageBytes;
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq)
-                    bulk_g2s(b_buf[buf] + qq * kKBlockBytes, src + qq * kKBlockBytes, kKBlockBytes, &bar_b_full[buf]);
+                mbar_expect_tx(&bar_b_full[buf], G::IMAGE);
+                const uint8_t* src = w2_images + (size_t)chunk_id(g) * G::IMAGE;
+                for (uint32_t off = 0; off < G::IMAGE; off += kKBlockBytes)
+                    bulk_g2s(b_buf[buf] + off, src + off, kKBlockBytes, &bar_b_full[buf]);
             };
             for (int g = 0; g < total_chunks; ++g) {   // chunks 0 and 1 were requested during set-up
                 const int it = g / nchunks, ci = g - it * nchunks, nc = chunk_id(g), buf = g & 1;
@@ -239,19 +255,19 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                 }
                 mbar_wait(&bar_b_full[buf], (g >> 1) & 1);
                 const uint32_t d_tmem = tmem_base + (uint32_t)nc * 128;
-                const uint64_t w_desc = w_desc0 + (uint64_t)(buf ? (kChunkImageBytes >> 4) : 0);
+                const uint64_t w_desc = w_desc0 + (uint64_t)(buf ? (G::IMAGE >> 4) : 0);
                 uint32_t acc = 0;
-#pragma unroll
                 // The tensor core accumulates with truncation, a bias that grows with the number of
                 // additions into a LARGE accumulator: the two small correction products go first
-                // (accumulator still ~2^-11 of its final size), the 8 main MMAs last.
+                // (accumulator still ~2^-11 of its final size), the main MMAs last.
+#pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {   // W_hi*act_lo, W_lo*act_hi, W_hi*act_hi
                     const uint64_t act_base = (pass == 0) ? act_desc_lo : act_desc_hi;
-                    const uint64_t w_base = w_desc + (uint64_t)((pass == 1) ? ((2 * kKBlockBytes) >> 4) : 0);
+                    const uint64_t w_base = w_desc + (uint64_t)((pass == 1) ? (G::TILE >> 4) : 0);
 #pragma unroll
-                    for (int kb = 0; kb < 2; ++kb)
+                    for (int kb = 0; kb < G::KBLK; ++kb)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < G::KSTEPS; ++k) {
                             const uint64_t off = (uint64_t)((kb * kKBlockBytes + k * 32) >> 4);
                             // transposed product: A operand = weight chunk (M = 128 channels),
                             // B operand = activation tile (N = 128 rows)
@@ -272,17 +288,19 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
         // ========================= compute / epilogue =========================
         // Software pipeline: the FFMA first layer of tile it+1 runs while the tensor cores work on
         // tile it; only the final split + store into the (single) activation tile waits for them.
-        const int p = tid & 63, cg = tid >> 6;          // pair within tile, 16-channel group (0..7)
+        const int p = tid & 63, cg = tid >> 6;          // pair within tile, channel group (0..7)
         const int q = warp & 3, cs = warp >> 2;         // TMEM lane quarter (channels), row segment
         float y[CPT], z[CPT];
-        float bias[3];
+        float bias[G::NCH];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) bias[c] = __ldg(w.b2 + c * 128 + q * 32 + lane);
+        for (int c = 0; c < G::NCH; ++c) {
+            const int gch = c * 128 + q * 32 + lane;
+            bias[c] = (gch < 3 * H) ? __ldg(w.b2 + gch) : 0.f;
+        }
 
         auto first_layer = [&](int it) {
             const int p0 = ((int)blockIdx.x + it * (int)gridDim.x) * kUmmaPairs;
-            // cutoff value/derivative once per pair (not per basis function): lanes with the same
-            // pair recompute it at most ceil(K / (threads per pair)) times instead of K times
+            // cutoff value/derivative once per pair (not per basis function)
             for (int idx = tid; idx < kUmmaPairs * K; idx += kUmmaComputeThreads) {
                 const int pp = idx / K, k = idx - pp * K;
                 const float d = (p0 + pp < P) ? __ldg(pair_dist + p0 + pp) : rc;
@@ -324,28 +342,45 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
             }
         };
         auto publish_tile = [&]() {   // SiLU / tangent, two-term split, swizzled store, hand-off
-            const int kb = cg >> 2;                    // channels 0..63 -> K-block 0, 64..127 -> 1
-            uint8_t* a_hi = smem + UmmaSmem::A_HI + kb * kKBlockBytes;
-            uint8_t* a_lo = smem + UmmaSmem::A_LO + kb * kKBlockBytes;
+            const int ch0 = cg * CPT;                  // first channel (= K index) of this thread
+            const int kb = ch0 >> 6;                   // 64-wide K block
+            uint8_t* a_hi = smem + G::A_HI + kb * kKBlockBytes;
+            uint8_t* a_lo = smem + G::A_LO + kb * kKBlockBytes;
+            float hv[CPT], tv[CPT];
 #pragma unroll
-            for (int j = 0; j < CPT / 8; ++j) {
-                float hv[8], tv[8];
+            for (int i = 0; i < CPT; ++i) {
+                const float yy = y[i];
+                const float sg = sigmoidf_(yy);
+                hv[i] = yy * sg;
+                tv[i] = sg * (1.0f + yy * (1.0f - sg)) * z[i];
+            }
+            if constexpr (CPT >= 8) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float yy = y[8 * j + i];
-                    const float sg = sigmoidf_(yy);
-                    hv[i] = yy * sg;
-                    tv[i] = sg * (1.0f + yy * (1.0f - sg)) * z[8 * j + i];
+                for (int j = 0; j < CPT / 8; ++j) {
+                    float h8[8], t8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { h8[i] = hv[8 * j + i]; t8[i] = tv[8 * j + i]; }
+                    const int chunk = ((ch0 & 63) >> 3) + j;
+                    uint4 hi, lo;
+                    split8(h8, hi, lo);
+                    const uint32_t oh = sw128_offset(p, chunk), ot = sw128_offset(kUmmaPairs + p, chunk);
+                    *reinterpret_cast<uint4*>(a_hi + oh) = hi;
+                    *reinterpret_cast<uint4*>(a_lo + oh) = lo;
+                    split8(t8, hi, lo);
+                    *reinterpret_cast<uint4*>(a_hi + ot) = hi;
+                    *reinterpret_cast<uint4*>(a_lo + ot) = lo;
                 }
-                const int chunk = (cg & 3) * (CPT / 8) + j;
-                uint4 hi, lo;
-                split8(hv, hi, lo);
-                const uint32_t oh = sw128_offset(p, chunk), ot = sw128_offset(kUmmaPairs + p, chunk);
-                *reinterpret_cast<uint4*>(a_hi + oh) = hi;
-                *reinterpret_cast<uint4*>(a_lo + oh) = lo;
-                split8(tv, hi, lo);
-                *reinterpret_cast<uint4*>(a_hi + ot) = hi;
-                *reinterpret_cast<uint4*>(a_lo + ot) = lo;
+            } else {   // 4 channels per thread: half of a 16-byte chunk
+                const int chunk = (ch0 & 63) >> 3;
+                const uint32_t half8 = (uint32_t)(ch0 & 4) * 2;
+                uint2 hi, lo;
+                split4(make_float4(hv[0], hv[1], hv[2], hv[3]), hi, lo);
+                const uint32_t oh = sw128_offset(p, chunk) + half8, ot = sw128_offset(kUmmaPairs + p, chunk) + half8;
+                *reinterpret_cast<uint2*>(a_hi + oh) = hi;
+                *reinterpret_cast<uint2*>(a_lo + oh) = lo;
+                split4(make_float4(tv[0], tv[1], tv[2], tv[3]), hi, lo);
+                *reinterpret_cast<uint2*>(a_hi + ot) = hi;
+                *reinterpret_cast<uint2*>(a_lo + ot) = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -361,20 +396,25 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
             // ---- epilogue of tile `it`: D[channel = lane][row = column] -> global ----
             const bool tangent = cs >= 2;                      // rows 64..127 hold f'
             const int row0 = p0 + (cs & 1) * 32;               // first pair of this warp's 32 rows
-            float* out = (tangent ? dfilt : filt) + (size_t)row0 * (3 * H) + q * 32 + lane;
+            float* out = (tangent ? dfilt : filt) + (size_t)row0 * (3 * H);
             for (int ci = 0; ci < nchunks; ++ci) {
-                const int nc = skip_vector_gate ? ci * 2 : ci;
+                const int nc = skip_chunk1 ? ci * 2 : ci;
                 mbar_wait(&bar_d_full[nc], it & 1);
                 __syncwarp();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(nc * 128 + cs * 32), r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const float b = tangent ? 0.f : bias[nc];
-                float* o = out + nc * 128;
+                const int gch = nc * 128 + q * 32 + lane;       // filter channel of this lane
+                bool store = gch < 3 * H;
+                if (skip_vector_gate && gch >= H && gch < 2 * H) store = false;   // unused b gate of layer 0
+                if (store) {
+                    const float b = tangent ? 0.f : bias[nc];
+                    float* o = out + gch;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (row0 + j < P) __stcs(o + (size_t)j * (3 * H), fmaf(__uint_as_float(r[j]), kAccUnscale, b));
+                    for (int j = 0; j < 32; ++j)
+                        if (row0 + j < P) __stcs(o + (size_t)j * (3 * H), fmaf(__uint_as_float(r[j]), kAccUnscale, b));
+                }
             }
             // all MMAs of tile `it` are complete (last chunk waited): the activation tile is free
             if (it + 1 < my_tiles) publish_tile();
@@ -384,7 +424,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
     __syncthreads();
     if (warp == kUmmaComputeWarps) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(G::TMEM_COLS));
     }
 }
 

@@ -82,7 +82,8 @@ struct mlffd_ctx {
     std::string err;
     float* weights_d = nullptr;
     uint8_t* w2_images_d = nullptr;   // swizzled fp16 hi/lo 64 KB weight images (tensor-core path)
-    bool use_umma = false;
+    bool use_umma = false;          // tensor-core update block (H = 128)
+    bool use_umma_filter = false;   // tensor-core filter table (H = 128, 64, 32)
     struct ImageOffsets { size_t filter, upd_f1, upd_f2, upd_b1, upd_b2; } img[kMaxLayers] = {};
     const float *emb = nullptr, *centers = nullptr, *gammas = nullptr;
     LayerWeights layer[kMaxLayers];
@@ -216,17 +217,14 @@ template <int H>
 int launch_filter(mlffd_ctx* ctx, int l, const float* dist, const int* num_pairs_ptr,
                   int num_pairs_arg, const DeviceStatus* status, float* filt, float* dfilt,
                   int64_t pair_bound, cudaStream_t st) {
-    if constexpr (H == 128) {
-        if (ctx->use_umma) {
-            const int grid = clamp_grid(ceil_div(std::max<int64_t>(pair_bound, 1), kUmmaPairs), kNumSMs);
-            filter_table_umma_kernel<<<grid, kUmmaThreads, UmmaSmem::total(ctx->K), st>>>(
-                dist, num_pairs_ptr, num_pairs_arg, status, ctx->centers, ctx->gammas, ctx->K,
-                ctx->cfg.cutoff, ctx->layer[l].filter,
-                ctx->w2_images_d + ctx->img[l].filter,
-                (l == 0 && status != nullptr) ? 1 : 0, filt, dfilt);
-            LAUNCHED(ctx, "filter_table_umma_kernel", MLFFD_STAGE_FILTER, st);
-            return MLFFD_OK;
-        }
+    if (ctx->use_umma_filter) {
+        const int grid = clamp_grid(ceil_div(std::max<int64_t>(pair_bound, 1), kUmmaPairs), kNumSMs);
+        filter_table_umma_kernel<H><<<grid, kUmmaThreads, UmmaGeom<H>::total(ctx->K), st>>>(
+            dist, num_pairs_ptr, num_pairs_arg, status, ctx->centers, ctx->gammas, ctx->K,
+            ctx->cfg.cutoff, ctx->layer[l].filter, ctx->w2_images_d + ctx->img[l].filter,
+            (l == 0 && status != nullptr) ? 1 : 0, filt, dfilt);
+        LAUNCHED(ctx, "filter_table_umma_kernel", MLFFD_STAGE_FILTER, st);
+        return MLFFD_OK;
     }
     const int blocks_per_sm = (filter_smem_bytes<H>() <= 110 * 1024) ? 2 : 1;
     const int grid = clamp_grid(ceil_div(std::max<int64_t>(pair_bound, 1), kFilterPairs),
@@ -583,15 +581,18 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     e = cudaMalloc(&ctx->status_d, sizeof(DeviceStatus));
     if (e != cudaSuccess) return bail(MLFFD_ENOMEM, cudaGetErrorString(e));
     cudaMemset(ctx->status_d, 0, sizeof(DeviceStatus));
-    if (config->precision == MLFFD_PREC_TC_FP16X2 && H == 128) {
-        // 64 KB K-major SWIZZLE_128B images of 128x128 blocks of an [out][in] matrix:
-        // [hi kb0 | hi kb1 | lo kb0 | lo kb1], each 128 rows x 64 halves (see filter_umma.cuh).
+    if (config->precision == MLFFD_PREC_TC_FP16X2) {
+        // K-major SWIZZLE_128B images of 128-row blocks of an [out][in] matrix:
+        // [hi kb0 .. | lo kb0 ..], each K block 128 rows x 64 halves (see filter_umma.cuh); rows or
+        // columns beyond the matrix are zero.
         std::vector<__half> img;
-        auto add_image = [&](const float* Wm, int ld, int r0, int c0) {
+        auto add_image = [&](const float* Wm, int ld, int rows, int cols, int r0, int c0, int kblk) {
             const size_t base = img.size();
-            img.resize(base + kChunkImageBytes / 2);
+            const size_t term = (size_t)kblk * (kKBlockBytes / 2);
+            img.resize(base + 2 * term, __float2half_rn(0.f));
             for (int r = 0; r < 128; ++r)
-                for (int k = 0; k < 128; ++k) {
+                for (int k = 0; k < kblk * 64; ++k) {
+                    if (r0 + r >= rows || c0 + k >= cols) continue;
                     const float x = Wm[(size_t)(r0 + r) * ld + c0 + k] * kWeightScale;
                     const __half hi = __float2half_rn(x);
                     const __half lo = __float2half_rn(x - __half2float(hi));
@@ -599,39 +600,48 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
                     const size_t off = (size_t)(r / 8) * 512 + (size_t)(r % 8) * 64 +
                                        (size_t)(((kc / 8) ^ (r % 8)) * 8) + (size_t)(kc % 8);
                     img[base + (size_t)kb * (kKBlockBytes / 2) + off] = hi;
-                    img[base + (size_t)(2 + kb) * (kKBlockBytes / 2) + off] = lo;
+                    img[base + term + (size_t)kb * (kKBlockBytes / 2) + off] = lo;
                 }
             return base * sizeof(__half);
         };
         const float* q = weights_host + (size_t)(config->max_z + 1) * H + 2 * K;
+        const int fkblk = (H > 64) ? H / 64 : 1;
+        const int fchunks = (3 * H + 127) / 128;
         std::vector<float> M1T((size_t)2 * H * H), M2T((size_t)H * 3 * H);
         for (int l = 0; l < L; ++l) {
             const float* W2 = q + (size_t)H * K + H;                       // filter layer 2 [3H][H]
             const float* M1 = W2 + (size_t)3 * H * H + 3 * H;              // update_mlp.0 [H][2H]
             const float* M2 = M1 + (size_t)H * 2 * H + H;                  // update_mlp.2 [3H][H]
-            for (int r = 0; r < H; ++r)
-                for (int c = 0; c < 2 * H; ++c) M1T[(size_t)c * H + r] = M1[(size_t)r * 2 * H + c];
-            for (int r = 0; r < 3 * H; ++r)
-                for (int c = 0; c < H; ++c) M2T[(size_t)c * 3 * H + r] = M2[(size_t)r * H + c];
-            ctx->img[l].filter = add_image(W2, H, 0, 0);
-            add_image(W2, H, 128, 0); add_image(W2, H, 256, 0);
-            ctx->img[l].upd_f1 = add_image(M1, 2 * H, 0, 0);               // [ks][c]: W = M1 [H][2H]
-            add_image(M1, 2 * H, 0, 128);
-            ctx->img[l].upd_f2 = add_image(M2, H, 0, 0);                   // W = M2 [3H][H]
-            add_image(M2, H, 128, 0); add_image(M2, H, 256, 0);
-            ctx->img[l].upd_b1 = add_image(M2T.data(), 3 * H, 0, 0);       // W = M2^T [H][3H]
-            add_image(M2T.data(), 3 * H, 0, 128); add_image(M2T.data(), 3 * H, 0, 256);
-            ctx->img[l].upd_b2 = add_image(M1T.data(), H, 0, 0);           // W = M1^T [2H][H]
-            add_image(M1T.data(), H, 128, 0);
+            for (int c = 0; c < fchunks; ++c) {
+                const size_t off = add_image(W2, H, 3 * H, H, c * 128, 0, fkblk);
+                if (c == 0) ctx->img[l].filter = off;
+            }
+            if (H == 128) {
+                for (int r = 0; r < H; ++r)
+                    for (int c = 0; c < 2 * H; ++c) M1T[(size_t)c * H + r] = M1[(size_t)r * 2 * H + c];
+                for (int r = 0; r < 3 * H; ++r)
+                    for (int c = 0; c < H; ++c) M2T[(size_t)c * 3 * H + r] = M2[(size_t)r * H + c];
+                ctx->img[l].upd_f1 = add_image(M1, 2 * H, H, 2 * H, 0, 0, 2);          // [ks][c]: W = M1 [H][2H]
+                add_image(M1, 2 * H, H, 2 * H, 0, 128, 2);
+                ctx->img[l].upd_f2 = add_image(M2, H, 3 * H, H, 0, 0, 2);              // W = M2 [3H][H]
+                add_image(M2, H, 3 * H, H, 128, 0, 2); add_image(M2, H, 3 * H, H, 256, 0, 2);
+                ctx->img[l].upd_b1 = add_image(M2T.data(), 3 * H, H, 3 * H, 0, 0, 2);  // W = M2^T [H][3H]
+                add_image(M2T.data(), 3 * H, H, 3 * H, 0, 128, 2); add_image(M2T.data(), 3 * H, H, 3 * H, 0, 256, 2);
+                ctx->img[l].upd_b2 = add_image(M1T.data(), H, 2 * H, H, 0, 0, 2);      // W = M1^T [2H][H]
+                add_image(M1T.data(), H, 2 * H, H, 128, 0, 2);
+            }
             q += per_layer;
         }
         e = cudaMalloc(&ctx->w2_images_d, img.size() * sizeof(__half));
         if (e != cudaSuccess) return bail(MLFFD_ENOMEM, cudaGetErrorString(e));
         e = cudaMemcpy(ctx->w2_images_d, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
-        e = cudaFuncSetAttribute(filter_table_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)UmmaSmem::total(K));
+        if (H == 128) e = cudaFuncSetAttribute(filter_table_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<128>::total(K));
+        else if (H == 64) e = cudaFuncSetAttribute(filter_table_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<64>::total(K));
+        else e = cudaFuncSetAttribute(filter_table_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<32>::total(K));
         if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
+        ctx->use_umma_filter = true;
+        if (H == 128) {
 #define SET_ROWS_ATTR(OP)                                                                            \
         e = cudaFuncSetAttribute(umma_rows_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  (int)UmmaRowsSmem::TOTAL);                                          \
@@ -640,7 +650,8 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
         SET_ROWS_ATTR(UpdateBwd1Op<false>) SET_ROWS_ATTR(UpdateBwd1Op<true>)
         SET_ROWS_ATTR(UpdateBwd2Op<false>) SET_ROWS_ATTR(UpdateBwd2Op<true>)
 #undef SET_ROWS_ATTR
-        ctx->use_umma = true;
+            ctx->use_umma = true;
+        }
     }
     const float* W = ctx->weights_d;
     ctx->emb = W + o_emb; ctx->centers = W + o_centers; ctx->gammas = W + o_gammas;

@@ -311,9 +311,10 @@ def test_edge_capacity_overflow_recovers(variant):
 # ---------------------------------------------------------------------------------------------
 # tensor-core path (tcgen05, two-term FP16 split): must meet the SAME FP32 bounds
 # ---------------------------------------------------------------------------------------------
-def test_tensor_core_filter_table_matches_ffma_and_oracle():
-    model_tc, state, cfg = _model("original", precision="tc")
-    model_32, _, _ = _model("original", precision="fp32")
+@pytest.mark.parametrize("variant_name", ["original", "tiny", "ultra_tiny"])
+def test_tensor_core_filter_table_matches_ffma_and_oracle(variant_name):
+    model_tc, state, cfg = _model(variant_name, precision="tc")
+    model_32, _, _ = _model(variant_name, precision="fp32")
     rc = cfg["cutoff"]
     d = torch.cat([torch.linspace(0.4, rc + 0.3, 4099), torch.tensor([rc, rc - 1e-6, 0.9572])]).float()
     for l in range(cfg["num_interactions"]):
