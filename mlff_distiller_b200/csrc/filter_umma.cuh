@@ -1,26 +1,40 @@
-// Filter table on the 5th-generation tensor cores (tcgen05 / TMEM), H = 128.
+// Filter table on the 5th-generation tensor cores (tcgen05 / TMEM), H = 128 / 64 / 32.
 //
 // Same contract as filter_table_kernel (filter.cuh): for a tile of 64 undirected pairs compute
-// f(d) and f'(d) in R^{3H}.  The second dense layer  [h; t] (128 rows x K=128)  x  W2^T (K x 384)
-// runs as tcgen05.mma kind::f16 with FP32 accumulation in tensor memory.  To keep FP32-grade
-// accuracy (north-star: 1e-5 eV/atom, 1e-4 eV/A) both operands are split into two FP16 terms,
-// x = x_hi + x_lo with x_lo = fp16(x - x_hi)  (22 significand bits), and three products are
-// accumulated:  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is ~2^-22 relative).  Each FP16
-// product is exact in the FP32 accumulator, so the result differs from an FP32 FFMA GEMM only by
-// accumulation-order rounding.  Cost: 3 MMAs at the FP16 rate = 1.5 TF32-rate passes, 4 bytes per
-// operand element (same footprint as one TF32 operand).
+// f(d) and f'(d) in R^{3H}.  BOTH dense layers run as tcgen05.mma kind::f16 with FP32
+// accumulation in tensor memory:
+//   layer 1:  D1[channel][row] = W1 (H x 32, K = num_rbf padded)  x  [phi~ ; phi~']^T   (128 rows)
+//   layer 2:  D2[channel][row] = W2 chunk (128 x H)               x  [h ; t]^T          (128 rows)
+// with h = SiLU(y), t = SiLU'(y) * z the value / tangent of the hidden layer (y, z = the two row
+// halves of D1).  To keep FP32-grade accuracy (north-star: 1e-5 eV/atom, 1e-4 eV/A) both operands
+// of every product are split into two FP16 terms, x = x_hi + x_lo with x_lo = fp16(x - x_hi)
+// (22 significand bits), and three products are accumulated: lo*hi + hi*lo + hi*hi (the dropped
+// lo*lo term is ~2^-22 relative).  Each FP16 product is exact in the FP32 accumulator, so the
+// result differs from an FP32 FFMA GEMM only by accumulation-order rounding.
 //
-// Roles (544 threads, one persistent CTA per SM):
-//   warps 0-15 compute: RBF + first layer (FFMA, registers) -> split -> swizzled activation tile
-//              in smem; then epilogue: tcgen05.ld accumulator -> + bias -> global.  The GEMM is
-//              issued TRANSPOSED (D[channel][row] = W2_chunk x act^T: the weight image is the A
-//              operand, the activation tile the B operand), so a TMEM lane is an output channel
-//              and the 32 lanes of a warp store 128 contiguous bytes of one filter row.
-//   warp 16    issuer (one lane): streams the pre-swizzled W2 chunk images (64 KB each: hi/lo x 2
-//              K-blocks) from L2 with cp.async.bulk into a 2-deep ring, issues the 24 MMAs of a
-//              128-channel chunk, commits to an mbarrier per chunk so the epilogue of chunk c
-//              overlaps the MMAs of chunk c+1.  The first layer of tile t+1 overlaps the MMAs of
-//              tile t (software pipeline in the compute warps).
+// Both GEMMs are issued TRANSPOSED (the weight image is the A operand, the activation tile the B
+// operand), so a TMEM lane is a channel: the first-layer epilogue applies bias / SiLU per lane,
+// and the second-layer epilogue stores 128 contiguous bytes of one filter row per warp
+// instruction.
+//
+// Roles (576 threads, one persistent CTA per SM):
+//   warps 0-15 compute: RBF x cutoff (and derivative) -> split -> B tile of layer 1;  D1 -> SiLU /
+//              tangent -> split -> B tile of layer 2 (same shared memory: K block 0 of the
+//              activation tile is free between the layer-2 MMAs of two tiles);  D2 -> + bias ->
+//              global.  The RBF math of tile t+1 runs while the tensor cores work on chunk 0 of
+//              tile t.
+//   warp 16    issuer (one lane): 6 MMAs of layer 1, then the 24 MMAs of each 128-channel chunk of
+//              layer 2, committing to an mbarrier per chunk so the epilogue of chunk c overlaps
+//              the MMAs of chunk c+1.
+//   warp 17    weight loader (one lane): streams the pre-swizzled W2 chunk images (64 KB each:
+//              hi/lo x 2 K-blocks) from L2 with cp.async.bulk into a 2-deep ring; chunk g is
+//              requested the moment the MMAs of chunk g-2 have completed.  (When the issuer did
+//              this itself every chunk exposed ~2.1k cycles of load latency: tcgen05.mma issue
+//              blocks while the tensor-core queue is full, so its refill was always late.)
+//   The layer-1 weight image (32 KB) stays resident in shared memory.
+// Measured per 64-pair tile on a B200 (C2, -DMLFFD_FILTER_TIMING): epilogue stores 7.8k cycles
+// (196 KB at ~25 B/clk/SM: the SM's store path), publish 3.6k, RBF + chunk-0 MMA wait 2.5k,
+// layer-1 round trip 0.7k; the tensor pipe is busy ~40 % of the time.
 // Operand layout: K-major, SWIZZLE_128B (8-row x 128-byte atoms, 16-byte chunk c of row r stored
 // at c ^ (r % 8)), descriptor SBO = 1024 B, version 1; instruction descriptor M=128, N=128, F16
 // inputs, F32 accumulate.  Encodings pinned by tools/umma_test.cu on a B200.
@@ -35,6 +49,7 @@ constexpr int kUmmaPairs = 64;                 // pairs per tile -> 128 GEMM row
 constexpr int kUmmaComputeWarps = 16;
 constexpr int kUmmaComputeThreads = 32 * kUmmaComputeWarps;   // compute / epilogue warps
 constexpr int kUmmaThreads = kUmmaComputeThreads + 32;        // + 1 issuer warp
+constexpr int kFilterUmmaThreads = kUmmaComputeThreads + 64;  // filter table: + issuer warp + weight-loader warp
 constexpr uint32_t kKBlockBytes = 16384;       // 128 rows x 64 halves
 constexpr uint32_t kChunkImageBytes = 65536;   // H = 128 image: hi kb0 | hi kb1 | lo kb0 | lo kb1
 constexpr uint32_t kTmemCols = 512;
@@ -43,6 +58,11 @@ constexpr uint32_t kTmemCols = 512;
 //   KBLK   64-wide K blocks of the activation / weight tiles (H = 32 is zero-padded to 64)
 //   KSTEPS MMA K-steps (16 each) issued per K block
 //   NCH    128-channel output chunks covering the 3H filter channels (padded with zero rows)
+// Shared memory: activation tile (hi | lo), two-deep ring of second-layer weight chunks, the
+// resident first-layer weight image (hi | lo, one K block: num_rbf <= 32 padded with zeros), tail
+// (mbarriers, TMEM base, RBF centres / gammas).  The RBF tile of the first-layer GEMM lives in K
+// block 0 of the activation tile (free between the second-layer MMAs of two tiles).
+constexpr int kUmmaMaxRbf = 32;
 template <int H>
 struct UmmaGeom {
     static constexpr int KBLK = (H > 64) ? H / 64 : 1;
@@ -50,17 +70,16 @@ struct UmmaGeom {
     static constexpr int NCH = (3 * H + 127) / 128;
     static constexpr uint32_t TILE = KBLK * kKBlockBytes;          // one FP16 term of a 128-row tile
     static constexpr uint32_t IMAGE = 2 * TILE;                    // hi | lo
-    static constexpr uint32_t TMEM_COLS = (NCH * 128 > 256) ? 512 : (NCH * 128 > 128 ? 256 : 128);
+    static constexpr uint32_t D1_COL = NCH * 128;                  // first-layer accumulator columns
+    static constexpr uint32_t TMEM_COLS = (D1_COL + 128 > 256) ? 512 : 256;
     static constexpr uint32_t A_HI = 0;
     static constexpr uint32_t A_LO = TILE;
     static constexpr uint32_t B0 = 2 * TILE;
     static constexpr uint32_t B1 = B0 + IMAGE;
-    static constexpr uint32_t PHI = B1 + IMAGE;                                // [64][33] f32
-    static constexpr uint32_t DPHI = PHI + kUmmaPairs * kPhiStride * 4;        // [64][33] f32
-    static constexpr uint32_t W1T = DPHI + kUmmaPairs * kPhiStride * 4;        // [K][H] f32
-    static constexpr uint32_t total(int K) {
-        return W1T + (uint32_t)K * H * 4 + H * 4 /*b1*/ + 64 /*mbarriers, tmem base*/ + 512 /*cutoff per pair*/ + 1024 /*align*/;
-    }
+    static constexpr uint32_t W1_HI = B1 + IMAGE;
+    static constexpr uint32_t W1_LO = W1_HI + kKBlockBytes;
+    static constexpr uint32_t TAIL = W1_LO + kKBlockBytes;         // 10 mbarriers, tmem base, centres, gammas
+    static constexpr uint32_t total() { return TAIL + 128 + 2 * kUmmaMaxRbf * 4 + 1024 /*align*/; }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,6 +138,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
 // Power-of-two pre-scaling keeps the low FP16 term out of the subnormal range (an unscaled term
 // below 6e-5 would be quantised to 2^-24 absolute): activations are split as 2^3 x, weights as
 // 2^8 w, and the epilogue multiplies the FP32 accumulator by 2^-11 (all exact).
@@ -165,15 +192,34 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int chunk) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
 }
 
+// Phase timing for tuning (nvcc -DMLFFD_FILTER_TIMING): warp 0 of block 0 prints the cycles it
+// spent in each phase of the compute / epilogue role.
+#ifdef MLFFD_FILTER_TIMING
+#define FT_DECL long long ft_acc[6] = {0, 0, 0, 0, 0, 0}; long long ft_t = clock64();
+#define FT_MARK(i) { const long long ft_n = clock64(); ft_acc[i] += ft_n - ft_t; ft_t = ft_n; }
+#define FT_PRINT if (blockIdx.x == 0 && tid == 0) printf("filter phases (cycles, %d tiles): wait_d %lld  epilogue %lld  rbf %lld  wait_d1 %lld  publish %lld  sync %lld\n", my_tiles, ft_acc[0], ft_acc[1], ft_acc[2], ft_acc[3], ft_acc[4], ft_acc[5]);
+#else
+#define FT_DECL
+#define FT_MARK(i)
+#define FT_PRINT
+#endif
+
+// fp16 two-term split of one value, pre-scaled like split8
+__device__ __forceinline__ void split1(float x, __half& hi, __half& lo) {
+    x *= kActScale;
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+
 template <int H>
-__global__ void __launch_bounds__(kUmmaThreads, 1)
+__global__ void __launch_bounds__(kFilterUmmaThreads, 1)
 filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restrict__ num_pairs_ptr,
                          int num_pairs_arg, const DeviceStatus* __restrict__ status,
                          const float* __restrict__ centers, const float* __restrict__ gammas, int K,
-                         float rc, FilterWeights w, const uint8_t* __restrict__ w2_images,
-                         int skip_vector_gate, float* __restrict__ filt, float* __restrict__ dfilt) {
+                         float rc, FilterWeights w, const uint8_t* __restrict__ w1_image,
+                         const uint8_t* __restrict__ w2_images, int skip_vector_gate,
+                         float* __restrict__ filt, float* __restrict__ dfilt) {
     using G = UmmaGeom<H>;
-    constexpr int CPT = H / (kUmmaComputeThreads / kUmmaPairs);   // channels per thread (16 / 8 / 4)
     if (status != nullptr && status->overflow) return;
     const int P = (num_pairs_ptr != nullptr) ? *num_pairs_ptr : num_pairs_arg;
     const int num_tiles = (P + kUmmaPairs - 1) / kUmmaPairs;
@@ -183,16 +229,16 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
     // computed in the shared address space and every access below stays an LDS/STS.
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* phi_s = (float*)(smem + G::PHI);
-    float* dphi_s = (float*)(smem + G::DPHI);
-    float* w1t_s = (float*)(smem + G::W1T);
-    float* b1_s = w1t_s + K * H;
-    uint64_t* bars = (uint64_t*)(b1_s + H);          // a_full, b_full[2], d_full[3]
-    uint64_t* bar_a_full = bars;
-    uint64_t* bar_b_full = bars + 1;
-    uint64_t* bar_d_full = bars + 3;
-    uint32_t* tmem_base_s = (uint32_t*)(bars + 6);
-    float2* cut_s = (float2*)(bars + 8);             // [64] cutoff value and derivative per pair
+    uint64_t* bars = (uint64_t*)(smem + G::TAIL);
+    uint64_t* bar_a_full = bars;          // second-layer activation tile written
+    uint64_t* bar_b_full = bars + 1;      // [2] weight chunk landed
+    uint64_t* bar_d_full = bars + 3;      // [3] second-layer accumulator chunk complete
+    uint64_t* bar_phi_full = bars + 6;    // RBF tile written
+    uint64_t* bar_d1_full = bars + 7;     // first-layer accumulator complete
+    uint64_t* bar_w1_full = bars + 8;     // first-layer weight image landed (once)
+    uint32_t* tmem_base_s = (uint32_t*)(bars + 10);
+    float* cen_s = (float*)(smem + G::TAIL + 128);
+    float* gam_s = cen_s + kUmmaMaxRbf;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // layer 0 never reads the b gate (v_in = 0): for H = 128 that is exactly chunk 1, skipped
@@ -204,9 +250,12 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
     // ---- one-time setup ----
     if (warp == kUmmaComputeWarps) {
         if (lane == 0) {
-            for (int i = 0; i < 6; ++i) mbar_init(bars + i, 1);
+            for (int i = 0; i < 9; ++i) mbar_init(bars + i, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            // start streaming the first two weight chunks before anything else (latency path)
+            // start streaming the first-layer image and the first two weight chunks (latency path)
+            mbar_expect_tx(bar_w1_full, 2 * kKBlockBytes);
+            bulk_g2s(smem_u32(smem + G::W1_HI), w1_image, kKBlockBytes, bar_w1_full);
+            bulk_g2s(smem_u32(smem + G::W1_LO), w1_image + kKBlockBytes, kKBlockBytes, bar_w1_full);
             const int total0 = my_tiles * nchunks;
             for (int g = 0; g < 2 && g < total0; ++g) {
                 mbar_expect_tx(&bar_b_full[g], G::IMAGE);
@@ -220,9 +269,9 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(G::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    } else {
-        for (int idx = tid; idx < K * H / 4; idx += kUmmaComputeThreads) st4(w1t_s + 4 * idx, ldg4(w.W1t + 4 * idx));
-        for (int idx = tid; idx < H; idx += kUmmaComputeThreads) b1_s[idx] = __ldg(w.b1 + idx);
+    } else if (tid < kUmmaMaxRbf) {
+        cen_s[tid] = (tid < K) ? __ldg(centers + tid) : 0.f;
+        gam_s[tid] = (tid < K) ? __ldg(gammas + tid) : 0.f;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -237,29 +286,52 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
             // every operand descriptor is a constant plus a small offset in the 16-byte address field
             const uint64_t act_desc_hi = umma_desc_sw128(smem_u32(smem + G::A_HI));
             const uint64_t act_desc_lo = umma_desc_sw128(smem_u32(smem + G::A_LO));
+            const uint64_t w1_desc_hi = umma_desc_sw128(smem_u32(smem + G::W1_HI));
+            const uint64_t w1_desc_lo = umma_desc_sw128(smem_u32(smem + G::W1_LO));
             const uint64_t w_desc0 = umma_desc_sw128(b_buf[0]);
             const int total_chunks = my_tiles * nchunks;
             auto chunk_id = [&](int g) { const int ci = g % nchunks; return skip_chunk1 ? ci * 2 : ci; };
-            auto issue_load = [&](int g) {
-                const int buf = g & 1;
-                mbar_expect_tx(&bar_b_full[buf], G::IMAGE);
-                const uint8_t* src = w2_images + (size_t)chunk_id(g) * G::IMAGE;
-                for (uint32_t off = 0; off < G::IMAGE; off += kKBlockBytes)
-                    bulk_g2s(b_buf[buf] + off, src + off, kKBlockBytes, &bar_b_full[buf]);
-            };
+            mbar_wait(bar_w1_full, 0);
+#ifdef MLFFD_FILTER_TIMING
+            long long it_acc[5] = {0, 0, 0, 0, 0}, it_t = clock64();
+#define IT_MARK(i) { const long long n_ = clock64(); it_acc[i] += n_ - it_t; it_t = n_; }
+#else
+#define IT_MARK(i)
+#endif
             for (int g = 0; g < total_chunks; ++g) {   // chunks 0 and 1 were requested during set-up
                 const int it = g / nchunks, ci = g - it * nchunks, nc = chunk_id(g), buf = g & 1;
-                if (ci == 0) {  // activation tile `it` written; previous accumulators drained
+                if (ci == 0) {
+                    // first layer of tile `it`:  D1[channel][row] = W1 x [phi~ ; phi~']^T, K = 32.
+                    // The tensor core accumulates with truncation, a bias that grows with the number
+                    // of additions into a LARGE accumulator: the two small correction products go
+                    // first (accumulator still ~2^-11 of its final size), the main MMAs last.
+                    IT_MARK(4)
+                    mbar_wait(bar_phi_full, it & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    IT_MARK(0)
+                    uint32_t acc1 = 0;
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {   // W_hi*phi_lo, W_lo*phi_hi, W_hi*phi_hi
+                        const uint64_t phi_base = (pass == 0) ? act_desc_lo : act_desc_hi;
+                        const uint64_t w_base = (pass == 1) ? w1_desc_lo : w1_desc_hi;
+#pragma unroll
+                        for (int k = 0; k < kUmmaMaxRbf / 16; ++k) {
+                            umma_f16(tmem_base + G::D1_COL, w_base + (uint64_t)(k * 2), phi_base + (uint64_t)(k * 2), idesc, acc1);
+                            acc1 = 1;
+                        }
+                    }
+                    umma_commit(bar_d1_full);
+                    // activation tile `it` written (and with it the first-layer accumulator drained)
+                    IT_MARK(4)
                     mbar_wait(bar_a_full, it & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    IT_MARK(1)
                 }
                 mbar_wait(&bar_b_full[buf], (g >> 1) & 1);
+                IT_MARK(2)
                 const uint32_t d_tmem = tmem_base + (uint32_t)nc * 128;
                 const uint64_t w_desc = w_desc0 + (uint64_t)(buf ? (G::IMAGE >> 4) : 0);
                 uint32_t acc = 0;
-                // The tensor core accumulates with truncation, a bias that grows with the number of
-                // additions into a LARGE accumulator: the two small correction products go first
-                // (accumulator still ~2^-11 of its final size), the main MMAs last.
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {   // W_hi*act_lo, W_lo*act_hi, W_hi*act_hi
                     const uint64_t act_base = (pass == 0) ? act_desc_lo : act_desc_hi;
@@ -276,149 +348,180 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                         }
                 }
                 umma_commit(&bar_d_full[nc]);
-                // ring refill: chunk g-1 must have finished reading its buffer before chunk g+1 lands in it
-                if (g >= 1 && g + 1 < total_chunks) {
-                    const int gp = g - 1, itp = gp / nchunks;
-                    mbar_wait(&bar_d_full[chunk_id(gp)], itp & 1);
-                    issue_load(g + 1);
-                }
+            }
+#ifdef MLFFD_FILTER_TIMING
+            if (blockIdx.x == 0) printf("issuer waits (cycles): phi %lld  act %lld  weights %lld  issue %lld\n", it_acc[0], it_acc[1], it_acc[2], it_acc[4]);
+#endif
+        }
+    } else if (warp == kUmmaComputeWarps + 1) {
+        // ============================ weight loader ============================
+        // Streams second-layer weight chunk g into ring slot g % 2 as soon as the MMAs of chunk
+        // g - 2 (the slot's previous tenant) have completed.  A separate warp, because the issuer
+        // blocks in tcgen05.mma issue while the tensor-core queue is full: a refill issued from the
+        // issuer thread only starts when the NEXT chunk's MMAs are almost done (measured: 2.1k
+        // cycles of exposed load latency per chunk).
+        if (lane == 0) {
+            const uint32_t b_buf[2] = {smem_u32(smem + G::B0), smem_u32(smem + G::B1)};
+            const int total_chunks = my_tiles * nchunks;
+            for (int g = 2; g < total_chunks; ++g) {   // chunks 0 and 1 were requested during set-up
+                const int gp = g - 2, itp = gp / nchunks, cp = gp - itp * nchunks;
+                mbar_wait(&bar_d_full[skip_chunk1 ? cp * 2 : cp], itp & 1);
+                const int ci = g % nchunks, buf = g & 1;
+                mbar_expect_tx(&bar_b_full[buf], G::IMAGE);
+                const uint8_t* src = w2_images + (size_t)(skip_chunk1 ? ci * 2 : ci) * G::IMAGE;
+                for (uint32_t off = 0; off < G::IMAGE; off += kKBlockBytes)
+                    bulk_g2s(b_buf[buf] + off, src + off, kKBlockBytes, &bar_b_full[buf]);
             }
         }
     } else {
         // ========================= compute / epilogue =========================
-        // Software pipeline: the FFMA first layer of tile it+1 runs while the tensor cores work on
-        // tile it; only the final split + store into the (single) activation tile waits for them.
-        const int p = tid & 63, cg = tid >> 6;          // pair within tile, channel group (0..7)
-        const int q = warp & 3, cs = warp >> 2;         // TMEM lane quarter (channels), row segment
-        float y[CPT], z[CPT];
+        const int q = warp & 3, cs = warp >> 2;         // TMEM lane quarter (channels), column segment
+        const int ch = q * 32 + lane;                   // hidden channel of this lane (first layer)
+        const float b1v = (ch < H) ? __ldg(w.b1 + ch) : 0.f;
         float bias[G::NCH];
 #pragma unroll
         for (int c = 0; c < G::NCH; ++c) {
-            const int gch = c * 128 + q * 32 + lane;
+            const int gch = c * 128 + ch;
             bias[c] = (gch < 3 * H) ? __ldg(w.b2 + gch) : 0.f;
         }
 
-        auto first_layer = [&](int it) {
-            const int p0 = ((int)blockIdx.x + it * (int)gridDim.x) * kUmmaPairs;
-            // cutoff value/derivative once per pair (not per basis function)
-            for (int idx = tid; idx < kUmmaPairs * K; idx += kUmmaComputeThreads) {
-                const int pp = idx / K, k = idx - pp * K;
-                const float d = (p0 + pp < P) ? __ldg(pair_dist + p0 + pp) : rc;
-                if (k == 0) {
-                    const float kPi = 3.14159274101257324f;
-                    const float arg = (kPi * d) / rc;
-                    const bool inside = d < rc;
-                    cut_s[pp] = make_float2(inside ? 0.5f * (cosf(arg) + 1.0f) : 0.0f,
-                                            inside ? -0.5f * (kPi / rc) * sinf(arg) : 0.0f);
-                }
-                const float diff = d - __ldg(centers + k), gamma = __ldg(gammas + k);
-                const float phi = expf(-gamma * (diff * diff));
-                phi_s[pp * kPhiStride + k] = phi;                            // plain Gaussian for now
-                dphi_s[pp * kPhiStride + k] = -2.0f * gamma * diff * phi;
-            }
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            for (int idx = tid; idx < kUmmaPairs * K; idx += kUmmaComputeThreads) {
-                const int pp = idx / K, k = idx - pp * K;
-                const float2 c = cut_s[pp];
-                const float phi = phi_s[pp * kPhiStride + k], dphi = dphi_s[pp * kPhiStride + k];
-                phi_s[pp * kPhiStride + k] = phi * c.x;                      // same products as rbf_cutoff
-                dphi_s[pp * kPhiStride + k] = dphi * c.x + phi * c.y;
-            }
-            asm volatile("bar.sync 1, 512;" ::: "memory");
+        // RBF x cutoff and its derivative for the 64 pairs of a tile (same products as rbf_cutoff,
+        // filter.cuh), split and written as the B operand of the first-layer GEMM: rows 0..63 =
+        // phi~, rows 64..127 = phi~'.  Thread = (pair, 8-wide K chunk); K is padded to 32.
+        FT_DECL
+        uint4 phi_hi, phi_lo, dphi_hi, dphi_lo;   // this thread's chunk of the next RBF tile
+        auto rbf_compute = [&](int it) {   // pure math (overlaps the tensor cores)
+            if (tid < 4 * kUmmaPairs) {
+                const int p = tid >> 2, chunk = tid & 3;
+                const int gp = ((int)blockIdx.x + it * (int)gridDim.x) * kUmmaPairs + p;
+                const float d = (gp < P) ? __ldg(pair_dist + gp) : rc;
+                const float kPi = 3.14159274101257324f;
+                const float arg = (kPi * d) / rc;
+                const bool inside = d < rc;
+                const float cut = inside ? 0.5f * (cosf(arg) + 1.0f) : 0.0f;
+                const float dcut = inside ? -0.5f * (kPi / rc) * sinf(arg) : 0.0f;
+                float v8[8], t8[8];
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) { y[c] = b1_s[cg * CPT + c]; z[c] = 0.f; }
-#pragma unroll 4
-            for (int k = 0; k < K; ++k) {
-                const float ph = phi_s[p * kPhiStride + k], dph = dphi_s[p * kPhiStride + k];
-                const float4* wrow = reinterpret_cast<const float4*>(w1t_s + k * H + cg * CPT);
-#pragma unroll
-                for (int c4 = 0; c4 < CPT / 4; ++c4) {
-                    const float4 wv = wrow[c4];
-                    y[4 * c4 + 0] = fmaf(ph, wv.x, y[4 * c4 + 0]); z[4 * c4 + 0] = fmaf(dph, wv.x, z[4 * c4 + 0]);
-                    y[4 * c4 + 1] = fmaf(ph, wv.y, y[4 * c4 + 1]); z[4 * c4 + 1] = fmaf(dph, wv.y, z[4 * c4 + 1]);
-                    y[4 * c4 + 2] = fmaf(ph, wv.z, y[4 * c4 + 2]); z[4 * c4 + 2] = fmaf(dph, wv.z, z[4 * c4 + 2]);
-                    y[4 * c4 + 3] = fmaf(ph, wv.w, y[4 * c4 + 3]); z[4 * c4 + 3] = fmaf(dph, wv.w, z[4 * c4 + 3]);
+                for (int i = 0; i < 8; ++i) {
+                    const int k = chunk * 8 + i;
+                    const float diff = d - cen_s[k], gamma = gam_s[k];
+                    const float phi = expf(-gamma * (diff * diff));
+                    const float dphi = -2.0f * gamma * diff * phi;
+                    v8[i] = (k < K) ? phi * cut : 0.f;
+                    t8[i] = (k < K) ? dphi * cut + phi * dcut : 0.f;
                 }
+                split8(v8, phi_hi, phi_lo);
+                split8(t8, dphi_hi, dphi_lo);
             }
         };
-        auto publish_tile = [&]() {   // SiLU / tangent, two-term split, swizzled store, hand-off
-            const int ch0 = cg * CPT;                  // first channel (= K index) of this thread
-            const int kb = ch0 >> 6;                   // 64-wide K block
-            uint8_t* a_hi = smem + G::A_HI + kb * kKBlockBytes;
-            uint8_t* a_lo = smem + G::A_LO + kb * kKBlockBytes;
-            float hv[CPT], tv[CPT];
-#pragma unroll
-            for (int i = 0; i < CPT; ++i) {
-                const float yy = y[i];
-                const float sg = sigmoidf_(yy);
-                hv[i] = yy * sg;
-                tv[i] = sg * (1.0f + yy * (1.0f - sg)) * z[i];
+        auto rbf_store = [&]() {           // needs the activation tile free (second-layer MMAs done)
+            FT_MARK(5)
+            if (tid < 4 * kUmmaPairs) {
+                const int p = tid >> 2, chunk = tid & 3;
+                const uint32_t ov = sw128_offset(p, chunk), ot = sw128_offset(kUmmaPairs + p, chunk);
+                *reinterpret_cast<uint4*>(smem + G::A_HI + ov) = phi_hi;
+                *reinterpret_cast<uint4*>(smem + G::A_LO + ov) = phi_lo;
+                *reinterpret_cast<uint4*>(smem + G::A_HI + ot) = dphi_hi;
+                *reinterpret_cast<uint4*>(smem + G::A_LO + ot) = dphi_lo;
             }
-            if constexpr (CPT >= 8) {
+            FT_MARK(2)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (tid == 0) mbar_arrive(bar_phi_full);
+            FT_MARK(5)
+        };
+        // First-layer accumulator -> SiLU / tangent -> two-term split -> swizzled activation tile.
+        // Lane = hidden channel; this warp handles pairs cs*16 .. cs*16+15 (y) and their tangents.
+        auto publish_tile = [&](int it) {
+            mbar_wait(bar_d1_full, it & 1);
+            __syncwarp();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            FT_MARK(3)
+            if (ch < H) {
+                uint32_t ry[16], rz[16];
+                const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + G::D1_COL + (uint32_t)(cs * 16);
+                tmem_ld16(t0, ry);
+                tmem_ld16(t0 + kUmmaPairs, rz);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int kb = ch >> 6;
+                const uint32_t in_row = (uint32_t)(ch & 7) * 2;      // byte inside the 16-byte chunk
+                const int chunk = (ch & 63) >> 3;
+                uint8_t* a_hi = smem + G::A_HI + kb * kKBlockBytes + in_row;
+                uint8_t* a_lo = smem + G::A_LO + kb * kKBlockBytes + in_row;
 #pragma unroll
-                for (int j = 0; j < CPT / 8; ++j) {
-                    float h8[8], t8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { h8[i] = hv[8 * j + i]; t8[i] = tv[8 * j + i]; }
-                    const int chunk = ((ch0 & 63) >> 3) + j;
-                    uint4 hi, lo;
-                    split8(h8, hi, lo);
+                for (int j = 0; j < 16; ++j) {
+                    const int p = cs * 16 + j;
+                    const float yy = fmaf(__uint_as_float(ry[j]), kAccUnscale, b1v);
+                    const float zz = __uint_as_float(rz[j]) * kAccUnscale;
+                    const float sg = sigmoidf_(yy);
+                    const float hv = yy * sg;
+                    const float tv = sg * (1.0f + yy * (1.0f - sg)) * zz;
+                    __half hh, hl, th, tl;
+                    split1(hv, hh, hl);
+                    split1(tv, th, tl);
                     const uint32_t oh = sw128_offset(p, chunk), ot = sw128_offset(kUmmaPairs + p, chunk);
-                    *reinterpret_cast<uint4*>(a_hi + oh) = hi;
-                    *reinterpret_cast<uint4*>(a_lo + oh) = lo;
-                    split8(t8, hi, lo);
-                    *reinterpret_cast<uint4*>(a_hi + ot) = hi;
-                    *reinterpret_cast<uint4*>(a_lo + ot) = lo;
+                    *reinterpret_cast<__half*>(a_hi + oh) = hh;
+                    *reinterpret_cast<__half*>(a_lo + oh) = hl;
+                    *reinterpret_cast<__half*>(a_hi + ot) = th;
+                    *reinterpret_cast<__half*>(a_lo + ot) = tl;
                 }
-            } else {   // 4 channels per thread: half of a 16-byte chunk
-                const int chunk = (ch0 & 63) >> 3;
-                const uint32_t half8 = (uint32_t)(ch0 & 4) * 2;
-                uint2 hi, lo;
-                split4(make_float4(hv[0], hv[1], hv[2], hv[3]), hi, lo);
-                const uint32_t oh = sw128_offset(p, chunk) + half8, ot = sw128_offset(kUmmaPairs + p, chunk) + half8;
-                *reinterpret_cast<uint2*>(a_hi + oh) = hi;
-                *reinterpret_cast<uint2*>(a_lo + oh) = lo;
-                split4(make_float4(tv[0], tv[1], tv[2], tv[3]), hi, lo);
-                *reinterpret_cast<uint2*>(a_hi + ot) = hi;
-                *reinterpret_cast<uint2*>(a_lo + ot) = lo;
             }
+            FT_MARK(4)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 512;" ::: "memory");
             if (tid == 0) mbar_arrive(bar_a_full);
+            FT_MARK(5)
         };
 
-        first_layer(0);
-        publish_tile();
+        rbf_compute(0);
+        rbf_store();
+        publish_tile(0);
         for (int it = 0; it < my_tiles; ++it) {
             const int p0 = ((int)blockIdx.x + it * (int)gridDim.x) * kUmmaPairs;
-            if (it + 1 < my_tiles) first_layer(it + 1);        // overlaps the MMAs of tile `it`
+            if (it + 1 < my_tiles) rbf_compute(it + 1);        // while the tensor cores work on chunk 0
+            FT_MARK(2)
             // ---- epilogue of tile `it`: D[channel = lane][row = column] -> global ----
             const bool tangent = cs >= 2;                      // rows 64..127 hold f'
             const int row0 = p0 + (cs & 1) * 32;               // first pair of this warp's 32 rows
             float* out = (tangent ? dfilt : filt) + (size_t)row0 * (3 * H);
-            for (int ci = 0; ci < nchunks; ++ci) {
-                const int nc = skip_chunk1 ? ci * 2 : ci;
+            const bool full = row0 + 32 <= P;
+#pragma unroll
+            for (int nc = 0; nc < G::NCH; ++nc) {
+                if (skip_chunk1 && nc == 1) continue;
                 mbar_wait(&bar_d_full[nc], it & 1);
                 __syncwarp();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                FT_MARK(0)
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(nc * 128 + cs * 32), r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int gch = nc * 128 + q * 32 + lane;       // filter channel of this lane
+                const int gch = nc * 128 + ch;                  // filter channel of this lane
                 bool store = gch < 3 * H;
                 if (skip_vector_gate && gch >= H && gch < 2 * H) store = false;   // unused b gate of layer 0
                 if (store) {
                     const float b = tangent ? 0.f : bias[nc];
                     float* o = out + gch;
+                    if (full) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (row0 + j < P) __stcs(o + (size_t)j * (3 * H), fmaf(__uint_as_float(r[j]), kAccUnscale, b));
+                        for (int j = 0; j < 32; ++j) __stcs(o + (size_t)j * (3 * H), fmaf(__uint_as_float(r[j]), kAccUnscale, b));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (row0 + j < P) __stcs(o + (size_t)j * (3 * H), fmaf(__uint_as_float(r[j]), kAccUnscale, b));
+                    }
                 }
+                FT_MARK(1)
             }
-            // all MMAs of tile `it` are complete (last chunk waited): the activation tile is free
-            if (it + 1 < my_tiles) publish_tile();
+            // all second-layer MMAs of tile `it` are complete (last chunk waited): the activation
+            // tile is free for the RBF tile and then the activations of tile it + 1
+            if (it + 1 < my_tiles) {
+                rbf_store();
+                publish_tile(it + 1);
+            }
         }
+        FT_PRINT
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();

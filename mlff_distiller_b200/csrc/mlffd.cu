@@ -23,6 +23,7 @@
 #include "umma_rows.cuh"
 #include "md.cuh"
 #include "message.cuh"
+#include "message_pipe.cuh"
 #include "message_staged.cuh"
 #include "neighbor.cuh"
 #include "readout.cuh"
@@ -79,12 +80,16 @@ struct mlffd_ctx {
     int neighbor_mode = 0;   // 0 auto, 1 sweep, 2 cells (env MLFFD_NEIGHBOR)
     int struct_hint = 0;     // max atoms per structure promised by the caller (0 = unknown)
     bool enable_staging = false;     // env MLFFD_STAGING=1
+    int msg_bwd_mode = 2;            // env MLFFD_MSG_BWD = edges (0) | pairs (1) | pipe (2)
+    int msg_fwd_mode = 1;            // env MLFFD_MSG_FWD = rows (0) | pipe (1)
+    int pipe_depth_fwd = 2;          // env MLFFD_PIPE_DEPTH_FWD: ring slots per warp
+    int pipe_depth_bwd = 2;          // env MLFFD_PIPE_DEPTH_BWD
     std::string err;
     float* weights_d = nullptr;
     uint8_t* w2_images_d = nullptr;   // swizzled fp16 hi/lo 64 KB weight images (tensor-core path)
     bool use_umma = false;          // tensor-core update block (H = 128)
     bool use_umma_filter = false;   // tensor-core filter table (H = 128, 64, 32)
-    struct ImageOffsets { size_t filter, upd_f1, upd_f2, upd_b1, upd_b2; } img[kMaxLayers] = {};
+    struct ImageOffsets { size_t filter1, filter, upd_f1, upd_f2, upd_b1, upd_b2; } img[kMaxLayers] = {};
     const float *emb = nullptr, *centers = nullptr, *gammas = nullptr;
     LayerWeights layer[kMaxLayers];
     HeadWeights head{};
@@ -219,9 +224,10 @@ int launch_filter(mlffd_ctx* ctx, int l, const float* dist, const int* num_pairs
                   int64_t pair_bound, cudaStream_t st) {
     if (ctx->use_umma_filter) {
         const int grid = clamp_grid(ceil_div(std::max<int64_t>(pair_bound, 1), kUmmaPairs), kNumSMs);
-        filter_table_umma_kernel<H><<<grid, kUmmaThreads, UmmaGeom<H>::total(ctx->K), st>>>(
+        filter_table_umma_kernel<H><<<grid, kFilterUmmaThreads, UmmaGeom<H>::total(), st>>>(
             dist, num_pairs_ptr, num_pairs_arg, status, ctx->centers, ctx->gammas, ctx->K,
-            ctx->cfg.cutoff, ctx->layer[l].filter, ctx->w2_images_d + ctx->img[l].filter,
+            ctx->cfg.cutoff, ctx->layer[l].filter, ctx->w2_images_d + ctx->img[l].filter1,
+            ctx->w2_images_d + ctx->img[l].filter,
             (l == 0 && status != nullptr) ? 1 : 0, filt, dfilt);
         LAUNCHED(ctx, "filter_table_umma_kernel", MLFFD_STAGE_FILTER, st);
         return MLFFD_OK;
@@ -234,6 +240,57 @@ int launch_filter(mlffd_ctx* ctx, int l, const float* dist, const int* num_pairs
         ctx->cfg.cutoff, ctx->layer[l].filter, (l == 0 && status != nullptr) ? 1 : 0, filt, dfilt);
     LAUNCHED(ctx, "filter_table_kernel", MLFFD_STAGE_FILTER, st);
     return MLFFD_OK;
+}
+
+template <bool LAYER0, int D>
+void launch_forward_pipe_d(mlffd_ctx* ctx, int l, int grid, int N, cudaStream_t st) {
+    Workspace& ws = ctx->ws;
+    auto kernel = message_forward_pipe_kernel<LAYER0, D>;
+    constexpr size_t smem = message_forward_pipe_smem<D>();
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    kernel<<<grid, 32 * kPipeWarps, smem, st>>>(ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l],
+                                              LAYER0 ? nullptr : ws.v_in[l], ws.s_msg[l], ws.v_msg[l], N,
+                                              ctx->status_d);
+}
+void launch_forward_pipe(mlffd_ctx* ctx, int l, int grid, int N, cudaStream_t st) {
+#define FWD_PIPE(D) (l == 0 ? launch_forward_pipe_d<true, D>(ctx, l, grid, N, st) : launch_forward_pipe_d<false, D>(ctx, l, grid, N, st))
+    switch (ctx->pipe_depth_fwd) {
+        case 3: FWD_PIPE(3); break;
+        case 4: FWD_PIPE(4); break;
+        case 8: FWD_PIPE(8); break;
+        default: FWD_PIPE(2); break;
+    }
+#undef FWD_PIPE
+}
+
+template <bool LAYER0, int D>
+void launch_backward_pipe_d(mlffd_ctx* ctx, int l, int grid, const float* sb, const float* vb, float* sb_in,
+                            float* vb_in, int N, cudaStream_t st) {
+    Workspace& ws = ctx->ws;
+    auto kernel = message_backward_pipe_kernel<LAYER0, D>;
+    constexpr size_t smem = message_backward_pipe_smem<D>();
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    kernel<<<grid, 32 * kPipeWarps, smem, st>>>(ws.rowptr, ws.col, ws.pair, ws.rev, ws.geo, ws.filt[l], ws.dfilt[l],
+                                              ws.s_in[l], LAYER0 ? nullptr : ws.v_in[l], sb, vb, sb_in, vb_in,
+                                              ws.edge_adj + (size_t)l * ws.cap_edges, N, ctx->status_d);
+}
+void launch_backward_pipe(mlffd_ctx* ctx, int l, int grid, const float* sb, const float* vb, float* sb_in,
+                          float* vb_in, int N, cudaStream_t st) {
+#define BWD_PIPE(D) (l == 0 ? launch_backward_pipe_d<true, D>(ctx, l, grid, sb, vb, sb_in, vb_in, N, st) \
+                            : launch_backward_pipe_d<false, D>(ctx, l, grid, sb, vb, sb_in, vb_in, N, st))
+    switch (ctx->pipe_depth_bwd) {
+        case 4: BWD_PIPE(4); break;
+        default: BWD_PIPE(2); break;
+    }
+#undef BWD_PIPE
 }
 
 template <int H>
@@ -256,6 +313,11 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     // L1/L2 and the kernels are bound by streaming the filter-table rows -- so it is opt-in
     // (MLFFD_STAGING=1) and kept for bit-identity tests and for future tuning.
     const bool staged = ctx->enable_staging && hint > 0 && staged_smem <= 227 * 1024;
+    // reverse message kernels: 0 = one directed edge at a time (accumulates edge adjoints in place),
+    // 1 = every pair once, 2 = pair once + cp.async ring (H = 128); 1 and 2 write per-layer slabs
+    const bool bwd_pipe = !staged && ctx->msg_bwd_mode == 2 && H == 128;
+    const bool fwd_pipe = !staged && ctx->msg_fwd_mode == 1 && H == 128;
+    const bool adj_slabs = !staged && ctx->msg_bwd_mode >= 1;
     const int staged_grid = staged ? clamp_grid(n_structs, kNumSMs * (int)std::min<size_t>(8, (227 * 1024) / staged_smem)) : 1;
 
     embedding_kernel<H><<<clamp_grid(ceil_div((int64_t)N * (H / 4), 256), kNumSMs * 8), 256, 0, st>>>(
@@ -274,7 +336,9 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
             message_forward_staged_kernel<H, false><<<staged_grid, kStagedThreads, staged_smem, st>>>(
                 offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], ws.v_in[l],
                 ws.s_msg[l], ws.v_msg[l], ctx->status_d);
-        else if (l == 0)
+        else if (fwd_pipe) {
+            if constexpr (H == 128) launch_forward_pipe(ctx, l, msg_grid, N, st);
+        } else if (l == 0)
             message_forward_kernel<H, true><<<msg_grid, 256, 0, st>>>(
                 ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], nullptr, ws.s_msg[l],
                 ws.v_msg[l], N, status);
@@ -364,6 +428,10 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     message_backward_kernel<H, LAYER0, ACC><<<msg_grid, 256, 0, st>>>(                           \
         ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.dfilt[l], ws.s_in[l], ws.v_in[l], sb, \
         vb, sb_in, vb_in, ws.edge_adj, N, status)
+#define MSG_BWD_PAIRS(LAYER0)                                                                    \
+    message_backward_pairs_kernel<H, LAYER0, false><<<msg_grid, 256, 0, st>>>(                   \
+        ws.rowptr, ws.col, ws.pair, ws.rev, ws.geo, ws.filt[l], ws.dfilt[l], ws.s_in[l],         \
+        ws.v_in[l], sb, vb, sb_in, vb_in, ws.edge_adj + (size_t)l * ws.cap_edges, N, status)
 #define MSG_BWD_EDGES(LAYER0, ACC)                                                                         \
     message_backward_edges_staged_kernel<H, LAYER0, ACC><<<staged_grid, kStagedThreads, staged_smem, st>>>(             \
         offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.dfilt[l], ws.s_in[l],   \
@@ -377,13 +445,21 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
                     offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.filt[l], sb, vb, sb_in, vb_in,
                     ctx->status_d);
             }
+        } else if (bwd_pipe) {
+            if constexpr (H == 128) launch_backward_pipe(ctx, l, msg_grid, sb, vb, sb_in, vb_in, N, st);
+        } else if (ctx->msg_bwd_mode >= 1) {
+            if (l == 0) MSG_BWD_PAIRS(true); else MSG_BWD_PAIRS(false);
         } else if (l == 0) { if (first) MSG_BWD(true, false); else MSG_BWD(true, true); }
         else        { if (first) MSG_BWD(false, false); else MSG_BWD(false, true); }
+#undef MSG_BWD_PAIRS
 #undef MSG_BWD_EDGES
 #undef MSG_BWD
         LAUNCHED(ctx, "message_backward_kernel", MLFFD_STAGE_MESSAGE_BWD, st);
     }
-    force_kernel<<<warp_grid, 256, 0, st>>>(ws.rowptr, ws.rev, ws.geo, ws.edge_adj, forces, N, status);
+    force_kernel<<<warp_grid, 256, 0, st>>>(ws.rowptr, ws.rev, ws.geo, ws.edge_adj, adj_slabs ? L : 1,
+                                            (size_t)ws.cap_edges,
+                                            ctx->debug_keep ? ws.edge_adj + (size_t)L * ws.cap_edges : nullptr,
+                                            forces, N, status);
     LAUNCHED(ctx, "force_kernel", MLFFD_STAGE_FORCE, st);
     return MLFFD_OK;
 }
@@ -524,6 +600,11 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     const char* dbg = std::getenv("MLFFD_DEBUG_KEEP");
     ctx->debug_keep = dbg && dbg[0] == '1';
     if (const char* ns = std::getenv("MLFFD_STAGING")) ctx->enable_staging = ns[0] == '1';
+    if (const char* ns = std::getenv("MLFFD_MSG_BWD"))
+        ctx->msg_bwd_mode = !std::strcmp(ns, "edges") ? 0 : !std::strcmp(ns, "pairs") ? 1 : 2;
+    if (const char* ns = std::getenv("MLFFD_MSG_FWD")) ctx->msg_fwd_mode = !std::strcmp(ns, "rows") ? 0 : 1;
+    if (const char* ns = std::getenv("MLFFD_PIPE_DEPTH_FWD")) ctx->pipe_depth_fwd = std::atoi(ns);
+    if (const char* ns = std::getenv("MLFFD_PIPE_DEPTH_BWD")) ctx->pipe_depth_bwd = std::atoi(ns);
     if (const char* nm = std::getenv("MLFFD_NEIGHBOR"))
         ctx->neighbor_mode = (std::strcmp(nm, "sweep") == 0) ? 1 : (std::strcmp(nm, "cells") == 0) ? 2 : 0;
 
@@ -609,6 +690,7 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
         const int fchunks = (3 * H + 127) / 128;
         std::vector<float> M1T((size_t)2 * H * H), M2T((size_t)H * 3 * H);
         for (int l = 0; l < L; ++l) {
+            ctx->img[l].filter1 = add_image(q, K, H, K, 0, 0, 1);          // filter layer 1 [H][K], K padded
             const float* W2 = q + (size_t)H * K + H;                       // filter layer 2 [3H][H]
             const float* M1 = W2 + (size_t)3 * H * H + 3 * H;              // update_mlp.0 [H][2H]
             const float* M2 = M1 + (size_t)H * 2 * H + H;                  // update_mlp.2 [3H][H]
@@ -636,11 +718,11 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
         if (e != cudaSuccess) return bail(MLFFD_ENOMEM, cudaGetErrorString(e));
         e = cudaMemcpy(ctx->w2_images_d, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
-        if (H == 128) e = cudaFuncSetAttribute(filter_table_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<128>::total(K));
-        else if (H == 64) e = cudaFuncSetAttribute(filter_table_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<64>::total(K));
-        else e = cudaFuncSetAttribute(filter_table_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<32>::total(K));
+        if (H == 128) e = cudaFuncSetAttribute(filter_table_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<128>::total());
+        else if (H == 64) e = cudaFuncSetAttribute(filter_table_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<64>::total());
+        else e = cudaFuncSetAttribute(filter_table_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<32>::total());
         if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
-        ctx->use_umma_filter = true;
+        ctx->use_umma_filter = K <= kUmmaMaxRbf;   // first layer runs as one 32-wide K block
         if (H == 128) {
 #define SET_ROWS_ATTR(OP)                                                                            \
         e = cudaFuncSetAttribute(umma_rows_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -709,7 +791,7 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
     const size_t o_rev = plan.take(sizeof(int) * E);
     const size_t o_pair = plan.take(sizeof(int) * E);
     const size_t o_geo = plan.take(sizeof(float4) * E);
-    const size_t o_adj = plan.take(sizeof(float4) * E);
+    const size_t o_adj = plan.take(sizeof(float4) * E * (L + 1));   // per-layer slabs + debug sum
     const size_t o_pdist = plan.take(sizeof(float) * P);
     const size_t o_eps = plan.take(sizeof(float) * N);
     const int64_t C = 2 * N + 8 * max_structures + 2;   // cell capacity (grid_setup caps cells per structure)
@@ -891,7 +973,7 @@ extern "C" int mlffd_debug_buffer(mlffd_ctx* ctx, const char* name, int32_t laye
     else if (n == "pair") { p = ws.pair; cnt = E; }
     else if (n == "edge_dst") { p = ws.edge_dst; cnt = E; }
     else if (n == "geo") { p = ws.geo; cnt = E; es = 16; }
-    else if (n == "edge_adj") { p = ws.edge_adj; cnt = E; es = 16; }
+    else if (n == "edge_adj") { p = ws.edge_adj + (size_t)ctx->L * ws.cap_edges; cnt = E; es = 16; }
     else if (n == "pair_dist") { p = ws.pair_dist; cnt = P; }
     else if (n == "atom_energy") { p = ws.eps; cnt = N; }
     else if (n == "s_out") { p = ws.s_in[L]; cnt = N * H; }

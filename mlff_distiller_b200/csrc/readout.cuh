@@ -173,11 +173,23 @@ __device__ __forceinline__ float3 edge_position_adjoint(const float4 g, const fl
                        fmaf(scale, g.z, adj.z * inv_q));
 }
 
-// One warp per atom j: F_j = sum_{e in row j} (r_bar_e - r_bar_rev(e)).
+// Edge adjoint summed over the per-layer slabs, last layer first (the order the single-buffer
+// accumulation of the reverse pass uses).
+__device__ __forceinline__ float4 edge_adjoint_sum(const float4* __restrict__ edge_adj, int e, int slabs,
+                                                   size_t slab_stride) {
+    float4 t = __ldg(edge_adj + (size_t)(slabs - 1) * slab_stride + e);
+    for (int l = slabs - 2; l >= 0; --l) t = add4(__ldg(edge_adj + (size_t)l * slab_stride + e), t);
+    return t;
+}
+
+// One warp per atom j: F_j = sum_{e in row j} (r_bar_e - r_bar_rev(e)).  edge_adj holds `slabs`
+// per-layer slabs of slab_stride entries (1 when the reverse pass accumulated in place);
+// adj_sum_out (debug only) receives the summed adjoint of every edge.
 __global__ void __launch_bounds__(256)
 force_kernel(const int* __restrict__ rowptr, const int* __restrict__ rev,
-             const float4* __restrict__ geo, const float4* __restrict__ edge_adj,
-             float* __restrict__ forces, int num_atoms, const DeviceStatus* __restrict__ status) {
+             const float4* __restrict__ geo, const float4* __restrict__ edge_adj, int slabs,
+             size_t slab_stride, float4* __restrict__ adj_sum_out, float* __restrict__ forces,
+             int num_atoms, const DeviceStatus* __restrict__ status) {
     if (status->overflow) return;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -187,8 +199,11 @@ force_kernel(const int* __restrict__ rowptr, const int* __restrict__ rev,
         float fx = 0.f, fy = 0.f, fz = 0.f;
         for (int e = e0 + lane; e < e1; e += 32) {
             const int r = __ldg(rev + e);
-            const float3 a = edge_position_adjoint(__ldg(geo + e), __ldg(edge_adj + e));
-            const float3 b = edge_position_adjoint(__ldg(geo + r), __ldg(edge_adj + r));
+            const float4 adj_e = edge_adjoint_sum(edge_adj, e, slabs, slab_stride);
+            const float4 adj_r = edge_adjoint_sum(edge_adj, r, slabs, slab_stride);
+            if (adj_sum_out != nullptr) adj_sum_out[e] = adj_e;
+            const float3 a = edge_position_adjoint(__ldg(geo + e), adj_e);
+            const float3 b = edge_position_adjoint(__ldg(geo + r), adj_r);
             fx += a.x - b.x; fy += a.y - b.y; fz += a.z - b.z;
         }
         fx = group_sum<32>(fx); fy = group_sum<32>(fy); fz = group_sum<32>(fz);

@@ -438,27 +438,60 @@ def test_staged_message_kernels_bit_identical(variant_name):
     z_d = torch.from_numpy(z.astype(np.int32)).to(dev)
     p_d = torch.from_numpy(pos).to(dev)
     o_d = torch.from_numpy(off.astype(np.int32)).to(dev)
-    out = {}
-    for mode in ("staged", "generic"):
-        if mode == "staged":
-            os.environ["MLFFD_STAGING"] = "1"
+    def run(env, max_atoms):
+        os.environ.update(env)
         try:
             model, state, cfg = _model(variant_name)
-            model.engine()   # the context reads MLFFD_STAGING when it is created
+            model.engine()   # the context reads its MLFFD_* knobs when it is created
         finally:
-            os.environ.pop("MLFFD_STAGING", None)
-        e, f = model.energy_and_forces_packed(z_d, p_d, o_d, len(structs), max_atoms=int(counts.max()))
-        assert model.engine()._hint == int(counts.max())
-        out[mode] = (e.cpu().numpy(), f.cpu().numpy())
-    assert np.array_equal(out["staged"][0], out["generic"][0])
-    assert np.array_equal(out["staged"][1], out["generic"][1])
-    # a wrong promise is detected on the device and the call falls back to the generic kernels
-    os.environ["MLFFD_STAGING"] = "1"
-    try:
-        model, state, cfg = _model(variant_name)
-        model.engine()
-    finally:
-        os.environ.pop("MLFFD_STAGING", None)
-    e, f = model.energy_and_forces_packed(z_d, p_d, o_d, len(structs), max_atoms=25)
-    assert model.engine()._hint == 0
-    assert np.array_equal(e.cpu().numpy(), out["generic"][0]) and np.array_equal(f.cpu().numpy(), out["generic"][1])
+            for k in env:
+                os.environ.pop(k, None)
+        e, f = model.energy_and_forces_packed(z_d, p_d, o_d, len(structs), max_atoms=max_atoms)
+        return model, e.cpu().numpy(), f.cpu().numpy()
+
+    # the staged kernels restate the per-directed-edge kernels (same accumulation order)
+    m_staged, e_staged, f_staged = run({"MLFFD_STAGING": "1"}, int(counts.max()))
+    assert m_staged.engine()._hint == int(counts.max())
+    m_edges, e_edges, f_edges = run({"MLFFD_MSG_FWD": "rows", "MLFFD_MSG_BWD": "edges"}, int(counts.max()))
+    assert np.array_equal(e_staged, e_edges)
+    assert np.array_equal(f_staged, f_edges)
+    # a wrong promise is detected on the device and the call falls back to the default kernels
+    m_default, e_default, f_default = run({}, 0)
+    m_wrong, e_wrong, f_wrong = run({"MLFFD_STAGING": "1"}, 25)
+    assert m_wrong.engine()._hint == 0
+    assert np.array_equal(e_wrong, e_default) and np.array_equal(f_wrong, f_default)
+
+
+@pytest.mark.parametrize("variant_name", ["original", "tiny", "ultra_tiny"])
+def test_message_kernel_variants_agree(variant_name):
+    """cp.async-pipelined message kernels == plain kernels bit for bit; the pair-once reverse pass
+    differs from the per-directed-edge one only by rounding."""
+    from mlff_distiller_b200 import synthetic
+    structs = (synthetic.druglike_batch(40, first=300, ragged=True) + [synthetic.water(), synthetic.Structure([6], [[0, 0, 0]])]
+               + [synthetic.alkane_chain(40)])
+    z, pos, off = synthetic.concatenate(structs)
+    dev = "cuda:0"
+    z_d = torch.from_numpy(z.astype(np.int32)).to(dev)
+    p_d = torch.from_numpy(pos.astype(np.float32)).to(dev)
+    o_d = torch.from_numpy(off.astype(np.int32)).to(dev)
+
+    def run(env):
+        os.environ.update(env)
+        try:
+            model, state, cfg = _model(variant_name)
+            model.engine()
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        e, f = model.energy_and_forces_packed(z_d, p_d, o_d, len(structs))
+        return e.cpu().numpy(), f.cpu().numpy()
+
+    e_def, f_def = run({})
+    e_pairs, f_pairs = run({"MLFFD_MSG_FWD": "rows", "MLFFD_MSG_BWD": "pairs"})
+    assert np.array_equal(e_def, e_pairs) and np.array_equal(f_def, f_pairs)
+    for depth in ("2", "8"):
+        e_d, f_d = run({"MLFFD_PIPE_DEPTH_FWD": depth, "MLFFD_PIPE_DEPTH_BWD": "2" if depth == "2" else "4"})
+        assert np.array_equal(e_def, e_d) and np.array_equal(f_def, f_d)
+    e_edges, f_edges = run({"MLFFD_MSG_FWD": "rows", "MLFFD_MSG_BWD": "edges"})
+    assert np.array_equal(e_def, e_edges)
+    assert np.max(np.abs(f_def - f_edges)) <= 2e-5
