@@ -97,7 +97,9 @@ def algorithmic_work(N, E, P, H, K, L):
         # gathers of neighbour rows (E * `gather` bytes) are L2 traffic and not counted here
         mf_b += P * nf + E * 24 + N * (4 * H * 4 + gather)
         mf_f += E * 2 * H * (1 + (0 if l == 0 else 3) + 3)
-        mb_b += P * 2 * nf + E * (24 + 16 + (0 if l == L - 1 else 16)) \
+        # reverse: every pair's (a, b, c, a', b', c') once (layer 0: c, a', c'), indices col / pair / rev,
+        # geometry, one edge-adjoint slab entry written per edge (no read-modify-write)
+        mb_b += P * (3 if l == 0 else 6) * H * 4 + E * (12 + 16 + 16) \
             + N * (gather + 4 * H * 4 + (0 if l == 0 else 4 * H * 4))
         mb_f += E * 2 * H * (2 + 6 + 3 + (0 if l == 0 else 3 + 2 + 4))
     w["message_fwd"] = {"flops": mf_f, "bytes": mf_b}
@@ -115,7 +117,7 @@ def algorithmic_work(N, E, P, H, K, L):
     head = H * H // 2 + H * H // 8 + H // 4
     w["readout"] = {"flops": N * 4 * head, "bytes": N * 4 * (2 * H + 1)}
     w["neighbor"] = {"flops": 0, "bytes": N * (12 + 4 + 16) + E * (4 * 4 + 16) + P * 4}
-    w["force"] = {"flops": E * 40, "bytes": E * (4 + 4 * 16) + N * 12}
+    w["force"] = {"flops": E * 40, "bytes": E * (4 + 16 + 16 * L) + N * 12}   # rev, geo, L adjoint slabs
     w["embedding"] = {"flops": 0, "bytes": N * (4 + 2 * H * 4)}
     w["energy_sum"] = {"flops": N, "bytes": N * 4}
     return w

@@ -352,16 +352,16 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
             if (ctx->use_umma) {
                 const UpdateWeights& uw = ctx->layer[l].update;
                 const int rows_grid = clamp_grid(ceil_div(N, 128), kNumSMs);
-                umma_rows_kernel<UpdateFwd1Op><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                umma_rows_kernel<UpdateFwd1Op><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
                     UpdateFwd1Op{ws.s_msg[l], ws.v_msg[l], uw.m1, ws.y1[l]}, N,
                     ctx->w2_images_d + ctx->img[l].upd_f1, status);
                 LAUNCHED(ctx, "umma_rows_kernel<UpdateFwd1Op>", MLFFD_STAGE_UPDATE_FWD, st);
                 if (l == L - 1)
-                    umma_rows_kernel<UpdateFwd2Op<true>><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                    umma_rows_kernel<UpdateFwd2Op<true>><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
                         UpdateFwd2Op<true>{ws.y1[l], ws.s_msg[l], ws.v_msg[l], uw.m2, uw.U, ws.s_in[l + 1], nullptr, nullptr},
                         N, ctx->w2_images_d + ctx->img[l].upd_f2, status);
                 else
-                    umma_rows_kernel<UpdateFwd2Op<false>><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                    umma_rows_kernel<UpdateFwd2Op<false>><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
                         UpdateFwd2Op<false>{ws.y1[l], ws.s_msg[l], ws.v_msg[l], uw.m2, uw.U, ws.s_in[l + 1], ws.v_in[l + 1], ws.gates[l]},
                         N, ctx->w2_images_d + ctx->img[l].upd_f2, status);
                 upd_done = true;
@@ -398,16 +398,16 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
                 const UpdateWeights& uw = ctx->layer[l].update;
                 const int rows_grid = clamp_grid(ceil_div(N, 128), kNumSMs);
                 if (l == L - 1) {
-                    umma_rows_kernel<UpdateBwd1Op<true>><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                    umma_rows_kernel<UpdateBwd1Op<true>><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
                         UpdateBwd1Op<true>{sb, vb, ws.v_msg[l], uw.U, ws.y1[l]}, N, ctx->w2_images_d + ctx->img[l].upd_b1, status);
                     LAUNCHED(ctx, "umma_rows_kernel<UpdateBwd1Op>", MLFFD_STAGE_UPDATE_BWD, st);
-                    umma_rows_kernel<UpdateBwd2Op<true>><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                    umma_rows_kernel<UpdateBwd2Op<true>><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
                         UpdateBwd2Op<true>{ws.y1[l], ws.v_msg[l], nullptr, uw.U, sb, vb}, N, ctx->w2_images_d + ctx->img[l].upd_b2, status);
                 } else {
-                    umma_rows_kernel<UpdateBwd1Op<false>><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                    umma_rows_kernel<UpdateBwd1Op<false>><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
                         UpdateBwd1Op<false>{sb, vb, ws.v_msg[l], uw.U, ws.y1[l]}, N, ctx->w2_images_d + ctx->img[l].upd_b1, status);
                     LAUNCHED(ctx, "umma_rows_kernel<UpdateBwd1Op>", MLFFD_STAGE_UPDATE_BWD, st);
-                    umma_rows_kernel<UpdateBwd2Op<false>><<<rows_grid, kUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                    umma_rows_kernel<UpdateBwd2Op<false>><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
                         UpdateBwd2Op<false>{ws.y1[l], ws.v_msg[l], ws.gates[l], uw.U, sb, vb}, N, ctx->w2_images_d + ctx->img[l].upd_b2, status);
                 }
                 bwd_done = true;

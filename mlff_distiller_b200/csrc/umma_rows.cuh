@@ -13,8 +13,10 @@
 // so norms, SiLU, gates, the 3x3 spatial mixing and residuals are fused around the GEMM and the
 // only HBM traffic is the per-atom feature rows.
 //
-// Roles: 16 compute/epilogue warps + 1 issuer warp (bulk-copies the pre-swizzled 64 KB weight
-// images [ks][chunk] through a 2-deep ring and issues 24 MMAs per image).
+// Roles: 16 compute/epilogue warps + 1 issuer warp (24 MMAs per weight image) + 1 loader warp
+// (bulk-copies the pre-swizzled 64 KB weight images [ks][chunk] through a 2-deep ring; image g is
+// requested the moment the MMAs of image g-2 have completed -- the issuer itself blocks in
+// tcgen05.mma issue while the tensor-core queue is full, so a refill issued from it starts late).
 #pragma once
 #include "filter_umma.cuh"
 
@@ -30,7 +32,7 @@ struct UmmaRowsSmem {
 };
 
 template <class Op>
-__global__ void __launch_bounds__(kUmmaThreads, 1)
+__global__ void __launch_bounds__(kFilterUmmaThreads, 1)
 umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
                  const DeviceStatus* __restrict__ status) {
     constexpr int KS = Op::KS, NC = Op::NC;
@@ -85,15 +87,6 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
             const uint64_t act_desc_hi = umma_desc_sw128(smem_u32(smem + UmmaRowsSmem::A_HI));
             const uint64_t act_desc_lo = umma_desc_sw128(smem_u32(smem + UmmaRowsSmem::A_LO));
             const uint64_t w_desc0 = umma_desc_sw128(b_buf[0]);
-            const int total = my_tiles * PER_TILE;
-            auto issue_load = [&](int g) {
-                const int buf = g & 1;
-                mbar_expect_tx(&bar_b_full[buf], kChunkImageBytes);
-                const uint8_t* src = images + (size_t)(g % PER_TILE) * kChunkImageBytes;
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq)
-                    bulk_g2s(b_buf[buf] + qq * kKBlockBytes, src + qq * kKBlockBytes, kKBlockBytes, &bar_b_full[buf]);
-            };
             int g = 0;   // images 0 and 1 were requested during set-up
             for (int it = 0; it < my_tiles; ++it) {
                 for (int ks = 0; ks < KS; ++ks) {
@@ -135,13 +128,24 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
                             }
                         umma_commit(&bar_b_free[buf]);
                         if (ks == KS - 1) umma_commit(&bar_d_full[c]);
-                        if (g >= 1 && g + 1 < total) {   // ring refill behind the previous image
-                            mbar_wait(&bar_b_free[(g - 1) & 1], ((g - 1) >> 1) & 1);
-                            issue_load(g + 1);
-                        }
                     }
                     umma_commit(bar_act_free);
                 }
+            }
+        }
+    } else if (warp == kUmmaComputeWarps + 1) {
+        // ============================ weight loader ============================
+        if (lane == 0) {
+            const uint32_t b_buf[2] = {smem_u32(smem + UmmaRowsSmem::B0), smem_u32(smem + UmmaRowsSmem::B1)};
+            const int total = my_tiles * PER_TILE;
+            for (int g = 2; g < total; ++g) {   // images 0 and 1 were requested during set-up
+                const int buf = g & 1;
+                mbar_wait(&bar_b_free[buf], ((g - 2) >> 1) & 1);   // MMAs of image g-2 done with the slot
+                mbar_expect_tx(&bar_b_full[buf], kChunkImageBytes);
+                const uint8_t* src = images + (size_t)(g % PER_TILE) * kChunkImageBytes;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq)
+                    bulk_g2s(b_buf[buf] + qq * kKBlockBytes, src + qq * kKBlockBytes, kKBlockBytes, &bar_b_full[buf]);
             }
         }
     } else {
