@@ -200,6 +200,20 @@ int mlffd_profile_read(mlffd_ctx* ctx, mlffd_profile* out);
 const char* mlffd_stage_name(int32_t stage);
 
 /*
+ * Strain derivative of the energy of the LAST mlffd_energy_forces call (which must have been made
+ * with forces_d != NULL, on the same stream, with the same offsets):
+ *   virial_d[b*9 + 3*a + c] = dE_b / d eps_ac = sum over the directed edges e of structure b of
+ *   (dE/dr_e)_a (r_e)_c,   r_e = x_src - x_dst (minimum image),   x -> (1 + eps) x.
+ * stress = virial / volume (eV/A^3; ASE Voigt order xx, yy, zz, yz, xz, xy after symmetrising).
+ * The reference's counterpart, inference/ase_calculator.py:521-588 (_compute_stress), differentiates
+ * with respect to a `cell` tensor the model never reads and returns zeros; this entry point is the
+ * working version and its parity is pinned only by the oracle's autograd
+ * strain derivative and by finite differences.
+ */
+int mlffd_virial(mlffd_ctx* ctx, const int32_t* offsets_d, int32_t num_structures, float* virial_d,
+                 void* stream);
+
+/*
  * On-device velocity Verlet (replaces the host-side ASE VelocityVerlet loop the reference drives
  * through src/mlff_distiller/testing/nve_harness.py:214-235; one step = kick_drift,
  * mlffd_energy_forces on pos32_d, kick_energy).  Integrator state is FP64 (as ASE's), the model

@@ -28,7 +28,7 @@ EXPORTS = [
     "mlffd_workspace_reserve", "mlffd_neighbor_list", "mlffd_export_edges",
     "mlffd_energy_forces", "mlffd_get_status", "mlffd_filter_table", "mlffd_debug_buffer",
     "mlffd_profile_enable", "mlffd_profile_read", "mlffd_stage_name",
-    "mlffd_md_kick_drift", "mlffd_md_kick_energy", "mlffd_set_structure_hint",
+    "mlffd_md_kick_drift", "mlffd_md_kick_energy", "mlffd_set_structure_hint", "mlffd_virial",
 ]
 NUM_STAGES = 10
 
@@ -138,6 +138,8 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     lib.mlffd_stage_name.argtypes = [i32]
     lib.mlffd_set_structure_hint.restype = ctypes.c_int
     lib.mlffd_set_structure_hint.argtypes = [vp, i32]
+    lib.mlffd_virial.restype = ctypes.c_int
+    lib.mlffd_virial.argtypes = [vp, vp, i32, vp, vp]
     f64 = ctypes.c_double
     lib.mlffd_md_kick_drift.restype = ctypes.c_int
     lib.mlffd_md_kick_drift.argtypes = [i64, vp, vp, vp, vp, f64, vp, vp]

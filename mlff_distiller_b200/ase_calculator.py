@@ -146,10 +146,20 @@ class StudentForceFieldCalculator(_AseCalculator):
             cell = np.asarray(atoms.get_cell(), dtype=np.float64)
             pbc = np.asarray(atoms.get_pbc(), dtype=bool)
             self._validate_inputs(positions, numbers, cell, pbc)
-            energy, forces = self._evaluate_single(positions, numbers, cell, pbc)
+            want_stress = "stress" in properties and self.enable_stress
+            volume = abs(float(np.linalg.det(cell)))
+            energy, forces, virial = self._evaluate_single(positions, numbers, cell, pbc,
+                                                           want_virial=want_stress and volume > 1e-12)
             results: Dict[str, Any] = {"energy": energy, "forces": forces}
-            if "stress" in properties and self.enable_stress:
-                results["stress"] = np.zeros(6)  # the reference's stress path also yields zeros
+            if want_stress:
+                if virial is None:
+                    # no cell: like the reference (ase_calculator.py:521-588), whose stress path
+                    # yields zeros for every input
+                    results["stress"] = np.zeros(6)
+                else:
+                    # ASE convention: stress = (1/V) dE/d(strain), Voigt order xx yy zz yz xz xy
+                    sig = 0.5 * (virial + virial.T) / volume
+                    results["stress"] = np.array([sig[0, 0], sig[1, 1], sig[2, 2], sig[1, 2], sig[0, 2], sig[0, 1]])
             self.results = results
             self._n_calls += 1
             if self.enable_timing:
@@ -195,7 +205,7 @@ class StudentForceFieldCalculator(_AseCalculator):
                         f"pbc_mode='minimum_image' needs cell heights >= 2*cutoff "
                         f"({2 * self.model.cutoff:.2f} Å); axis {k} has {height:.3f} Å")
 
-    def _evaluate_single(self, positions, numbers, cell, pbc):
+    def _evaluate_single(self, positions, numbers, cell, pbc, want_virial: bool = False):
         dev = self.device
         n = len(numbers)
         if (self._numbers_cache is None or len(self._numbers_cache[0]) != n
@@ -204,7 +214,7 @@ class StudentForceFieldCalculator(_AseCalculator):
             off_d = torch.tensor([0, n], dtype=torch.int32, device=dev)
             self._numbers_cache = (np.array(numbers), z_d, off_d)
             self._pin_pos = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-            self._pin_out = torch.empty(3 * n + 1, dtype=torch.float32).pin_memory()
+            self._pin_out = torch.empty(3 * n + 10, dtype=torch.float32).pin_memory()
         _, z_d, off_d = self._numbers_cache
         self._pin_pos.copy_(torch.from_numpy(np.ascontiguousarray(positions, dtype=np.float64)))
         pos_d = self._pin_pos.to(dev, non_blocking=True)
@@ -212,11 +222,15 @@ class StudentForceFieldCalculator(_AseCalculator):
         if self.pbc_mode == "minimum_image" and pbc.any():
             cells_d, pbc_d = StudentForceField.pack_cells(torch.from_numpy(cell), torch.from_numpy(pbc), 1, dev)
         e_d, f_d = self.model.energy_and_forces_packed(z_d, pos_d, off_d, 1, cells_d, pbc_d)
-        out_d = torch.cat([e_d.reshape(1), f_d.reshape(-1)])
-        self._pin_out.copy_(out_d, non_blocking=True)
+        parts = [e_d.reshape(1), f_d.reshape(-1)]
+        if want_virial:
+            parts.append(self.model.virial_of_last_call(off_d, 1).reshape(-1))
+        out_d = torch.cat(parts)
+        self._pin_out[:out_d.numel()].copy_(out_d, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         out = self._pin_out.numpy()
-        return float(out[0]), out[1:].reshape(n, 3).copy()
+        virial = out[3 * n + 1:3 * n + 10].reshape(3, 3).astype(np.float64) if want_virial else None
+        return float(out[0]), out[1:3 * n + 1].reshape(n, 3).copy(), virial
 
     # ---- batches --------------------------------------------------------------------------
     def calculate_batch(self, atoms_list, properties: Sequence[str] = ("energy", "forces")

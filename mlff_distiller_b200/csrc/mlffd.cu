@@ -48,6 +48,7 @@ struct Workspace {
     int *atom_struct = nullptr, *deg = nullptr, *deg_low = nullptr, *rowptr = nullptr, *lowptr = nullptr;
     int *col = nullptr, *edge_dst = nullptr, *rev = nullptr, *pair = nullptr;
     float4 *geo = nullptr, *edge_adj = nullptr;
+    double* virial64 = nullptr;      // [cap_structs][9] FP64 accumulators of mlffd_virial
     float* pair_dist = nullptr;
     // cell list (large structures)
     GridInfo* grids = nullptr;
@@ -80,6 +81,7 @@ struct mlffd_ctx {
     int neighbor_mode = 0;   // 0 auto, 1 sweep, 2 cells (env MLFFD_NEIGHBOR)
     int struct_hint = 0;     // max atoms per structure promised by the caller (0 = unknown)
     bool enable_staging = false;     // env MLFFD_STAGING=1
+    int last_adj_slabs = 0;          // edge-adjoint slabs written by the last force evaluation (0 = none)
     int msg_bwd_mode = 2;            // env MLFFD_MSG_BWD = edges (0) | pairs (1) | pipe (2)
     int msg_fwd_mode = 1;            // env MLFFD_MSG_FWD = rows (0) | pipe (1)
     int pipe_depth_fwd = 2;          // env MLFFD_PIPE_DEPTH_FWD: ring slots per warp
@@ -387,7 +389,7 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     structure_energy_kernel<<<clamp_grid(ceil_div(n_structs, 8), kNumSMs * 8), 256, 0, st>>>(
         ws.eps, offsets, n_structs, energy, status);
     LAUNCHED(ctx, "structure_energy_kernel", MLFFD_STAGE_ENERGY_SUM, st);
-    if (!want_forces) return MLFFD_OK;
+    if (!want_forces) { ctx->last_adj_slabs = 0; return MLFFD_OK; }
 
     for (int l = L - 1; l >= 0; --l) {
         float* sb = ws.sbar[adj(l)];
@@ -456,6 +458,7 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
 #undef MSG_BWD
         LAUNCHED(ctx, "message_backward_kernel", MLFFD_STAGE_MESSAGE_BWD, st);
     }
+    ctx->last_adj_slabs = adj_slabs ? L : 1;
     force_kernel<<<warp_grid, 256, 0, st>>>(ws.rowptr, ws.rev, ws.geo, ws.edge_adj, adj_slabs ? L : 1,
                                             (size_t)ws.cap_edges,
                                             ctx->debug_keep ? ws.edge_adj + (size_t)L * ws.cap_edges : nullptr,
@@ -600,6 +603,10 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     const char* dbg = std::getenv("MLFFD_DEBUG_KEEP");
     ctx->debug_keep = dbg && dbg[0] == '1';
     if (const char* ns = std::getenv("MLFFD_STAGING")) ctx->enable_staging = ns[0] == '1';
+    // measured (C2 shapes, one B200): the pair-once reverse pass wins at H = 128 (1.49 vs 1.97 ms),
+    // but with 2 - 4 atoms per warp its two edge classes diverge and the per-directed-edge kernel
+    // is faster (Tiny 0.69 vs 0.88 ms, Ultra-tiny 0.44 vs 0.57 ms)
+    ctx->msg_bwd_mode = (H == 128) ? 2 : 0;
     if (const char* ns = std::getenv("MLFFD_MSG_BWD"))
         ctx->msg_bwd_mode = !std::strcmp(ns, "edges") ? 0 : !std::strcmp(ns, "pairs") ? 1 : 2;
     if (const char* ns = std::getenv("MLFFD_MSG_FWD")) ctx->msg_fwd_mode = !std::strcmp(ns, "rows") ? 0 : 1;
@@ -794,6 +801,7 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
     const size_t o_adj = plan.take(sizeof(float4) * E * (L + 1));   // per-layer slabs + debug sum
     const size_t o_pdist = plan.take(sizeof(float) * P);
     const size_t o_eps = plan.take(sizeof(float) * N);
+    const size_t o_virial = plan.take(sizeof(double) * 9 * max_structures);
     const int64_t C = 2 * N + 8 * max_structures + 2;   // cell capacity (grid_setup caps cells per structure)
     {
         size_t cub_cells = 0;
@@ -828,6 +836,7 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
     }
     o_s_in[L] = plan.take(sizeof(float) * N * H);
     if (ws.arena) { cudaFree(ws.arena); ws = Workspace(); }
+    ctx->last_adj_slabs = 0;
     void* arena = nullptr;
     cudaError_t e = cudaMalloc(&arena, plan.total);
     if (e != cudaSuccess) {
@@ -846,6 +855,7 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
     ws.geo = (float4*)(base + o_geo); ws.edge_adj = (float4*)(base + o_adj);
     ws.pair_dist = (float*)(base + o_pdist);
     ws.eps = (float*)(base + o_eps);
+    ws.virial64 = (double*)(base + o_virial);
     ws.cub_temp = base + o_cub; ws.cub_bytes = cub_bytes;
     ws.grids = (GridInfo*)(base + o_grids);
     ws.ncells = (int*)(base + o_ncells); ws.total_cells = ws.ncells + max_structures;
@@ -952,6 +962,29 @@ extern "C" int mlffd_filter_table(mlffd_ctx* ctx, int32_t layer, const float* di
         case 64:  return launch_filter<64>(ctx, layer, dist_d, nullptr, (int)num_pairs, nullptr, filter_d, dfilter_d, num_pairs, st);
         default:  return launch_filter<32>(ctx, layer, dist_d, nullptr, (int)num_pairs, nullptr, filter_d, dfilter_d, num_pairs, st);
     }
+}
+
+extern "C" int mlffd_virial(mlffd_ctx* ctx, const int32_t* offsets_d, int32_t num_structures,
+                            float* virial_d, void* stream) {
+    if (!ctx) return MLFFD_EINVAL;
+    if (!offsets_d || !virial_d || num_structures < 1)
+        return fail(ctx, MLFFD_EINVAL, "mlffd_virial: bad argument");
+    if (ctx->last_adj_slabs == 0 || num_structures != ctx->last_structs)
+        return fail(ctx, MLFFD_EINVAL, "mlffd_virial: call mlffd_energy_forces with forces first (same structures)");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace& ws = ctx->ws;
+    // few structures with many edges each (a periodic box) -> several chunk blocks per structure
+    const int64_t per_struct = std::max<int64_t>(1, ws.cap_edges / std::max<int64_t>(1, ctx->last_structs));
+    const int chunks = (int)std::min<int64_t>(64, std::max<int64_t>(1, per_struct / kVirialChunk));
+    if (chunks > 1) CUDA_TRY(ctx, cudaMemsetAsync(ws.virial64, 0, sizeof(double) * 9 * num_structures, st));
+    virial_kernel<<<dim3(num_structures, chunks), 256, 0, st>>>(offsets_d, num_structures, ws.rowptr, ws.geo, ws.edge_adj,
+                                                                ctx->last_adj_slabs, (size_t)ws.cap_edges,
+                                                                ws.virial64, ctx->status_d);
+    virial_finalize_kernel<<<ceil_div(9 * num_structures, 256), 256, 0, st>>>(ws.virial64, 9 * num_structures,
+                                                                               virial_d, ctx->status_d);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return MLFFD_OK;
 }
 
 extern "C" int mlffd_debug_buffer(mlffd_ctx* ctx, const char* name, int32_t layer, void** ptr_out,

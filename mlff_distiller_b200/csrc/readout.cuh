@@ -215,4 +215,65 @@ force_kernel(const int* __restrict__ rowptr, const int* __restrict__ rev,
     }
 }
 
+// Strain derivative of the energy (virial), per structure:  W_ab = dE/d eps_ab = sum_e r_bar_{e,a}
+// r_{e,b} over all directed edges of the structure, with r_e = x_src - x_dst (minimum image) the
+// edge vector the model saw and r_bar_e its adjoint (same expression as the force kernel).  The
+// reference has no working equivalent: inference/ase_calculator.py:521-588 differentiates with
+// respect to a `cell` tensor the model never uses and falls back to zeros.
+// A structure's edges are one contiguous CSR range; a block reduces one chunk of kVirialChunk edges
+// in FP64 and adds its 9 partial sums with FP64 atomics (sum order varies, the FP32 result does not).
+constexpr int kVirialChunk = 8192;
+
+__global__ void __launch_bounds__(256)
+virial_kernel(const int* __restrict__ offsets, int num_structures, const int* __restrict__ rowptr,
+              const float4* __restrict__ geo, const float4* __restrict__ edge_adj, int slabs,
+              size_t slab_stride, double* __restrict__ virial, const DeviceStatus* __restrict__ status) {
+    if (status->overflow) return;
+    __shared__ double part[8][9];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    // blockIdx.x walks (structure, chunk) pairs; chunks per structure are not known on the host
+    // (edge counts live on the device), so every structure gets gridDim.y chunk slots
+    const int b = blockIdx.x;
+    if (b >= num_structures) return;
+    const int e_lo = __ldg(rowptr + __ldg(offsets + b)), e_hi = __ldg(rowptr + __ldg(offsets + b + 1));
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c0 = e_lo + (int)blockIdx.y * kVirialChunk; c0 < e_hi; c0 += (int)gridDim.y * kVirialChunk) {
+        const int c1 = min(c0 + kVirialChunk, e_hi);
+        for (int e = c0 + (int)threadIdx.x; e < c1; e += (int)blockDim.x) {
+            const float4 g = __ldg(geo + e);
+            const float3 rb = edge_position_adjoint(g, edge_adjoint_sum(edge_adj, e, slabs, slab_stride));
+            const float q = g.w + kUnitEps;
+            const float r[3] = {g.x * q, g.y * q, g.z * q};
+            const float a[3] = {rb.x, rb.y, rb.z};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc[3 * i + j] += (double)a[i] * (double)r[j];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) part[wib][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += part[w][threadIdx.x];
+        if (gridDim.y == 1) virial[(size_t)b * 9 + threadIdx.x] = v;
+        else atomicAdd(virial + (size_t)b * 9 + threadIdx.x, v);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+virial_finalize_kernel(const double* __restrict__ virial, int count, float* __restrict__ out,
+                       const DeviceStatus* __restrict__ status) {
+    if (status->overflow) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (float)virial[i];
+}
+
 }  // namespace mlffd

@@ -105,6 +105,10 @@ class Engine:
             self._ctx, _ptr(z), _ptr(pos), _ptr(offsets), int(n_structs), int(pos.shape[0]),
             _ptr(cells), _ptr(pbc), _ptr(energy), _ptr(forces), self._stream()))
 
+    def virial_async(self, offsets: torch.Tensor, n_structs: int, virial: torch.Tensor):
+        """dE_b / d strain [B,3,3] of the last energy_forces_async call (same stream, forces requested)."""
+        self._check(self.lib.mlffd_virial(self._ctx, _ptr(offsets), int(n_structs), _ptr(virial), self._stream()))
+
     def neighbor_list_async(self, pos: torch.Tensor, offsets: torch.Tensor, n_structs: int,
                             cells: Optional[torch.Tensor] = None, pbc: Optional[torch.Tensor] = None):
         self._check(self.lib.mlffd_neighbor_list(

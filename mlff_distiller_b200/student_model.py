@@ -295,6 +295,30 @@ class StudentForceField(nn.Module):
         Returns (E [B], F [N,3])."""
         return self._run(z_i32, pos_f32, offsets_i32, n_structs, cells, pbc, True, max_atoms)
 
+    def virial_of_last_call(self, offsets_i32: torch.Tensor, n_structs: int) -> torch.Tensor:
+        """dE_b / d strain, ``[B,3,3]``, of the evaluation that just ran through
+        :meth:`energy_and_forces_packed` / :meth:`forward_with_analytical_forces` (same stream).
+        W_ac = sum over directed edges of (dE/dr_e)_a (r_e)_c with x -> (1 + eps) x; stress = W / V."""
+        w = torch.empty((n_structs, 3, 3), dtype=torch.float32, device=offsets_i32.device)
+        self.engine().virial_async(offsets_i32, n_structs, w)
+        return w
+
+    def predict_energy_forces_stress(self, atomic_numbers: torch.Tensor, positions: torch.Tensor,
+                                     cell: torch.Tensor, pbc: Optional[torch.Tensor] = None
+                                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """(E, F [N,3], stress [3,3] in eV/A^3) for one structure with a cell.  The stress is the
+        symmetrised strain derivative of the energy divided by the cell volume -- the quantity
+        inference/ase_calculator.py:521-588 tries to obtain (and returns zeros for, because the
+        reference model never reads its ``cell`` argument)."""
+        z, pos, offsets, nb, cells_d, pbc_d = self._prepare(atomic_numbers, positions, cell, pbc, None)
+        e, f = self._run(z, pos.detach().contiguous(), offsets, nb, cells_d, pbc_d, True)
+        w = self.virial_of_last_call(offsets, nb)[0]
+        vol = torch.linalg.det(torch.as_tensor(cell, dtype=torch.float64).reshape(3, 3)).abs()
+        if float(vol) <= 0.0:
+            raise ValueError("stress needs a cell with non-zero volume")
+        stress = (0.5 * (w + w.T).double() / vol).to(torch.float32)
+        return e.reshape(()), f, stress
+
     # ---- checkpoints ----------------------------------------------------------------------
     def save(self, path: Union[str, Path]):
         """Reference inference checkpoint layout (student_model.py:1075-1099)."""

@@ -190,13 +190,16 @@ def readout(w, s):
 
 def forward(w, atomic_numbers: torch.Tensor, positions: torch.Tensor, cutoff: float,
             batch: Optional[torch.Tensor] = None, edge_index: Optional[torch.Tensor] = None,
-            shift_vectors: Optional[torch.Tensor] = None, keep: Optional[dict] = None):
+            shift_vectors: Optional[torch.Tensor] = None, keep: Optional[dict] = None,
+            strain: Optional[torch.Tensor] = None):
     """StudentForceField.forward (student_model.py:675-757).
 
     ``edge_index`` defaults to the dense open-boundary graph; a periodic caller injects its own
     edge list and Cartesian ``shift_vectors`` (edge vector = x_src - x_dst - shift).
     ``keep`` (a dict) receives every intermediate, with ``retain_grad`` when differentiable, so
     tests can compare the CUDA stages and adjoints one by one.
+    ``strain`` ``[B,3,3]`` deforms every edge vector of structure b as r -> (1 + eps_b) r (positions
+    and cell strained together), the handle :func:`energy_forces_virial` differentiates through.
     """
     n = atomic_numbers.shape[0]
     if batch is None:
@@ -210,6 +213,8 @@ def forward(w, atomic_numbers: torch.Tensor, positions: torch.Tensor, cutoff: fl
     edge_vector = positions[src] - positions[dst]
     if shift_vectors is not None:
         edge_vector = edge_vector - shift_vectors
+    if strain is not None:
+        edge_vector = edge_vector + torch.einsum("eab,eb->ea", strain[batch[src]], edge_vector)
     d, unit, edge_rbf = edge_features(w, edge_vector, cutoff)
 
     def _keep(name, t):
@@ -253,6 +258,24 @@ def energy_and_forces(w, atomic_numbers, positions, cutoff: float, batch=None, e
     e = forward(w, atomic_numbers, pos, cutoff, batch, edge_index, shift_vectors, keep)
     grad = torch.autograd.grad(e, pos, grad_outputs=torch.ones_like(e))[0]
     return e.detach(), -grad
+
+
+def energy_forces_virial(w, atomic_numbers, positions, cutoff: float, batch=None, edge_index=None,
+                         shift_vectors=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(E [B] or scalar, F [N,3], W [B,3,3]) with W_ac = dE_b / d eps_ac at eps = 0 by autograd.
+    stress = sym(W) / V.  The reference has no working counterpart: its _compute_stress
+    (inference/ase_calculator.py:521-588) asks autograd for dE/d(cell) of a model that never reads
+    the cell, catches the error and returns zeros -- so this function is the definition the CUDA
+    virial is tested against, together with finite differences of the energy (tests)."""
+    n = atomic_numbers.shape[0]
+    if batch is None:
+        batch = torch.zeros(n, dtype=torch.long)
+    nb = int(batch.max()) + 1 if n else 1
+    pos = positions.detach().clone().requires_grad_(True)
+    eps = torch.zeros(nb, 3, 3, dtype=positions.dtype, requires_grad=True)
+    e = forward(w, atomic_numbers, pos, cutoff, batch, edge_index, shift_vectors, None, eps)
+    gpos, geps = torch.autograd.grad(e.sum(), (pos, eps))
+    return e.detach(), -gpos, geps
 
 
 def energy_and_forces_with_adjoints(w, atomic_numbers, positions, cutoff: float, batch=None,

@@ -486,11 +486,12 @@ def test_message_kernel_variants_agree(variant_name):
         e, f = model.energy_and_forces_packed(z_d, p_d, o_d, len(structs))
         return e.cpu().numpy(), f.cpu().numpy()
 
-    e_def, f_def = run({})
+    e_def, f_def = run({"MLFFD_MSG_FWD": "pipe", "MLFFD_MSG_BWD": "pipe"})   # falls back to pairs for H != 128
     e_pairs, f_pairs = run({"MLFFD_MSG_FWD": "rows", "MLFFD_MSG_BWD": "pairs"})
     assert np.array_equal(e_def, e_pairs) and np.array_equal(f_def, f_pairs)
     for depth in ("2", "8"):
-        e_d, f_d = run({"MLFFD_PIPE_DEPTH_FWD": depth, "MLFFD_PIPE_DEPTH_BWD": "2" if depth == "2" else "4"})
+        e_d, f_d = run({"MLFFD_MSG_FWD": "pipe", "MLFFD_MSG_BWD": "pipe", "MLFFD_PIPE_DEPTH_FWD": depth,
+                        "MLFFD_PIPE_DEPTH_BWD": "2" if depth == "2" else "4"})
         assert np.array_equal(e_def, e_d) and np.array_equal(f_def, f_d)
     e_edges, f_edges = run({"MLFFD_MSG_FWD": "rows", "MLFFD_MSG_BWD": "edges"})
     assert np.array_equal(e_def, e_edges)
