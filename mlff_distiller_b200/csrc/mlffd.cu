@@ -81,6 +81,7 @@ struct mlffd_ctx {
     int neighbor_mode = 0;   // 0 auto, 1 sweep, 2 cells (env MLFFD_NEIGHBOR)
     int struct_hint = 0;     // max atoms per structure promised by the caller (0 = unknown)
     bool enable_staging = false;     // env MLFFD_STAGING=1
+    uint32_t pipe_configured = 0;    // bit per pipelined-kernel instantiation whose smem attribute is set on this device
     int last_adj_slabs = 0;          // edge-adjoint slabs written by the last force evaluation (0 = none)
     int msg_bwd_mode = 2;            // env MLFFD_MSG_BWD = edges (0) | pairs (1) | pipe (2)
     int msg_fwd_mode = 1;            // env MLFFD_MSG_FWD = rows (0) | pipe (1)
@@ -249,10 +250,11 @@ void launch_forward_pipe_d(mlffd_ctx* ctx, int l, int grid, int N, cudaStream_t 
     Workspace& ws = ctx->ws;
     auto kernel = message_forward_pipe_kernel<LAYER0, D>;
     constexpr size_t smem = message_forward_pipe_smem<D>();
-    static bool configured = false;
-    if (!configured) {
+    // per context (device), not per process: a second context on another GPU needs the attribute too
+    constexpr uint32_t bit = 1u << (2 * D + (LAYER0 ? 1 : 0) + 0);
+    if (!(ctx->pipe_configured & bit)) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        ctx->pipe_configured |= bit;
     }
     kernel<<<grid, 32 * kPipeWarps, smem, st>>>(ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l],
                                               LAYER0 ? nullptr : ws.v_in[l], ws.s_msg[l], ws.v_msg[l], N,
@@ -275,10 +277,11 @@ void launch_backward_pipe_d(mlffd_ctx* ctx, int l, int grid, const float* sb, co
     Workspace& ws = ctx->ws;
     auto kernel = message_backward_pipe_kernel<LAYER0, D>;
     constexpr size_t smem = message_backward_pipe_smem<D>();
-    static bool configured = false;
-    if (!configured) {
+    // per context (device), not per process: a second context on another GPU needs the attribute too
+    constexpr uint32_t bit = 1u << (2 * D + (LAYER0 ? 1 : 0) + 14);
+    if (!(ctx->pipe_configured & bit)) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        ctx->pipe_configured |= bit;
     }
     kernel<<<grid, 32 * kPipeWarps, smem, st>>>(ws.rowptr, ws.col, ws.pair, ws.rev, ws.geo, ws.filt[l], ws.dfilt[l],
                                               ws.s_in[l], LAYER0 ? nullptr : ws.v_in[l], sb, vb, sb_in, vb_in,
