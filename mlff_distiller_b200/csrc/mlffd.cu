@@ -81,6 +81,8 @@ struct mlffd_ctx {
     int neighbor_mode = 0;   // 0 auto, 1 sweep, 2 cells (env MLFFD_NEIGHBOR)
     int struct_hint = 0;     // max atoms per structure promised by the caller (0 = unknown)
     bool enable_staging = false;     // env MLFFD_STAGING=1
+    int readout_mode = 0;            // env MLFFD_READOUT: 0 = by size, 1 = tile, 2 = warp
+    bool readout_configured = false; // smem attribute of readout_tile_kernel set on this device
     uint32_t pipe_configured = 0;    // bit per pipelined-kernel instantiation whose smem attribute is set on this device
     int last_adj_slabs = 0;          // edge-adjoint slabs written by the last force evaluation (0 = none)
     int msg_bwd_mode = 2;            // env MLFFD_MSG_BWD = edges (0) | pairs (1) | pipe (2)
@@ -386,8 +388,17 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
 
     const bool want_forces = forces != nullptr;
     auto adj = [&](int l) { return ctx->debug_keep ? l : (l & 1); };
-    readout_kernel<H><<<clamp_grid(ceil_div(N, 8 * 4), kNumSMs * 8), 256, 0, st>>>(ws.s_in[L], ctx->head, ws.eps,
-                                                 want_forces ? ws.sbar[adj(L - 1)] : nullptr, N, status);
+    // enough 64-atom tiles to fill the GPU: register-tiled GEMMs (env MLFFD_READOUT = tile | warp forces one)
+    if (H == 128 && (ctx->readout_mode == 1 || (ctx->readout_mode == 0 && N >= 64 * kNumSMs))) {
+        if (!ctx->readout_configured) {
+            cudaFuncSetAttribute(readout_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)readout_tile_smem_bytes());
+            ctx->readout_configured = true;
+        }
+        readout_tile_kernel<<<clamp_grid(ceil_div(N, kTileRows), kNumSMs * 3), kGemmThreads, readout_tile_smem_bytes(), st>>>(
+            ws.s_in[L], ctx->head, ws.eps, want_forces ? ws.sbar[adj(L - 1)] : nullptr, N, status);
+    } else
+        readout_kernel<H><<<clamp_grid(ceil_div(N, 8 * 4), kNumSMs * 8), 256, 0, st>>>(ws.s_in[L], ctx->head, ws.eps,
+                                                     want_forces ? ws.sbar[adj(L - 1)] : nullptr, N, status);
     LAUNCHED(ctx, "readout_kernel", MLFFD_STAGE_READOUT, st);
     structure_energy_kernel<<<clamp_grid(ceil_div(n_structs, 8), kNumSMs * 8), 256, 0, st>>>(
         ws.eps, offsets, n_structs, energy, status);
@@ -612,6 +623,7 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     ctx->msg_bwd_mode = (H == 128) ? 2 : 0;
     if (const char* ns = std::getenv("MLFFD_MSG_BWD"))
         ctx->msg_bwd_mode = !std::strcmp(ns, "edges") ? 0 : !std::strcmp(ns, "pairs") ? 1 : 2;
+    if (const char* ns = std::getenv("MLFFD_READOUT")) ctx->readout_mode = !std::strcmp(ns, "tile") ? 1 : 2;
     if (const char* ns = std::getenv("MLFFD_MSG_FWD")) ctx->msg_fwd_mode = !std::strcmp(ns, "rows") ? 0 : 1;
     if (const char* ns = std::getenv("MLFFD_PIPE_DEPTH_FWD")) ctx->pipe_depth_fwd = std::atoi(ns);
     if (const char* ns = std::getenv("MLFFD_PIPE_DEPTH_BWD")) ctx->pipe_depth_bwd = std::atoi(ns);

@@ -13,6 +13,7 @@
 // analytical_gradients.accumulate_forces_from_edges (:325-339).
 #pragma once
 #include "common.cuh"
+#include "tile_gemm.cuh"
 
 namespace mlffd {
 
@@ -139,6 +140,117 @@ readout_kernel(const float* __restrict__ s, HeadWeights w, float* __restrict__ e
             }
         }
         __syncwarp();
+    }
+}
+
+// Tiled variant of readout_kernel for H = 128: 64 atoms per block, the four small GEMMs (head
+// forward H -> H/2 -> H/4, reverse H/4 -> H/2 -> H) on the register-tiled FFMA block of
+// tile_gemm.cuh with weights staged in shared memory, so every weight fetched feeds 4 x RN FMAs
+// instead of 4 (the warp-per-4-atoms kernel above is bound by L1 weight loads).  Pre-activations
+// stay in registers between the forward and the reverse half (same thread <-> same rows/columns).
+constexpr size_t readout_tile_smem_bytes() { return sizeof(float) * (size_t)(128 * kAStride + 128 * 64); }
+
+__global__ void __launch_bounds__(kGemmThreads)
+readout_tile_kernel(const float* __restrict__ s, HeadWeights w, float* __restrict__ eps,
+                    float* __restrict__ sbar, int num_atoms, const DeviceStatus* __restrict__ status) {
+    constexpr int H = 128, H2 = 64, H4 = 32;
+    if (status->overflow) return;
+    extern __shared__ __align__(16) float smem[];
+    float* A_s = smem;                      // [K <= 128][AS]  activations, k-major
+    float* W_s = A_s + H * kAStride;        // [K][N] weight chunk, K*N <= 8192
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int num_tiles = (num_atoms + kTileRows - 1) / kTileRows;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int a0 = tile * kTileRows;
+        __syncthreads();   // previous tile done with A_s / W_s
+        // stage s rows k-major (row fastest across threads: conflict-free smem stores)
+        for (int idx = tid; idx < kTileRows * (H / 4); idx += kGemmThreads) {
+            const int m = idx % kTileRows, c4 = idx / kTileRows;
+            const int atom = a0 + m;
+            const float4 v = (atom < num_atoms) ? ldg4(s + (size_t)atom * H + 4 * c4) : make4(0.f);
+            A_s[(4 * c4 + 0) * kAStride + m] = v.x;
+            A_s[(4 * c4 + 1) * kAStride + m] = v.y;
+            A_s[(4 * c4 + 2) * kAStride + m] = v.z;
+            A_s[(4 * c4 + 3) * kAStride + m] = v.w;
+        }
+        load_weight_chunk<H2>(W_s, w.A1t, H2, 0, 0, H);
+        __syncthreads();
+        // ---- y1 = s A1^T + a1  (K = 128, N = 64) ----
+        float y1[4][TileTraits<H2>::RN];
+        tile_zero<H2>(y1);
+        tile_fma<H2>(y1, A_s, W_s, H, ty, tx);
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < TileTraits<H2>::RN; ++c) {
+            const int n = tile_col<H2>(tx, c);
+            const float b = __ldg(w.a1 + n);
+            float h[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { y1[r][c] += b; h[r] = siluf_(y1[r][c]); }
+            st4(A_s + n * kAStride + ty * 4, make_float4(h[0], h[1], h[2], h[3]));
+        }
+        load_weight_chunk<H4>(W_s, w.A2t, H4, 0, 0, H2);
+        __syncthreads();
+        // ---- y2 = h1 A2^T + a2  (K = 64, N = 32);  eps = A3 . SiLU(y2) + a3 ----
+        float y2[4][TileTraits<H4>::RN];
+        tile_zero<H4>(y2);
+        tile_fma<H4>(y2, A_s, W_s, H2, ty, tx);
+        __syncthreads();
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < TileTraits<H4>::RN; ++c) {
+            const int n = tile_col<H4>(tx, c);
+            const float b = __ldg(w.a2 + n), a3 = __ldg(w.A3 + n);
+            float yb[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float y = y2[r][c] + b;
+                part[r] = fmaf(siluf_(y), a3, part[r]);
+                yb[r] = a3 * silu_gradf_(y);          // adjoint of the layer-2 pre-activation
+            }
+            st4(A_s + n * kAStride + ty * 4, make_float4(yb[0], yb[1], yb[2], yb[3]));
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) part[r] += __shfl_xor_sync(0xffffffffu, part[r], o);   // over tx
+            const int atom = a0 + ty * 4 + r;
+            if (tx == 0 && atom < num_atoms) eps[atom] = part[r] + __ldg(w.a3);
+        }
+        if (sbar == nullptr) continue;
+        load_weight_chunk<H2>(W_s, w.A2, H2, 0, 0, H4);
+        __syncthreads();
+        // ---- y1_bar = (y2_bar A2) * SiLU'(y1)  (K = 32, N = 64) ----
+        float hb[4][TileTraits<H2>::RN];
+        tile_zero<H2>(hb);
+        tile_fma<H2>(hb, A_s, W_s, H4, ty, tx);
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < TileTraits<H2>::RN; ++c) {
+            const int n = tile_col<H2>(tx, c);
+            float v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[r] = hb[r][c] * silu_gradf_(y1[r][c]);
+            st4(A_s + n * kAStride + ty * 4, make_float4(v[0], v[1], v[2], v[3]));
+        }
+        load_weight_chunk<H>(W_s, w.A1, H, 0, 0, H2);
+        __syncthreads();
+        // ---- s_bar = y1_bar A1  (K = 64, N = 128) ----
+        float sb[4][TileTraits<H>::RN];
+        tile_zero<H>(sb);
+        tile_fma<H>(sb, A_s, W_s, H2, ty, tx);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int atom = a0 + ty * 4 + r;
+            if (atom >= num_atoms) continue;
+#pragma unroll
+            for (int g = 0; g < TileTraits<H>::NG; ++g) {
+                float v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = sb[r][g * 4 + q];
+                stv<4>(sbar + (size_t)atom * H + g * TileTraits<H>::GROUP_STRIDE + tx * 4, v);
+            }
+        }
     }
 }
 

@@ -496,3 +496,34 @@ def test_message_kernel_variants_agree(variant_name):
     e_edges, f_edges = run({"MLFFD_MSG_FWD": "rows", "MLFFD_MSG_BWD": "edges"})
     assert np.array_equal(e_def, e_edges)
     assert np.max(np.abs(f_def - f_edges)) <= 2e-5
+
+
+def test_tiled_readout_matches_warp_readout_and_oracle():
+    """readout_tile_kernel (H = 128, large batches) against the warp kernel and the FP64 oracle."""
+    from mlff_distiller_b200 import synthetic
+    structs = synthetic.druglike_batch(9, first=700, ragged=True) + [synthetic.water()]
+    z, pos, off = synthetic.concatenate(structs)
+    pos32 = pos.astype(np.float32)
+    dev = "cuda:0"
+    z_d = torch.from_numpy(z.astype(np.int32)).to(dev)
+    p_d = torch.from_numpy(pos32).to(dev)
+    o_d = torch.from_numpy(off.astype(np.int32)).to(dev)
+    out = {}
+    for mode in ("tile", "warp"):
+        os.environ["MLFFD_READOUT"] = mode
+        try:
+            model, state, cfg = _model("original")
+            model.engine()
+        finally:
+            os.environ.pop("MLFFD_READOUT", None)
+        e, f = model.energy_and_forces_packed(z_d, p_d, o_d, len(structs))
+        e0 = model.forward(torch.from_numpy(z), torch.from_numpy(pos32), batch=po.batch_from_offsets(off))
+        assert np.array_equal(e0.cpu().numpy(), e.cpu().numpy())      # energy-only path, same kernel
+        out[mode] = (e.cpu().numpy().astype(np.float64), f.cpu().numpy().astype(np.float64))
+    e_ref, f_ref = po.evaluate(state, cfg["cutoff"], z, pos32.astype(np.float64), off, dtype=torch.float64)
+    counts = np.diff(off)
+    for mode in out:
+        assert np.max(np.abs(out[mode][0] - e_ref) / counts) <= E_TOL, mode
+        assert np.max(np.abs(out[mode][1] - f_ref)) <= 3e-5, mode
+    assert np.max(np.abs(out["tile"][0] - out["warp"][0]) / counts) <= 2e-6
+    assert np.max(np.abs(out["tile"][1] - out["warp"][1])) <= 1e-5
