@@ -138,6 +138,17 @@ int mlffd_energy_forces(mlffd_ctx* ctx, const int32_t* z_d, const float* pos_d,
 int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out);
 
 /*
+ * Non-blocking companion of mlffd_get_status for callers that keep several steps in flight (the
+ * pipelined batched-structure interface, StudentForceFieldCalculator.evaluate_stream): enqueues on
+ * `stream` a copy of the device status words of the step enqueued just before it into
+ * `status_out`, six int32 in pinned host (or device) memory:
+ *   [0] num_edges  [1] num_pairs  [2] overflow  [3] max_degree  [4] overflow_events (sticky)
+ *   [5] hint_violation
+ * Valid once the stream has passed this point (record an event after the call).  Never synchronises.
+ */
+int mlffd_status_async(mlffd_ctx* ctx, int32_t* status_out, void* stream);
+
+/*
  * Optional promise that no structure of the coming calls has more than this many atoms (0 =
  * unknown, the default).  With small structures (<= 113 atoms at H = 128) the message kernels
  * switch to a structure-per-block variant that stages the structure's feature rows in shared

@@ -13,7 +13,7 @@ __version__ = "0.1.0"
 
 def __getattr__(name):
     # Lazy: importing the package must not require the CUDA library (CPU build/ABI checks).
-    if name in ("StudentForceField", "radius_graph"):
+    if name in ("StudentForceField", "EnergyOnlyWrapper", "radius_graph"):
         from . import student_model
         return getattr(student_model, name)
     if name == "StudentForceFieldCalculator":

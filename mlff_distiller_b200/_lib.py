@@ -17,7 +17,7 @@ from typing import List, Optional
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libmlffd.so"
 SOURCES = ["mlffd.cu"]
-HEADERS = ["common.cuh", "neighbor.cuh", "cell_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh", "message_staged.cuh",
+HEADERS = ["common.cuh", "neighbor.cuh", "cell_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh", "message_pipe.cuh", "message_staged.cuh",
            "update.cuh", "readout.cuh", "md.cuh", "../../include/mlffd.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -29,6 +29,7 @@ EXPORTS = [
     "mlffd_energy_forces", "mlffd_get_status", "mlffd_filter_table", "mlffd_debug_buffer",
     "mlffd_profile_enable", "mlffd_profile_read", "mlffd_stage_name",
     "mlffd_md_kick_drift", "mlffd_md_kick_energy", "mlffd_set_structure_hint", "mlffd_virial",
+    "mlffd_status_async",
 ]
 NUM_STAGES = 10
 
@@ -125,6 +126,8 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     lib.mlffd_energy_forces.argtypes = [vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp]
     lib.mlffd_get_status.restype = ctypes.c_int
     lib.mlffd_get_status.argtypes = [vp, ctypes.POINTER(MlffdStatus)]
+    lib.mlffd_status_async.restype = ctypes.c_int
+    lib.mlffd_status_async.argtypes = [vp, vp, vp]
     lib.mlffd_filter_table.restype = ctypes.c_int
     lib.mlffd_filter_table.argtypes = [vp, i32, vp, i64, vp, vp, vp]
     lib.mlffd_debug_buffer.restype = ctypes.c_int

@@ -18,7 +18,7 @@ import logging
 import time
 import warnings
 from pathlib import Path
-from typing import Any, Dict, List, Optional, Sequence, Union
+from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -105,7 +105,7 @@ class StudentForceFieldCalculator(_AseCalculator):
         if dtype != torch.float32:
             raise ValueError("the CUDA path computes in float32; use the reference for other dtypes")
         ignored = [n for n, v in (("use_compile", use_compile), ("use_fp16", use_fp16),
-                                  ("use_jit", use_jit), ("batch_size", batch_size)) if v]
+                                  ("batch_size", batch_size)) if v]
         if ignored:
             logger.info("StudentForceFieldCalculator: ignoring %s (superseded by the CUDA path)", ignored)
         self.model = self._load_model()
@@ -120,12 +120,25 @@ class StudentForceFieldCalculator(_AseCalculator):
 
     # ---- model ----------------------------------------------------------------------------
     def _load_model(self) -> StudentForceField:
-        if not self.checkpoint_path.exists():
+        if self.use_jit:
+            # inference/ase_calculator.py:216-236: the model comes from the TorchScript archive.
+            # Its weights are read out of the archive and evaluated by the CUDA path (the archive's
+            # own graph is the reference's eager ops; it is not executed).
+            if not self.jit_path:
+                raise ValueError("use_jit=True but jit_path not provided")
+            if not self.jit_path.exists():
+                raise FileNotFoundError(
+                    f"TorchScript model not found: {self.jit_path}\n"
+                    f"Please export model to TorchScript first using scripts/export_to_torchscript.py")
+            source = self.jit_path
+        else:
+            source = self.checkpoint_path
+        if not source.exists():
             raise FileNotFoundError(
-                f"Checkpoint not found: {self.checkpoint_path}\n"
+                f"Checkpoint not found: {source}\n"
                 f"Please ensure the model has been trained and checkpoint saved.")
         try:
-            model = StudentForceField.load(self.checkpoint_path, device=str(self.device),
+            model = StudentForceField.load(source, device=str(self.device),
                                            precision=self.precision, pbc_mode=self.pbc_mode)
             model.eval()
             model.engine()  # fail loudly now if the CUDA library / device is missing
@@ -133,7 +146,7 @@ class StudentForceFieldCalculator(_AseCalculator):
         except FileNotFoundError:
             raise
         except Exception as e:
-            raise RuntimeError(f"Failed to load model from {self.checkpoint_path}: {e}") from e
+            raise RuntimeError(f"Failed to load model from {source}: {e}") from e
 
     # ---- single structure -----------------------------------------------------------------
     def calculate(self, atoms=None, properties: Sequence[str] = ("energy", "forces"),
@@ -288,14 +301,21 @@ class StudentForceFieldCalculator(_AseCalculator):
             # micro-batches that fit the workspace (a 100 k-structure sweep does not fit in one call)
             from .sharding import chunk_by_budget
             offs = np.concatenate([[0], np.cumsum(counts)])
+            chunks = chunk_by_budget(counts, self.max_atoms_per_call, 1 << 20)
             e_parts, f_parts = [], []
-            for a, b in chunk_by_budget(counts, self.max_atoms_per_call, 1 << 20):
-                sl = slice(int(offs[a]), int(offs[b]))
-                e, f = self.evaluate_arrays(numbers[sl], positions[sl], counts[a:b],
-                                            None if cells is None else cells[a:b],
-                                            None if pbcs is None else pbcs[a:b])
-                e_parts.append(e)
-                f_parts.append(f)
+            if cells is None or pbcs is None or not np.any(pbcs):
+                # open boundaries: keep the copies of chunk k+1 / k-1 under the kernels of chunk k
+                gen = ((numbers[int(offs[a]):int(offs[b])], positions[int(offs[a]):int(offs[b])], counts[a:b])
+                       for a, b in chunks)
+                for e, f in self.evaluate_stream(gen):
+                    e_parts.append(e)
+                    f_parts.append(f)
+            else:
+                for a, b in chunks:
+                    sl = slice(int(offs[a]), int(offs[b]))
+                    e, f = self.evaluate_arrays(numbers[sl], positions[sl], counts[a:b], cells[a:b], pbcs[a:b])
+                    e_parts.append(e)
+                    f_parts.append(f)
             return np.concatenate(e_parts), np.concatenate(f_parts)
         dev = self.device
         nb, n = len(counts), len(numbers)
@@ -326,6 +346,136 @@ class StudentForceFieldCalculator(_AseCalculator):
             raise RuntimeError(f"Failed to calculate properties for {len(numbers)} atoms: {e}") from e
         self._n_calls += 1
         return energies, forces
+
+    # ---- pipelined batches -----------------------------------------------------------------
+    def evaluate_stream(self, batches: Iterable[Tuple[np.ndarray, np.ndarray, np.ndarray]]
+                        ) -> Iterator[Tuple[np.ndarray, np.ndarray]]:
+        """Screening-sweep form of :meth:`evaluate_arrays`: takes an iterable of
+        ``(numbers, positions, counts)`` host batches (open boundaries) and yields
+        ``(energies [B] float32, forces [N,3] float32)`` per batch, in order.
+
+        Same work per batch as ``evaluate_arrays`` -- validation, host -> pinned -> device copy of
+        the inputs, one fused energy+force step, device -> pinned -> host copy of the results --
+        but two batches are in flight: while the kernels of batch k run on the compute stream, the
+        host converts and uploads batch k+1 on a copy stream and the results of batch k-1 come
+        back on another, so the GPU never waits for the host.  The step's status words travel
+        with the results (``mlffd_status_async``): an edge-workspace overflow is detected when the
+        batch is collected and that batch is re-run through the blocking path."""
+        dev = self.device
+        eng = self.model.engine()
+        compute = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_streams", None) is None:
+            self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            self._slots = [{"cap_n": 0, "cap_b": 0} for _ in range(2)]
+        s_in, s_out = self._copy_streams
+
+        def prepare(batch, slot):
+            numbers, positions, counts = (np.asarray(batch[0]), np.asarray(batch[1]),
+                                          np.asarray(batch[2], dtype=np.int64))
+            self._validate_arrays(numbers, positions, counts)
+            nb, n = len(counts), len(numbers)
+            if n > self.max_atoms_per_call and nb > 1:
+                raise ValueError(f"evaluate_stream: a batch holds {n} atoms; keep batches under "
+                                 f"max_atoms_per_call = {self.max_atoms_per_call}")
+            self._grow_slot(slot, n, nb)
+            slot["n"], slot["nb"], slot["max_count"] = n, nb, int(counts.max())
+            slot["z_h"][:n].copy_(torch.from_numpy(np.ascontiguousarray(numbers)))
+            slot["pos_h"][:n].copy_(torch.from_numpy(np.ascontiguousarray(positions)))
+            off_np = slot["off_h"].numpy()
+            off_np[0] = 0
+            np.cumsum(counts, out=off_np[1:nb + 1])
+            with torch.cuda.stream(s_in):
+                if slot.get("compute_done") is not None:   # the slot's previous tenant has been read
+                    s_in.wait_event(slot["compute_done"])
+                slot["z_d"][:n].copy_(slot["z_h"][:n], non_blocking=True)
+                slot["pos_d"][:n].copy_(slot["pos_h"][:n], non_blocking=True)
+                slot["off_d"][:nb + 1].copy_(slot["off_h"][:nb + 1], non_blocking=True)
+                slot["h2d_done"] = s_in.record_event()
+            return slot
+
+        def launch(slot):
+            n, nb = slot["n"], slot["nb"]
+            compute.wait_event(slot["h2d_done"])
+            eng.set_structure_hint(slot["max_count"] if nb >= 32 else 0)
+            eng.ensure(n, nb, self.model._edges_per_atom)
+            eng.energy_forces_async(slot["z_d"][:n], slot["pos_d"][:n], slot["off_d"][:nb + 1], nb,
+                                    slot["e_d"][:nb], slot["f_d"][:n])
+            eng.status_async(slot["status_h"])   # pinned host words, ordered behind the step
+            slot["compute_done"] = compute.record_event()
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(slot["compute_done"])
+                slot["e_h"][:nb].copy_(slot["e_d"][:nb], non_blocking=True)
+                slot["f_h"][:n].copy_(slot["f_d"][:n], non_blocking=True)
+                slot["out_done"] = s_out.record_event()
+
+        def collect(slot):
+            n, nb = slot["n"], slot["nb"]
+            slot["out_done"].synchronize()
+            status = slot["status_h"].numpy()
+            if status[2] or status[5]:   # overflow / hint violation: blocking path grows and re-runs
+                torch.cuda.synchronize(dev)
+                try:
+                    e_d, f_d = self.model.energy_and_forces_packed(
+                        slot["z_d"][:n], slot["pos_d"][:n], slot["off_d"][:nb + 1], nb,
+                        max_atoms=slot["max_count"])
+                    energies, forces = e_d.cpu().numpy(), f_d.cpu().numpy()
+                except Exception as e:
+                    raise RuntimeError(f"Failed to calculate properties for {n} atoms: {e}") from e
+            else:
+                energies = slot["e_h"][:nb].numpy().copy()
+                forces = slot["f_h"][:n].numpy().copy()
+            self._n_calls += 1
+            return energies, forces
+
+        it = iter(batches)
+        first = next(it, None)
+        if first is None:
+            return
+        k, prev = 0, None
+        cur = prepare(first, self._slots[0])
+        while cur is not None:
+            launch(cur)
+            if prev is not None:
+                yield collect(prev)
+            nxt_batch = next(it, None)
+            k += 1
+            nxt = prepare(nxt_batch, self._slots[k % 2]) if nxt_batch is not None else None
+            prev, cur = cur, nxt
+        yield collect(prev)
+
+    def _validate_arrays(self, numbers, positions, counts):
+        if len(numbers) == 0 or len(counts) == 0 or np.any(counts == 0):
+            raise ValueError("Cannot calculate properties for empty structure")
+        if int(counts.sum()) != len(numbers) or len(positions) != len(numbers):
+            raise ValueError("counts / numbers / positions disagree on the number of atoms")
+        if np.any(numbers < 1) or np.any(numbers > min(118, self.model.max_z)):
+            raise ValueError(f"Invalid atomic numbers: must be 1-{min(118, self.model.max_z)}")
+        if not np.isfinite(positions).all():
+            raise ValueError("Positions contain NaN or Inf values")
+
+    def _grow_slot(self, slot, n_atoms: int, n_structs: int):
+        """Grow-only pinned + device buffers of one pipeline slot."""
+        if slot["cap_n"] >= n_atoms and slot["cap_b"] >= n_structs:
+            return
+        dev = self.device
+        torch.cuda.synchronize(dev)   # nothing may still read the buffers being replaced
+        cap_n = max(n_atoms, int(1.25 * slot["cap_n"]))
+        cap_b = max(n_structs, int(1.25 * slot["cap_b"]))
+        slot.update({
+            "cap_n": cap_n, "cap_b": cap_b,
+            "z_h": torch.empty(cap_n, dtype=torch.int32).pin_memory(),
+            "pos_h": torch.empty((cap_n, 3), dtype=torch.float32).pin_memory(),
+            "off_h": torch.empty(cap_b + 1, dtype=torch.int32).pin_memory(),
+            "e_h": torch.empty(cap_b, dtype=torch.float32).pin_memory(),
+            "f_h": torch.empty((cap_n, 3), dtype=torch.float32).pin_memory(),
+            "status_h": torch.zeros(6, dtype=torch.int32).pin_memory(),
+            "z_d": torch.empty(cap_n, dtype=torch.int32, device=dev),
+            "pos_d": torch.empty((cap_n, 3), dtype=torch.float32, device=dev),
+            "off_d": torch.empty(cap_b + 1, dtype=torch.int32, device=dev),
+            "e_d": torch.empty(cap_b, dtype=torch.float32, device=dev),
+            "f_d": torch.empty((cap_n, 3), dtype=torch.float32, device=dev),
+            "compute_done": None,
+        })
 
     def _batch_staging(self, n_atoms: int, n_structs: int):
         """Grow-only pinned host + device staging buffers for the batched interface."""

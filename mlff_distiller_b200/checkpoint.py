@@ -211,13 +211,24 @@ def infer_config(state: Mapping[str, object], config: Optional[Mapping[str, obje
     return ModelConfig(**cfg)
 
 
+def is_torchscript_archive(path: Union[str, Path]) -> bool:
+    """True for a ``torch.jit.save`` archive (zip with a ``constants.pkl`` record), the format
+    ``use_jit=True, jit_path=...`` points at (inference/ase_calculator.py:216-236)."""
+    import zipfile
+    try:
+        with zipfile.ZipFile(path) as z:
+            return any(n.endswith("/constants.pkl") or n == "constants.pkl" for n in z.namelist())
+    except (zipfile.BadZipFile, OSError):
+        return False
+
+
 def load_any(path: Union[str, Path]) -> Tuple[Dict[str, np.ndarray], ModelConfig, Dict[str, object]]:
     """Read a checkpoint in any supported format.
 
     Returns ``(state_dict as numpy, ModelConfig, raw metadata)``.  Supported: ``.onnx`` exports,
     ``.npz`` archives of state_dict tensors (optionally with ``__config__`` json), and torch
     pickles in the inference or trainer layout (``model_state_dict`` key, optional ``model.``
-    prefix), or a bare state_dict.
+    prefix), a bare state_dict, or a TorchScript archive of the ``(Z, R) -> E`` wrapper.
     """
     path = Path(path)
     if not path.exists():
@@ -238,8 +249,20 @@ def load_any(path: Union[str, Path]) -> Tuple[Dict[str, np.ndarray], ModelConfig
         state = strip_prefix(state)
     else:
         import torch
-        ckpt = torch.load(path, map_location="cpu", weights_only=False)
-        if isinstance(ckpt, dict) and "model_state_dict" in ckpt:
+        if is_torchscript_archive(path):
+            ckpt = torch.jit.load(str(path), map_location="cpu")
+        else:
+            ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        if isinstance(ckpt, torch.jit.ScriptModule):
+            # TorchScript export of the (Z, R) -> E wrapper (scripts/export_to_torchscript.py:77-104):
+            # the parameters live under the wrapper's ``model.`` attribute
+            raw_state, config = ckpt.state_dict(), {}
+            meta = {"format": "torchscript"}
+            if not any(k.endswith("embedding.weight") for k in raw_state):
+                raise ValueError(
+                    f"{path}: TorchScript archive holds no parameters (frozen by "
+                    "optimize_for_inference?); export it without freezing or pass the checkpoint")
+        elif isinstance(ckpt, dict) and "model_state_dict" in ckpt:
             raw_state = ckpt["model_state_dict"]
             config = ckpt.get("config", {})
             meta = {k: v for k, v in ckpt.items() if k not in ("model_state_dict",)}

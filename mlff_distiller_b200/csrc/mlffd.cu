@@ -962,6 +962,15 @@ extern "C" int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out) {
     return MLFFD_OK;
 }
 
+extern "C" int mlffd_status_async(mlffd_ctx* ctx, int32_t* status_out, void* stream) {
+    if (!ctx || !status_out) return MLFFD_EINVAL;
+    static_assert(sizeof(DeviceStatus) == 6 * sizeof(int32_t), "mlffd_status_async copies six int32 words");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpyAsync(status_out, ctx->status_d, sizeof(DeviceStatus), cudaMemcpyDefault,
+                                  (cudaStream_t)stream));
+    return MLFFD_OK;
+}
+
 extern "C" int mlffd_filter_table(mlffd_ctx* ctx, int32_t layer, const float* dist_d,
                                   int64_t num_pairs, float* filter_d, float* dfilter_d,
                                   void* stream) {

@@ -127,6 +127,12 @@ class Engine:
         self._check(self.lib.mlffd_get_status(self._ctx, ctypes.byref(s)))
         return s
 
+    def status_async(self, out: torch.Tensor):
+        """Enqueue a copy of the step's six status words (num_edges, num_pairs, overflow,
+        max_degree, overflow_events, hint_violation) into ``out`` (int32[6], pinned host or device)
+        behind the step just enqueued on the current stream.  Never synchronises."""
+        self._check(self.lib.mlffd_status_async(self._ctx, out.data_ptr(), self._stream()))
+
     def profile_enable(self, enable: bool = True):
         """Reset launch counters; with ``enable`` also time every stage with CUDA events."""
         self._check(self.lib.mlffd_profile_enable(self._ctx, 1 if enable else 0))

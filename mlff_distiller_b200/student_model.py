@@ -360,6 +360,21 @@ class StudentForceField(nn.Module):
         return cls.from_state(state, cfg, str(dev), **kwargs)
 
 
+class EnergyOnlyWrapper(nn.Module):
+    """``(atomic_numbers, positions) -> energy``: the two-argument signature of the reference's
+    TorchScript export (``SimpleWrapper``, scripts/export_to_torchscript.py:77-84) that
+    ``StudentForceFieldCalculator(use_jit=True)`` calls before differentiating the energy with
+    respect to the positions (inference/ase_calculator.py:319-335).  ``state_dict`` keys carry the
+    same ``model.`` prefix as the export; the backward pass is the fused reverse kernels."""
+
+    def __init__(self, base_model: "StudentForceField"):
+        super().__init__()
+        self.model = base_model
+
+    def forward(self, atomic_numbers: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
+        return self.model(atomic_numbers, positions, None, None, None)
+
+
 def radius_graph(positions: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None,
                  loop: bool = False, use_torch_cluster: bool = True, *, engine=None,
                  cell=None, pbc=None) -> torch.Tensor:
@@ -393,4 +408,4 @@ def radius_graph(positions: torch.Tensor, r: float, batch: Optional[torch.Tensor
     raise RuntimeError("edge workspace overflow persisted after growing")
 
 
-__all__ = ["StudentForceField", "radius_graph"]
+__all__ = ["StudentForceField", "EnergyOnlyWrapper", "radius_graph"]

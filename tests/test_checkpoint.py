@@ -98,3 +98,47 @@ def test_onnx_reader_and_reference_round_trip(tmp_path):
     back = mod.StudentForceField.load(tmp_path / "ours.pt")
     for k, v in ours.state_dict().items():
         assert torch.equal(v, back.state_dict()[k]), k
+
+
+def _export_like_reference(model, path):
+    """A TorchScript archive laid out like scripts/export_to_torchscript.py:77-104 writes it: a
+    traced two-argument wrapper whose ``model`` attribute holds the student's modules."""
+    class SimpleWrapper(torch.nn.Module):
+        def __init__(self, base_model):
+            super().__init__()
+            self.model = base_model
+
+        def forward(self, atomic_numbers, positions):   # traceable stand-in graph (never executed by us)
+            return self.model.embedding(atomic_numbers).sum() + positions.sum() * self.model.rbf.centers.sum()
+
+    traced = torch.jit.trace(SimpleWrapper(model), (torch.tensor([1, 6, 8]), torch.zeros(3, 3)))
+    torch.jit.save(traced, str(path))
+
+
+def test_torchscript_archive_is_a_checkpoint_format(tmp_path, weights):
+    """`use_jit=True, jit_path=...` points at a TorchScript archive (inference/ase_calculator.py:216-236):
+    its parameters (``model.`` prefix) are read like any other checkpoint."""
+    state, cfg = weights
+    c = ck.infer_config(state, cfg)
+    model = StudentForceField.from_state(state, c, "cpu")
+    p = tmp_path / "student_jit.pt"
+    _export_like_reference(model, p)
+    assert ck.is_torchscript_archive(p)
+    model.save(tmp_path / "plain.pt")
+    assert not ck.is_torchscript_archive(tmp_path / "plain.pt")
+    st, c2, meta = ck.load_any(p)
+    assert meta["format"] == "torchscript" and c2 == c
+    for k, v in model.state_dict().items():
+        assert np.array_equal(st[k], v.numpy()), k
+    again = StudentForceField.load(p)
+    assert again.num_parameters() == model.num_parameters()
+
+
+def test_energy_only_wrapper_signature_and_keys(weights):
+    from mlff_distiller_b200.student_model import EnergyOnlyWrapper
+    state, cfg = weights
+    model = StudentForceField.from_state(state, ck.infer_config(state, cfg), "cpu")
+    w = EnergyOnlyWrapper(model)
+    assert set(w.state_dict()) == {"model." + k for k in model.state_dict()}
+    with pytest.raises(RuntimeError, match="no CPU fallback"):   # evaluation is CUDA-only
+        w(torch.tensor([8, 1, 1]), torch.zeros(3, 3))

@@ -197,3 +197,67 @@ def test_batched_interface_micro_batches_large_requests(calc):
         calc.max_atoms_per_call = old
     assert e.shape == e_ref.shape and f.shape == f_ref.shape
     assert np.abs(e - e_ref).max() < 2e-4 and np.abs(f - f_ref).max() < 2e-5
+
+
+def _ragged_batches(num, per, first):
+    out = []
+    for b in range(num):
+        structs = synthetic.druglike_batch(per, first=first + b * per, ragged=True)
+        z, pos, off = synthetic.concatenate(structs)
+        out.append((z, pos, np.diff(off)))
+    return out
+
+
+def test_evaluate_stream_matches_blocking_interface(calc):
+    """The pipelined sweep interface (two batches in flight, copies under the kernels) returns
+    exactly what the blocking call returns, batch by batch and in order."""
+    batches = _ragged_batches(5, 24, first=3000) + _ragged_batches(2, 3, first=3500)
+    ref = [calc.evaluate_arrays(*b) for b in batches]
+    n0 = calc.n_calls
+    got = list(calc.evaluate_stream(iter(batches)))
+    assert calc.n_calls == n0 + len(batches)
+    assert len(got) == len(ref)
+    for (e, f), (e_ref, f_ref), b in zip(got, ref, batches):
+        assert e.dtype == np.float32 and f.dtype == np.float32
+        assert e.shape == (len(b[2]),) and f.shape == (len(b[0]), 3)
+        assert np.array_equal(e, e_ref) and np.array_equal(f, f_ref)   # deterministic kernels
+    assert list(calc.evaluate_stream(iter([]))) == []
+    with pytest.raises(ValueError):
+        list(calc.evaluate_stream(iter([(np.array([1, 200]), np.zeros((2, 3)), np.array([2]))])))
+
+
+def test_evaluate_stream_recovers_from_edge_overflow():
+    """A batch whose edges overflow the workspace guess is detected from the status words that
+    travel with its results and re-run; the batches around it are unaffected."""
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+    fresh = StudentForceFieldCalculator(GOLDEN / "weights_original.npz", device="cuda")
+    fresh.model._edges_per_atom = 1   # first workspace guess far too small -> overflow in flight
+    batches = _ragged_batches(4, 16, first=4000)
+    got = list(fresh.evaluate_stream(iter(batches)))
+    good = StudentForceFieldCalculator(GOLDEN / "weights_original.npz", device="cuda")
+    for (e, f), b in zip(got, batches):
+        e_ref, f_ref = good.evaluate_arrays(*b)
+        assert np.array_equal(e, e_ref) and np.array_equal(f, f_ref)
+
+
+def test_use_jit_reads_the_torchscript_archive_and_wrapper_differentiates(calc, tmp_path):
+    """`use_jit=True`: the weights come from the TorchScript archive; the (Z, R) -> E wrapper
+    gives forces through autograd exactly as inference/ase_calculator.py:319-335 computes them."""
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+    from mlff_distiller_b200.student_model import EnergyOnlyWrapper, StudentForceField
+    from test_checkpoint import _export_like_reference
+    cpu_model = StudentForceField.load(GOLDEN / "weights_original.npz")
+    _export_like_reference(cpu_model, tmp_path / "student_jit.pt")
+    jit_calc = StudentForceFieldCalculator(tmp_path / "unused.pt", device="cuda", use_jit=True,
+                                           jit_path=tmp_path / "student_jit.pt")
+    a, b = synthetic.benzene(), synthetic.benzene()
+    a.calc, b.calc = jit_calc, calc
+    assert a.get_potential_energy() == b.get_potential_energy()
+    assert np.array_equal(a.get_forces(), b.get_forces())
+    wrapper = EnergyOnlyWrapper(calc.model)
+    z = torch.from_numpy(a.get_atomic_numbers()).to("cuda")
+    pos = torch.from_numpy(a.get_positions().astype(np.float32)).to("cuda").requires_grad_(True)
+    energy = wrapper(z, pos)
+    forces = -torch.autograd.grad(energy, pos)[0]
+    assert abs(float(energy) - b.get_potential_energy()) < 1e-5
+    assert np.abs(forces.cpu().numpy() - b.get_forces()).max() < 1e-6

@@ -118,3 +118,11 @@ def test_calculator_validation_messages_without_gpu():
         calc._validate_inputs(np.zeros((1, 3)), np.array([29]), np.eye(3) * 3.58, np.array([True] * 3))
     with pytest.raises(FileNotFoundError):
         StudentForceFieldCalculator("/nonexistent/best_model.pt", device="cuda")
+
+
+def test_use_jit_flag_errors_like_the_reference(tmp_path):
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+    with pytest.raises(ValueError, match="jit_path not provided"):
+        StudentForceFieldCalculator(tmp_path / "x.pt", device="cuda", use_jit=True)
+    with pytest.raises(FileNotFoundError, match="TorchScript model not found"):
+        StudentForceFieldCalculator(tmp_path / "x.pt", device="cuda", use_jit=True, jit_path=tmp_path / "missing_jit.pt")
