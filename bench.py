@@ -45,8 +45,9 @@ def parse_args():
     ap.add_argument("--variant", choices=sorted(VARIANT_FILES), default="original")
     ap.add_argument("--batch", type=int, default=1024, help="structures per GPU per step")
     ap.add_argument("--atoms", type=int, default=50)
-    ap.add_argument("--precision", choices=["fp32", "tc"], default="tc",
-                    help="fp32 = FFMA dense layers; tc = tcgen05 tensor cores with 2-term FP16 split (FP32-equivalent)")
+    ap.add_argument("--precision", choices=["fp32", "tc", "tc_fp16", "tc_bf16"], default="tc",
+                    help="fp32 = FFMA dense layers; tc = tcgen05 tensor cores with 2-term FP16 split (FP32-equivalent, "
+                         "the headline); tc_fp16 / tc_bf16 = single-pass products with looser stated bounds (NOT the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -385,7 +386,9 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "fp32" else "f32 (dense layers: 2-term f16 split products on tcgen05, f32 accumulate)",
+        "dtype": {"fp32": "f32", "tc": "f32 (dense layers: 2-term f16 split products on tcgen05, f32 accumulate)",
+                  "tc_fp16": "f16 operands / f32 accumulate in the dense layers (looser bounds, not the headline)",
+                  "tc_bf16": "bf16 operands / f32 accumulate in the dense layers (looser bounds, not the headline)"}[args.precision],
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "StudentForceFieldCalculator.evaluate_stream (host arrays in, host arrays out, two steps in flight)",

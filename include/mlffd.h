@@ -41,8 +41,12 @@ enum {
                                  products, FP32 accumulation in TMEM: FP32-equivalent (meets the
                                  FP32 bounds).  Filter table for H = 128 / 64 / 32, update block
                                  for H = 128 (FFMA otherwise). */
-    MLFFD_PREC_TF32 = 2,      /* reserved: single-pass TF32, looser bounds */
-    MLFFD_PREC_BF16 = 3       /* reserved: single-pass BF16, looser bounds */
+    MLFFD_PREC_TF32 = 2,      /* reserved (not implemented): MLFFD_PREC_TC_FP16 has the same 11-bit
+                                 significands at twice the tensor-core rate */
+    MLFFD_PREC_TC_BF16 = 3,   /* single product of BF16-rounded operands (8-bit significands), FP32
+                                 accumulation; looser bounds: DESIGN.md section 6 */
+    MLFFD_PREC_TC_FP16 = 4    /* single product of FP16-rounded operands (11-bit significands, the
+                                 precision class of TF32), FP32 accumulation; looser bounds */
 };
 
 /* Hyper-parameters = the `config` dict of StudentForceField.save

@@ -34,7 +34,7 @@ EXPORTS = [
 NUM_STAGES = 10
 
 MLFFD_OK, MLFFD_EINVAL, MLFFD_ECUDA, MLFFD_ECAPACITY, MLFFD_ENOMEM = 0, -1, -2, -3, -4
-PRECISIONS = {"fp32": 0, "tc": 1}
+PRECISIONS = {"fp32": 0, "tc": 1, "tc_bf16": 3, "tc_fp16": 4}
 
 
 class MlffdConfig(ctypes.Structure):

@@ -39,6 +39,7 @@
 // at c ^ (r % 8)), descriptor SBO = 1024 B, version 1; instruction descriptor M=128, N=128, F16
 // inputs, F32 accumulate.  Encodings pinned by tools/umma_test.cu on a B200.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "filter.cuh"
@@ -153,35 +154,59 @@ constexpr float kActScale = 8.0f;
 constexpr float kWeightScale = 256.0f;
 constexpr float kAccUnscale = 1.0f / (kActScale * kWeightScale);
 
-// fp16 two-term split of 8 consecutive channels, packed for one 16-byte swizzle chunk
-__device__ __forceinline__ void split8(const float (&xin)[8], uint4& hi, uint4& lo) {
+// Tensor-core arithmetic modes (mlffd_config.precision -> kernel argument `tc_mode`):
+//   kTcSplit  two-term FP16 split of both operands, three products: FP32-equivalent (default)
+//   kTcF16    one product of FP16-rounded operands (11-bit significands, the precision class of
+//             TF32): a third of the MMAs, half the weight bytes, no low-term work
+//   kTcBF16   one product of BF16-rounded operands (8-bit significands)
+// The single-pass modes only ever touch the `hi` halves of the operand tiles / weight images.
+constexpr int kTcSplit = 0, kTcF16 = 1, kTcBF16 = 2;
+
+// instruction descriptor: M = 128, N = 128, FP32 accumulate, A/B formats F16 (0) or BF16 (1)
+__device__ __forceinline__ uint32_t umma_idesc_128x128(int tc_mode) {
+    const uint32_t fmt = (tc_mode == kTcBF16) ? 1u : 0u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// 16-bit storage of one pre-scaled value: high term (FP16 or BF16 by mode) and FP16 low term
+// (meaningful in kTcSplit only)
+__device__ __forceinline__ void split_scaled(float x, int tc_mode, uint32_t& hi, uint32_t& lo) {
+    if (tc_mode == kTcBF16) {
+        hi = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x));
+        lo = 0u;
+    } else {
+        const __half h = __float2half_rn(x);
+        hi = (uint32_t)__half_as_ushort(h);
+        lo = (uint32_t)__half_as_ushort(__float2half_rn(x - __half2float(h)));
+    }
+}
+
+// split of 8 consecutive channels, packed for one 16-byte swizzle chunk
+__device__ __forceinline__ void split8(const float (&xin)[8], int tc_mode, uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
-    float x[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = xin[i] * kActScale;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __half h0 = __float2half_rn(x[2 * i]), h1 = __float2half_rn(x[2 * i + 1]);
-        const __half l0 = __float2half_rn(x[2 * i] - __half2float(h0));
-        const __half l1 = __float2half_rn(x[2 * i + 1] - __half2float(h1));
-        h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        uint32_t h0, l0, h1, l1;
+        split_scaled(xin[2 * i] * kActScale, tc_mode, h0, l0);
+        split_scaled(xin[2 * i + 1] * kActScale, tc_mode, h1, l1);
+        h[i] = h0 | (h1 << 16);
+        l[i] = l0 | (l1 << 16);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // same split for 4 consecutive channels (half a swizzle chunk, 8 bytes per term)
-__device__ __forceinline__ void split4(const float4& xin, uint2& hi, uint2& lo) {
+__device__ __forceinline__ void split4(const float4& xin, int tc_mode, uint2& hi, uint2& lo) {
     const float x[4] = {xin.x * kActScale, xin.y * kActScale, xin.z * kActScale, xin.w * kActScale};
     uint32_t h[2], l[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const __half h0 = __float2half_rn(x[2 * i]), h1 = __float2half_rn(x[2 * i + 1]);
-        const __half l0 = __float2half_rn(x[2 * i] - __half2float(h0));
-        const __half l1 = __float2half_rn(x[2 * i + 1] - __half2float(h1));
-        h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        uint32_t h0, l0, h1, l1;
+        split_scaled(x[2 * i], tc_mode, h0, l0);
+        split_scaled(x[2 * i + 1], tc_mode, h1, l1);
+        h[i] = h0 | (h1 << 16);
+        l[i] = l0 | (l1 << 16);
     }
     hi = make_uint2(h[0], h[1]);
     lo = make_uint2(l[0], l[1]);
@@ -204,14 +229,15 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int chunk) {
 #define FT_PRINT
 #endif
 
-// fp16 two-term split of one value, pre-scaled like split8
-__device__ __forceinline__ void split1(float x, __half& hi, __half& lo) {
-    x *= kActScale;
-    hi = __float2half_rn(x);
-    lo = __float2half_rn(x - __half2float(hi));
+// split of one value, pre-scaled like split8 (16-bit patterns)
+__device__ __forceinline__ void split1(float x, int tc_mode, uint16_t& hi, uint16_t& lo) {
+    uint32_t h, l;
+    split_scaled(x * kActScale, tc_mode, h, l);
+    hi = (uint16_t)h;
+    lo = (uint16_t)l;
 }
 
-template <int H>
+template <int H, int MODE = kTcSplit>
 __global__ void __launch_bounds__(kFilterUmmaThreads, 1)
 filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restrict__ num_pairs_ptr,
                          int num_pairs_arg, const DeviceStatus* __restrict__ status,
@@ -219,6 +245,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                          float rc, FilterWeights w, const uint8_t* __restrict__ w1_image,
                          const uint8_t* __restrict__ w2_images, int skip_vector_gate,
                          float* __restrict__ filt, float* __restrict__ dfilt) {
+    constexpr int tc_mode = MODE;
     using G = UmmaGeom<H>;
     if (status != nullptr && status->overflow) return;
     const int P = (num_pairs_ptr != nullptr) ? *num_pairs_ptr : num_pairs_arg;
@@ -246,6 +273,9 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
     const bool skip_chunk1 = skip_vector_gate && H == 128;
     const int nchunks = skip_chunk1 ? 2 : G::NCH;
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    constexpr bool single = tc_mode != kTcSplit;                   // one product, `hi` halves only
+    constexpr uint32_t w2_bytes = single ? G::TILE : G::IMAGE;     // bytes of a weight chunk in use
+    constexpr int first_pass = single ? 2 : 0;                     // passes: hi*lo, lo*hi, hi*hi
 
     // ---- one-time setup ----
     if (warp == kUmmaComputeWarps) {
@@ -253,16 +283,16 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
             for (int i = 0; i < 9; ++i) mbar_init(bars + i, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             // start streaming the first-layer image and the first two weight chunks (latency path)
-            mbar_expect_tx(bar_w1_full, 2 * kKBlockBytes);
+            mbar_expect_tx(bar_w1_full, single ? kKBlockBytes : 2 * kKBlockBytes);
             bulk_g2s(smem_u32(smem + G::W1_HI), w1_image, kKBlockBytes, bar_w1_full);
-            bulk_g2s(smem_u32(smem + G::W1_LO), w1_image + kKBlockBytes, kKBlockBytes, bar_w1_full);
+            if (!single) bulk_g2s(smem_u32(smem + G::W1_LO), w1_image + kKBlockBytes, kKBlockBytes, bar_w1_full);
             const int total0 = my_tiles * nchunks;
             for (int g = 0; g < 2 && g < total0; ++g) {
-                mbar_expect_tx(&bar_b_full[g], G::IMAGE);
+                mbar_expect_tx(&bar_b_full[g], w2_bytes);
                 const int cid = skip_chunk1 ? (g % nchunks) * 2 : (g % nchunks);
                 const uint8_t* src = w2_images + (size_t)cid * G::IMAGE;
                 const uint32_t dst = smem_u32(smem + (g ? G::B1 : G::B0));
-                for (uint32_t off = 0; off < G::IMAGE; off += kKBlockBytes)
+                for (uint32_t off = 0; off < w2_bytes; off += kKBlockBytes)
                     bulk_g2s(dst + off, src + off, kKBlockBytes, &bar_b_full[g]);
             }
         }
@@ -281,7 +311,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
     if (warp == kUmmaComputeWarps) {
         // =============================== issuer ===============================
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc = umma_idesc_128x128(tc_mode);
             const uint32_t b_buf[2] = {smem_u32(smem + G::B0), smem_u32(smem + G::B1)};
             // every operand descriptor is a constant plus a small offset in the 16-byte address field
             const uint64_t act_desc_hi = umma_desc_sw128(smem_u32(smem + G::A_HI));
@@ -311,7 +341,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                     IT_MARK(0)
                     uint32_t acc1 = 0;
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {   // W_hi*phi_lo, W_lo*phi_hi, W_hi*phi_hi
+                    for (int pass = first_pass; pass < 3; ++pass) {   // W_hi*phi_lo, W_lo*phi_hi, W_hi*phi_hi
                         const uint64_t phi_base = (pass == 0) ? act_desc_lo : act_desc_hi;
                         const uint64_t w_base = (pass == 1) ? w1_desc_lo : w1_desc_hi;
 #pragma unroll
@@ -333,7 +363,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                 const uint64_t w_desc = w_desc0 + (uint64_t)(buf ? (G::IMAGE >> 4) : 0);
                 uint32_t acc = 0;
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {   // W_hi*act_lo, W_lo*act_hi, W_hi*act_hi
+                for (int pass = first_pass; pass < 3; ++pass) {   // W_hi*act_lo, W_lo*act_hi, W_hi*act_hi
                     const uint64_t act_base = (pass == 0) ? act_desc_lo : act_desc_hi;
                     const uint64_t w_base = w_desc + (uint64_t)((pass == 1) ? (G::TILE >> 4) : 0);
 #pragma unroll
@@ -367,9 +397,9 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                 const int gp = g - 2, itp = gp / nchunks, cp = gp - itp * nchunks;
                 mbar_wait(&bar_d_full[skip_chunk1 ? cp * 2 : cp], itp & 1);
                 const int ci = g % nchunks, buf = g & 1;
-                mbar_expect_tx(&bar_b_full[buf], G::IMAGE);
+                mbar_expect_tx(&bar_b_full[buf], w2_bytes);
                 const uint8_t* src = w2_images + (size_t)(skip_chunk1 ? ci * 2 : ci) * G::IMAGE;
-                for (uint32_t off = 0; off < G::IMAGE; off += kKBlockBytes)
+                for (uint32_t off = 0; off < w2_bytes; off += kKBlockBytes)
                     bulk_g2s(b_buf[buf] + off, src + off, kKBlockBytes, &bar_b_full[buf]);
             }
         }
@@ -410,8 +440,8 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                     v8[i] = (k < K) ? phi * cut : 0.f;
                     t8[i] = (k < K) ? dphi * cut + phi * dcut : 0.f;
                 }
-                split8(v8, phi_hi, phi_lo);
-                split8(t8, dphi_hi, dphi_lo);
+                split8(v8, tc_mode, phi_hi, phi_lo);
+                split8(t8, tc_mode, dphi_hi, dphi_lo);
             }
         };
         auto rbf_store = [&]() {           // needs the activation tile free (second-layer MMAs done)
@@ -420,9 +450,11 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                 const int p = tid >> 2, chunk = tid & 3;
                 const uint32_t ov = sw128_offset(p, chunk), ot = sw128_offset(kUmmaPairs + p, chunk);
                 *reinterpret_cast<uint4*>(smem + G::A_HI + ov) = phi_hi;
-                *reinterpret_cast<uint4*>(smem + G::A_LO + ov) = phi_lo;
                 *reinterpret_cast<uint4*>(smem + G::A_HI + ot) = dphi_hi;
-                *reinterpret_cast<uint4*>(smem + G::A_LO + ot) = dphi_lo;
+                if (!single) {
+                    *reinterpret_cast<uint4*>(smem + G::A_LO + ov) = phi_lo;
+                    *reinterpret_cast<uint4*>(smem + G::A_LO + ot) = dphi_lo;
+                }
             }
             FT_MARK(2)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -457,14 +489,16 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                     const float sg = sigmoidf_(yy);
                     const float hv = yy * sg;
                     const float tv = sg * (1.0f + yy * (1.0f - sg)) * zz;
-                    __half hh, hl, th, tl;
-                    split1(hv, hh, hl);
-                    split1(tv, th, tl);
+                    uint16_t hh, hl, th, tl;
+                    split1(hv, tc_mode, hh, hl);
+                    split1(tv, tc_mode, th, tl);
                     const uint32_t oh = sw128_offset(p, chunk), ot = sw128_offset(kUmmaPairs + p, chunk);
-                    *reinterpret_cast<__half*>(a_hi + oh) = hh;
-                    *reinterpret_cast<__half*>(a_lo + oh) = hl;
-                    *reinterpret_cast<__half*>(a_hi + ot) = th;
-                    *reinterpret_cast<__half*>(a_lo + ot) = tl;
+                    *reinterpret_cast<uint16_t*>(a_hi + oh) = hh;
+                    *reinterpret_cast<uint16_t*>(a_hi + ot) = th;
+                    if (!single) {
+                        *reinterpret_cast<uint16_t*>(a_lo + oh) = hl;
+                        *reinterpret_cast<uint16_t*>(a_lo + ot) = tl;
+                    }
                 }
             }
             FT_MARK(4)

@@ -83,15 +83,20 @@ struct mlffd_ctx {
     bool enable_staging = false;     // env MLFFD_STAGING=1
     int readout_mode = 0;            // env MLFFD_READOUT: 0 = by size, 1 = tile, 2 = warp
     bool readout_configured = false; // smem attribute of readout_tile_kernel set on this device
-    uint32_t pipe_configured = 0;    // bit per pipelined-kernel instantiation whose smem attribute is set on this device
+    uint32_t pipe_configured_fwd[3] = {0, 0, 0};   // bit per pipelined-kernel instantiation whose smem
+    uint32_t pipe_configured_bwd[2] = {0, 0};      // attribute is set on this device, by block size
     int last_adj_slabs = 0;          // edge-adjoint slabs written by the last force evaluation (0 = none)
     int msg_bwd_mode = 2;            // env MLFFD_MSG_BWD = edges (0) | pairs (1) | pipe (2)
     int msg_fwd_mode = 1;            // env MLFFD_MSG_FWD = rows (0) | pipe (1)
+    int affine_fwd = 0;              // env MLFFD_AFFINE_FWD: warps per block of the structure-affine forward (0 = grid-stride: default, faster on C2)
+    int affine_bwd = 0;              // env MLFFD_AFFINE_BWD: same for the reverse kernel (0 | 8 | 16)
+    int affine_parts = 1;            // env MLFFD_AFFINE_PARTS: work units per structure
     int pipe_depth_fwd = 2;          // env MLFFD_PIPE_DEPTH_FWD: ring slots per warp
     int pipe_depth_bwd = 2;          // env MLFFD_PIPE_DEPTH_BWD
     std::string err;
     float* weights_d = nullptr;
     uint8_t* w2_images_d = nullptr;   // swizzled fp16 hi/lo 64 KB weight images (tensor-core path)
+    int tc_mode = 0;                // kTcSplit | kTcF16 | kTcBF16 (filter_umma.cuh), from cfg.precision
     bool use_umma = false;          // tensor-core update block (H = 128)
     bool use_umma_filter = false;   // tensor-core filter table (H = 128, 64, 32)
     struct ImageOffsets { size_t filter1, filter, upd_f1, upd_f2, upd_b1, upd_b2; } img[kMaxLayers] = {};
@@ -222,6 +227,14 @@ int set_kernel_attributes(mlffd_ctx* ctx) {
     return MLFFD_OK;
 }
 
+// Run a statement with the tensor-core arithmetic mode of the context as the constant MODE.
+#define TC_DISPATCH(mode, ...)                                                             \
+    do {                                                                                   \
+        if ((mode) == kTcF16) { constexpr int MODE = kTcF16; __VA_ARGS__; }                \
+        else if ((mode) == kTcBF16) { constexpr int MODE = kTcBF16; __VA_ARGS__; }         \
+        else { constexpr int MODE = kTcSplit; __VA_ARGS__; }                               \
+    } while (0)
+
 // ---- per-H launch sequences -----------------------------------------------------------------
 template <int H>
 int launch_filter(mlffd_ctx* ctx, int l, const float* dist, const int* num_pairs_ptr,
@@ -229,11 +242,11 @@ int launch_filter(mlffd_ctx* ctx, int l, const float* dist, const int* num_pairs
                   int64_t pair_bound, cudaStream_t st) {
     if (ctx->use_umma_filter) {
         const int grid = clamp_grid(ceil_div(std::max<int64_t>(pair_bound, 1), kUmmaPairs), kNumSMs);
-        filter_table_umma_kernel<H><<<grid, kFilterUmmaThreads, UmmaGeom<H>::total(), st>>>(
+        TC_DISPATCH(ctx->tc_mode, filter_table_umma_kernel<H, MODE><<<grid, kFilterUmmaThreads, UmmaGeom<H>::total(), st>>>(
             dist, num_pairs_ptr, num_pairs_arg, status, ctx->centers, ctx->gammas, ctx->K,
             ctx->cfg.cutoff, ctx->layer[l].filter, ctx->w2_images_d + ctx->img[l].filter1,
             ctx->w2_images_d + ctx->img[l].filter,
-            (l == 0 && status != nullptr) ? 1 : 0, filt, dfilt);
+            (l == 0 && status != nullptr) ? 1 : 0, filt, dfilt));
         LAUNCHED(ctx, "filter_table_umma_kernel", MLFFD_STAGE_FILTER, st);
         return MLFFD_OK;
     }
@@ -247,55 +260,84 @@ int launch_filter(mlffd_ctx* ctx, int l, const float* dist, const int* num_pairs
     return MLFFD_OK;
 }
 
-template <bool LAYER0, int D>
-void launch_forward_pipe_d(mlffd_ctx* ctx, int l, int grid, int N, cudaStream_t st) {
-    Workspace& ws = ctx->ws;
-    auto kernel = message_forward_pipe_kernel<LAYER0, D>;
-    constexpr size_t smem = message_forward_pipe_smem<D>();
-    // per context (device), not per process: a second context on another GPU needs the attribute too
-    constexpr uint32_t bit = 1u << (2 * D + (LAYER0 ? 1 : 0) + 0);
-    if (!(ctx->pipe_configured & bit)) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ctx->pipe_configured |= bit;
-    }
-    kernel<<<grid, 32 * kPipeWarps, smem, st>>>(ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l],
-                                              LAYER0 ? nullptr : ws.v_in[l], ws.s_msg[l], ws.v_msg[l], N,
-                                              ctx->status_d);
+// Structure-affine row order (message_pipe.cuh:RowCursor) pays when the batch holds many small
+// structures: enough work units to fill the chip, units short enough that a block's warps stay on
+// the same structure.  One block per SM slot; each block walks units blockIdx.x, + gridDim.x, ...
+inline bool use_affine(const mlffd_ctx* ctx, int warps, int n_structs, int N) {
+    return warps > 0 && n_structs * ctx->affine_parts >= 2 * kNumSMs && N / std::max(n_structs, 1) <= 512;
 }
-void launch_forward_pipe(mlffd_ctx* ctx, int l, int grid, int N, cudaStream_t st) {
-#define FWD_PIPE(D) (l == 0 ? launch_forward_pipe_d<true, D>(ctx, l, grid, N, st) : launch_forward_pipe_d<false, D>(ctx, l, grid, N, st))
+
+template <bool LAYER0, int D, int W>
+void launch_forward_pipe_w(mlffd_ctx* ctx, int l, int grid, int N, const int* offsets, int n_structs,
+                           cudaStream_t st) {
+    Workspace& ws = ctx->ws;
+    auto kernel = message_forward_pipe_kernel<LAYER0, D, W>;
+    constexpr size_t smem = message_forward_pipe_smem<D, W>();
+    // per context (device), not per process: a second context on another GPU needs the attribute too
+    constexpr int wbit = (W == 8) ? 0 : (W == 12) ? 1 : 2;
+    uint32_t& configured = ctx->pipe_configured_fwd[wbit];
+    constexpr uint32_t bit = 1u << (2 * D + (LAYER0 ? 1 : 0));
+    if (!(configured & bit)) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured |= bit;
+    }
+    kernel<<<grid, 32 * W, smem, st>>>(ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l],
+                                     LAYER0 ? nullptr : ws.v_in[l], ws.s_msg[l], ws.v_msg[l], N,
+                                     ctx->status_d, offsets, n_structs, ctx->affine_parts);
+}
+void launch_forward_pipe(mlffd_ctx* ctx, int l, int grid, int N, const int* offsets, int n_structs,
+                         cudaStream_t st) {
+#define FWD_PIPE(D, W, G, OFF) (l == 0 ? launch_forward_pipe_w<true, D, W>(ctx, l, G, N, OFF, n_structs, st) \
+                                       : launch_forward_pipe_w<false, D, W>(ctx, l, G, N, OFF, n_structs, st))
+    if (use_affine(ctx, ctx->affine_fwd, n_structs, N)) {
+        // resident blocks per SM by registers (80 / thread): 3 x 8 warps, 2 x 12, 1 x 24
+        const int units = n_structs * ctx->affine_parts;
+        switch (ctx->affine_fwd) {
+            case 8:  FWD_PIPE(2, 8, std::min(units, kNumSMs * 3), offsets); break;
+            case 12: FWD_PIPE(2, 12, std::min(units, kNumSMs * 2), offsets); break;
+            default: FWD_PIPE(2, 24, std::min(units, kNumSMs), offsets); break;
+        }
+        return;
+    }
     switch (ctx->pipe_depth_fwd) {
-        case 3: FWD_PIPE(3); break;
-        case 4: FWD_PIPE(4); break;
-        case 8: FWD_PIPE(8); break;
-        default: FWD_PIPE(2); break;
+        case 3: FWD_PIPE(3, 8, grid, nullptr); break;
+        case 4: FWD_PIPE(4, 8, grid, nullptr); break;
+        case 8: FWD_PIPE(8, 8, grid, nullptr); break;
+        default: FWD_PIPE(2, 8, grid, nullptr); break;
     }
 #undef FWD_PIPE
 }
 
-template <bool LAYER0, int D>
-void launch_backward_pipe_d(mlffd_ctx* ctx, int l, int grid, const float* sb, const float* vb, float* sb_in,
-                            float* vb_in, int N, cudaStream_t st) {
+template <bool LAYER0, int D, int W>
+void launch_backward_pipe_w(mlffd_ctx* ctx, int l, int grid, const float* sb, const float* vb, float* sb_in,
+                            float* vb_in, int N, const int* offsets, int n_structs, cudaStream_t st) {
     Workspace& ws = ctx->ws;
-    auto kernel = message_backward_pipe_kernel<LAYER0, D>;
-    constexpr size_t smem = message_backward_pipe_smem<D>();
-    // per context (device), not per process: a second context on another GPU needs the attribute too
-    constexpr uint32_t bit = 1u << (2 * D + (LAYER0 ? 1 : 0) + 14);
-    if (!(ctx->pipe_configured & bit)) {
+    auto kernel = message_backward_pipe_kernel<LAYER0, D, W>;
+    constexpr size_t smem = message_backward_pipe_smem<D, W>();
+    uint32_t& configured = ctx->pipe_configured_bwd[W == 8 ? 0 : 1];
+    constexpr uint32_t bit = 1u << (2 * D + (LAYER0 ? 1 : 0));
+    if (!(configured & bit)) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ctx->pipe_configured |= bit;
+        configured |= bit;
     }
-    kernel<<<grid, 32 * kPipeWarps, smem, st>>>(ws.rowptr, ws.col, ws.pair, ws.rev, ws.geo, ws.filt[l], ws.dfilt[l],
-                                              ws.s_in[l], LAYER0 ? nullptr : ws.v_in[l], sb, vb, sb_in, vb_in,
-                                              ws.edge_adj + (size_t)l * ws.cap_edges, N, ctx->status_d);
+    kernel<<<grid, 32 * W, smem, st>>>(ws.rowptr, ws.col, ws.pair, ws.rev, ws.geo, ws.filt[l], ws.dfilt[l],
+                                     ws.s_in[l], LAYER0 ? nullptr : ws.v_in[l], sb, vb, sb_in, vb_in,
+                                     ws.edge_adj + (size_t)l * ws.cap_edges, N, ctx->status_d,
+                                     offsets, n_structs, ctx->affine_parts);
 }
 void launch_backward_pipe(mlffd_ctx* ctx, int l, int grid, const float* sb, const float* vb, float* sb_in,
-                          float* vb_in, int N, cudaStream_t st) {
-#define BWD_PIPE(D) (l == 0 ? launch_backward_pipe_d<true, D>(ctx, l, grid, sb, vb, sb_in, vb_in, N, st) \
-                            : launch_backward_pipe_d<false, D>(ctx, l, grid, sb, vb, sb_in, vb_in, N, st))
+                          float* vb_in, int N, const int* offsets, int n_structs, cudaStream_t st) {
+#define BWD_PIPE(D, W, G, OFF) (l == 0 ? launch_backward_pipe_w<true, D, W>(ctx, l, G, sb, vb, sb_in, vb_in, N, OFF, n_structs, st) \
+                                       : launch_backward_pipe_w<false, D, W>(ctx, l, G, sb, vb, sb_in, vb_in, N, OFF, n_structs, st))
+    if (use_affine(ctx, ctx->affine_bwd, n_structs, N)) {
+        const int units = n_structs * ctx->affine_parts;
+        if (ctx->affine_bwd == 8) BWD_PIPE(2, 8, std::min(units, kNumSMs * 2), offsets);
+        else BWD_PIPE(2, 16, std::min(units, kNumSMs), offsets);
+        return;
+    }
     switch (ctx->pipe_depth_bwd) {
-        case 4: BWD_PIPE(4); break;
-        default: BWD_PIPE(2); break;
+        case 4: BWD_PIPE(4, 8, grid, nullptr); break;
+        default: BWD_PIPE(2, 8, grid, nullptr); break;
     }
 #undef BWD_PIPE
 }
@@ -344,7 +386,7 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
                 offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], ws.v_in[l],
                 ws.s_msg[l], ws.v_msg[l], ctx->status_d);
         else if (fwd_pipe) {
-            if constexpr (H == 128) launch_forward_pipe(ctx, l, msg_grid, N, st);
+            if constexpr (H == 128) launch_forward_pipe(ctx, l, msg_grid, N, offsets, n_structs, st);
         } else if (l == 0)
             message_forward_kernel<H, true><<<msg_grid, 256, 0, st>>>(
                 ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], nullptr, ws.s_msg[l],
@@ -359,18 +401,18 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
             if (ctx->use_umma) {
                 const UpdateWeights& uw = ctx->layer[l].update;
                 const int rows_grid = clamp_grid(ceil_div(N, 128), kNumSMs);
-                umma_rows_kernel<UpdateFwd1Op><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                TC_DISPATCH(ctx->tc_mode, umma_rows_kernel<UpdateFwd1Op, MODE><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
                     UpdateFwd1Op{ws.s_msg[l], ws.v_msg[l], uw.m1, ws.y1[l]}, N,
-                    ctx->w2_images_d + ctx->img[l].upd_f1, status);
+                    ctx->w2_images_d + ctx->img[l].upd_f1, status));
                 LAUNCHED(ctx, "umma_rows_kernel<UpdateFwd1Op>", MLFFD_STAGE_UPDATE_FWD, st);
                 if (l == L - 1)
-                    umma_rows_kernel<UpdateFwd2Op<true>><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                    TC_DISPATCH(ctx->tc_mode, umma_rows_kernel<UpdateFwd2Op<true>, MODE><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
                         UpdateFwd2Op<true>{ws.y1[l], ws.s_msg[l], ws.v_msg[l], uw.m2, uw.U, ws.s_in[l + 1], nullptr, nullptr},
-                        N, ctx->w2_images_d + ctx->img[l].upd_f2, status);
+                        N, ctx->w2_images_d + ctx->img[l].upd_f2, status));
                 else
-                    umma_rows_kernel<UpdateFwd2Op<false>><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                    TC_DISPATCH(ctx->tc_mode, umma_rows_kernel<UpdateFwd2Op<false>, MODE><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
                         UpdateFwd2Op<false>{ws.y1[l], ws.s_msg[l], ws.v_msg[l], uw.m2, uw.U, ws.s_in[l + 1], ws.v_in[l + 1], ws.gates[l]},
-                        N, ctx->w2_images_d + ctx->img[l].upd_f2, status);
+                        N, ctx->w2_images_d + ctx->img[l].upd_f2, status));
                 upd_done = true;
             }
         }
@@ -414,17 +456,17 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
                 const UpdateWeights& uw = ctx->layer[l].update;
                 const int rows_grid = clamp_grid(ceil_div(N, 128), kNumSMs);
                 if (l == L - 1) {
-                    umma_rows_kernel<UpdateBwd1Op<true>><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
-                        UpdateBwd1Op<true>{sb, vb, ws.v_msg[l], uw.U, ws.y1[l]}, N, ctx->w2_images_d + ctx->img[l].upd_b1, status);
+                    TC_DISPATCH(ctx->tc_mode, umma_rows_kernel<UpdateBwd1Op<true>, MODE><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                        UpdateBwd1Op<true>{sb, vb, ws.v_msg[l], uw.U, ws.y1[l]}, N, ctx->w2_images_d + ctx->img[l].upd_b1, status));
                     LAUNCHED(ctx, "umma_rows_kernel<UpdateBwd1Op>", MLFFD_STAGE_UPDATE_BWD, st);
-                    umma_rows_kernel<UpdateBwd2Op<true>><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
-                        UpdateBwd2Op<true>{ws.y1[l], ws.v_msg[l], nullptr, uw.U, sb, vb}, N, ctx->w2_images_d + ctx->img[l].upd_b2, status);
+                    TC_DISPATCH(ctx->tc_mode, umma_rows_kernel<UpdateBwd2Op<true>, MODE><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                        UpdateBwd2Op<true>{ws.y1[l], ws.v_msg[l], nullptr, uw.U, sb, vb}, N, ctx->w2_images_d + ctx->img[l].upd_b2, status));
                 } else {
-                    umma_rows_kernel<UpdateBwd1Op<false>><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
-                        UpdateBwd1Op<false>{sb, vb, ws.v_msg[l], uw.U, ws.y1[l]}, N, ctx->w2_images_d + ctx->img[l].upd_b1, status);
+                    TC_DISPATCH(ctx->tc_mode, umma_rows_kernel<UpdateBwd1Op<false>, MODE><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                        UpdateBwd1Op<false>{sb, vb, ws.v_msg[l], uw.U, ws.y1[l]}, N, ctx->w2_images_d + ctx->img[l].upd_b1, status));
                     LAUNCHED(ctx, "umma_rows_kernel<UpdateBwd1Op>", MLFFD_STAGE_UPDATE_BWD, st);
-                    umma_rows_kernel<UpdateBwd2Op<false>><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
-                        UpdateBwd2Op<false>{ws.y1[l], ws.v_msg[l], ws.gates[l], uw.U, sb, vb}, N, ctx->w2_images_d + ctx->img[l].upd_b2, status);
+                    TC_DISPATCH(ctx->tc_mode, umma_rows_kernel<UpdateBwd2Op<false>, MODE><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
+                        UpdateBwd2Op<false>{ws.y1[l], ws.v_msg[l], ws.gates[l], uw.U, sb, vb}, N, ctx->w2_images_d + ctx->img[l].upd_b2, status));
                 }
                 bwd_done = true;
             }
@@ -462,7 +504,7 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
                     ctx->status_d);
             }
         } else if (bwd_pipe) {
-            if constexpr (H == 128) launch_backward_pipe(ctx, l, msg_grid, sb, vb, sb_in, vb_in, N, st);
+            if constexpr (H == 128) launch_backward_pipe(ctx, l, msg_grid, sb, vb, sb_in, vb_in, N, offsets, n_structs, st);
         } else if (ctx->msg_bwd_mode >= 1) {
             if (l == 0) MSG_BWD_PAIRS(true); else MSG_BWD_PAIRS(false);
         } else if (l == 0) { if (first) MSG_BWD(true, false); else MSG_BWD(true, true); }
@@ -593,8 +635,9 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     if (L < 1 || L > kMaxLayers) return fail(nullptr, MLFFD_EINVAL, "num_interactions must be in 1..8");
     if (config->max_z < 1 || !(config->cutoff > 0.f))
         return fail(nullptr, MLFFD_EINVAL, "max_z and cutoff must be positive");
-    if (config->precision != MLFFD_PREC_FP32 && config->precision != MLFFD_PREC_TC_FP16X2)
-        return fail(nullptr, MLFFD_EINVAL, "precision must be MLFFD_PREC_FP32 or MLFFD_PREC_TC_FP16X2");
+    if (config->precision != MLFFD_PREC_FP32 && config->precision != MLFFD_PREC_TC_FP16X2 &&
+        config->precision != MLFFD_PREC_TC_FP16 && config->precision != MLFFD_PREC_TC_BF16)
+        return fail(nullptr, MLFFD_EINVAL, "precision must be MLFFD_PREC_FP32, _TC_FP16X2, _TC_FP16 or _TC_BF16");
     const size_t per_layer = (size_t)H * K + H + 3 * H * H + 3 * H + 2 * H * H + H + 3 * H * H + 3 * H + 9;
     const size_t expect = (size_t)(config->max_z + 1) * H + 2 * K + L * per_layer +
                           (size_t)(H / 2) * H + H / 2 + (size_t)(H / 4) * (H / 2) + H / 4 + H / 4 + 1;
@@ -625,6 +668,9 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
         ctx->msg_bwd_mode = !std::strcmp(ns, "edges") ? 0 : !std::strcmp(ns, "pairs") ? 1 : 2;
     if (const char* ns = std::getenv("MLFFD_READOUT")) ctx->readout_mode = !std::strcmp(ns, "tile") ? 1 : 2;
     if (const char* ns = std::getenv("MLFFD_MSG_FWD")) ctx->msg_fwd_mode = !std::strcmp(ns, "rows") ? 0 : 1;
+    if (const char* ns = std::getenv("MLFFD_AFFINE_FWD")) ctx->affine_fwd = std::atoi(ns);
+    if (const char* ns = std::getenv("MLFFD_AFFINE_BWD")) ctx->affine_bwd = std::atoi(ns);
+    if (const char* ns = std::getenv("MLFFD_AFFINE_PARTS")) ctx->affine_parts = std::max(1, std::atoi(ns));
     if (const char* ns = std::getenv("MLFFD_PIPE_DEPTH_FWD")) ctx->pipe_depth_fwd = std::atoi(ns);
     if (const char* ns = std::getenv("MLFFD_PIPE_DEPTH_BWD")) ctx->pipe_depth_bwd = std::atoi(ns);
     if (const char* nm = std::getenv("MLFFD_NEIGHBOR"))
@@ -684,28 +730,38 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     e = cudaMalloc(&ctx->status_d, sizeof(DeviceStatus));
     if (e != cudaSuccess) return bail(MLFFD_ENOMEM, cudaGetErrorString(e));
     cudaMemset(ctx->status_d, 0, sizeof(DeviceStatus));
-    if (config->precision == MLFFD_PREC_TC_FP16X2) {
+    if (config->precision != MLFFD_PREC_FP32) {
+        ctx->tc_mode = config->precision == MLFFD_PREC_TC_FP16 ? kTcF16
+                     : config->precision == MLFFD_PREC_TC_BF16 ? kTcBF16 : kTcSplit;
+        const int tc_mode = ctx->tc_mode;
         // K-major SWIZZLE_128B images of 128-row blocks of an [out][in] matrix:
         // [hi kb0 .. | lo kb0 ..], each K block 128 rows x 64 halves (see filter_umma.cuh); rows or
         // columns beyond the matrix are zero.
-        std::vector<__half> img;
+        // (the single-pass modes read only the hi halves; BF16 mode stores them as BF16 patterns)
+        std::vector<uint16_t> img;
         auto add_image = [&](const float* Wm, int ld, int rows, int cols, int r0, int c0, int kblk) {
             const size_t base = img.size();
             const size_t term = (size_t)kblk * (kKBlockBytes / 2);
-            img.resize(base + 2 * term, __float2half_rn(0.f));
+            img.resize(base + 2 * term, (uint16_t)0);
             for (int r = 0; r < 128; ++r)
                 for (int k = 0; k < kblk * 64; ++k) {
                     if (r0 + r >= rows || c0 + k >= cols) continue;
                     const float x = Wm[(size_t)(r0 + r) * ld + c0 + k] * kWeightScale;
-                    const __half hi = __float2half_rn(x);
-                    const __half lo = __float2half_rn(x - __half2float(hi));
+                    uint16_t hi, lo = 0;
+                    if (tc_mode == kTcBF16) {
+                        hi = static_cast<__nv_bfloat16_raw>(__float2bfloat16_rn(x)).x;
+                    } else {
+                        const __half h = __float2half_rn(x);
+                        hi = static_cast<__half_raw>(h).x;
+                        lo = static_cast<__half_raw>(__float2half_rn(x - __half2float(h))).x;
+                    }
                     const int kb = k / 64, kc = k % 64;
                     const size_t off = (size_t)(r / 8) * 512 + (size_t)(r % 8) * 64 +
                                        (size_t)(((kc / 8) ^ (r % 8)) * 8) + (size_t)(kc % 8);
                     img[base + (size_t)kb * (kKBlockBytes / 2) + off] = hi;
                     img[base + term + (size_t)kb * (kKBlockBytes / 2) + off] = lo;
                 }
-            return base * sizeof(__half);
+            return base * sizeof(uint16_t);
         };
         const float* q = weights_host + (size_t)(config->max_z + 1) * H + 2 * K;
         const int fkblk = (H > 64) ? H / 64 : 1;
@@ -736,19 +792,20 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
             }
             q += per_layer;
         }
-        e = cudaMalloc(&ctx->w2_images_d, img.size() * sizeof(__half));
+        e = cudaMalloc(&ctx->w2_images_d, img.size() * sizeof(uint16_t));
         if (e != cudaSuccess) return bail(MLFFD_ENOMEM, cudaGetErrorString(e));
-        e = cudaMemcpy(ctx->w2_images_d, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice);
+        e = cudaMemcpy(ctx->w2_images_d, img.data(), img.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
-        if (H == 128) e = cudaFuncSetAttribute(filter_table_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<128>::total());
-        else if (H == 64) e = cudaFuncSetAttribute(filter_table_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<64>::total());
-        else e = cudaFuncSetAttribute(filter_table_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<32>::total());
+        TC_DISPATCH(tc_mode,
+            if (H == 128) e = cudaFuncSetAttribute(filter_table_umma_kernel<128, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<128>::total());
+            else if (H == 64) e = cudaFuncSetAttribute(filter_table_umma_kernel<64, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<64>::total());
+            else e = cudaFuncSetAttribute(filter_table_umma_kernel<32, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<32>::total()));
         if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
         ctx->use_umma_filter = K <= kUmmaMaxRbf;   // first layer runs as one 32-wide K block
         if (H == 128) {
 #define SET_ROWS_ATTR(OP)                                                                            \
-        e = cudaFuncSetAttribute(umma_rows_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 (int)UmmaRowsSmem::TOTAL);                                          \
+        TC_DISPATCH(tc_mode, e = cudaFuncSetAttribute(umma_rows_kernel<OP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)UmmaRowsSmem::TOTAL));                                         \
         if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
         SET_ROWS_ATTR(UpdateFwd1Op) SET_ROWS_ATTR(UpdateFwd2Op<false>) SET_ROWS_ATTR(UpdateFwd2Op<true>)
         SET_ROWS_ATTR(UpdateBwd1Op<false>) SET_ROWS_ATTR(UpdateBwd1Op<true>)

@@ -31,12 +31,14 @@ struct UmmaRowsSmem {
     static constexpr uint32_t TOTAL = BARS + 128 + 1024 /*align*/;
 };
 
-template <class Op>
+template <class Op, int MODE = kTcSplit>
 __global__ void __launch_bounds__(kFilterUmmaThreads, 1)
 umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
                  const DeviceStatus* __restrict__ status) {
     constexpr int KS = Op::KS, NC = Op::NC;
-    constexpr bool SPLIT = KS > 1;   // separate TMEM accumulator for the correction products
+    constexpr bool single = MODE != kTcSplit;        // one product of the `hi` halves (filter_umma.cuh)
+    constexpr bool SPLIT = KS > 1 && !single;        // separate TMEM accumulator for the correction products
+    constexpr int kImageKBlocks = single ? 2 : 4;    // K blocks of a weight image in use: hi (| lo)
     static_assert(!SPLIT || 2 * NC * 128 <= (int)kTmemCols, "not enough tensor memory columns");
     if (status != nullptr && status->overflow) return;
     const int num_tiles = (num_rows + 127) / 128;
@@ -63,10 +65,10 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
             // start streaming the first two weight images before anything else (latency path)
             const int total0 = my_tiles * PER_TILE;
             for (int g = 0; g < 2 && g < total0; ++g) {
-                mbar_expect_tx(&bar_b_full[g], kChunkImageBytes);
+                mbar_expect_tx(&bar_b_full[g], kImageKBlocks * kKBlockBytes);
                 const uint8_t* src = images + (size_t)(g % PER_TILE) * kChunkImageBytes;
                 const uint32_t dst = smem_u32(smem + (g ? UmmaRowsSmem::B1 : UmmaRowsSmem::B0));
-                for (int qq = 0; qq < 4; ++qq)
+                for (int qq = 0; qq < kImageKBlocks; ++qq)
                     bulk_g2s(dst + qq * kKBlockBytes, src + qq * kKBlockBytes, kKBlockBytes, &bar_b_full[g]);
             }
         }
@@ -82,7 +84,7 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
     if (warp == kUmmaComputeWarps) {
         // =============================== issuer ===============================
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc = umma_idesc_128x128(MODE);
             const uint32_t b_buf[2] = {smem_u32(smem + UmmaRowsSmem::B0), smem_u32(smem + UmmaRowsSmem::B1)};
             const uint64_t act_desc_hi = umma_desc_sw128(smem_u32(smem + UmmaRowsSmem::A_HI));
             const uint64_t act_desc_lo = umma_desc_sw128(smem_u32(smem + UmmaRowsSmem::A_LO));
@@ -105,7 +107,7 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
                         const uint64_t w_desc = w_desc0 + (uint64_t)(buf ? (kChunkImageBytes >> 4) : 0);
                         uint32_t acc_corr = (ks > 0) ? 1u : 0u;
 #pragma unroll
-                        for (int pass = 0; pass < 2; ++pass) {   // W_hi*x_lo, W_lo*x_hi
+                        for (int pass = single ? 2 : 0; pass < 2; ++pass) {   // W_hi*x_lo, W_lo*x_hi
                             const uint64_t act_base = (pass == 0) ? act_desc_lo : act_desc_hi;
                             const uint64_t w_base = w_desc + (uint64_t)((pass == 1) ? ((2 * kKBlockBytes) >> 4) : 0);
 #pragma unroll
@@ -117,7 +119,7 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
                                     acc_corr = 1;
                                 }
                         }
-                        uint32_t acc_main = SPLIT ? ((ks > 0) ? 1u : 0u) : 1u;
+                        uint32_t acc_main = (SPLIT || single) ? ((ks > 0) ? 1u : 0u) : 1u;
 #pragma unroll
                         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
@@ -141,10 +143,10 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
             for (int g = 2; g < total; ++g) {   // images 0 and 1 were requested during set-up
                 const int buf = g & 1;
                 mbar_wait(&bar_b_free[buf], ((g - 2) >> 1) & 1);   // MMAs of image g-2 done with the slot
-                mbar_expect_tx(&bar_b_full[buf], kChunkImageBytes);
+                mbar_expect_tx(&bar_b_full[buf], kImageKBlocks * kKBlockBytes);
                 const uint8_t* src = images + (size_t)(g % PER_TILE) * kChunkImageBytes;
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq)
+                for (int qq = 0; qq < kImageKBlocks; ++qq)
                     bulk_g2s(b_buf[buf] + qq * kKBlockBytes, src + qq * kKBlockBytes, kKBlockBytes, &bar_b_full[buf]);
             }
         }
@@ -168,10 +170,10 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
 #pragma unroll
                 for (int rr = 0; rr < 8; ++rr) {
                     uint2 hi, lo;
-                    split4(x[rr], hi, lo);
+                    split4(x[rr], MODE, hi, lo);
                     const uint32_t o = sw128_offset(warp * 8 + rr, chunk) + half8;
                     *reinterpret_cast<uint2*>(a_hi + o) = hi;
-                    *reinterpret_cast<uint2*>(a_lo + o) = lo;
+                    if (!single) *reinterpret_cast<uint2*>(a_lo + o) = lo;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

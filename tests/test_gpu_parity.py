@@ -527,3 +527,32 @@ def test_tiled_readout_matches_warp_readout_and_oracle():
         assert np.max(np.abs(out[mode][1] - f_ref)) <= 3e-5, mode
     assert np.max(np.abs(out["tile"][0] - out["warp"][0]) / counts) <= 2e-6
     assert np.max(np.abs(out["tile"][1] - out["warp"][1])) <= 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# single-pass tensor-core modes: looser, STATED bounds
+# ---------------------------------------------------------------------------------------------
+LOOSE_BOUNDS = {            # (eV / atom, eV / A) against the reference's FP64 outputs
+    "tc_fp16": (2e-3, 5e-2),   # one product of FP16-rounded operands (11-bit significands, TF32 class)
+    "tc_bf16": (2e-2, 5e-1),   # one product of BF16-rounded operands (8-bit significands)
+}
+
+
+@pytest.mark.parametrize("mode", sorted(LOOSE_BOUNDS))
+@pytest.mark.parametrize("variant_name", ["original", "tiny"])
+def test_single_pass_tensor_core_modes_within_stated_bounds(variant_name, mode):
+    e_tol, f_tol = LOOSE_BOUNDS[mode]
+    model, state, cfg = _model(variant_name, precision=mode)
+    gold = load_golden(variant_name)
+    worst_e = worst_f = 0.0
+    for case in golden_cases(gold):
+        z, pos, off = gold[f"{case}_numbers"], gold[f"{case}_positions"], gold[f"{case}_offsets"]
+        e, f = _run(model, z, pos, off)
+        e2, f2 = _run(model, z, pos, off)
+        assert np.array_equal(e, e2) and np.array_equal(f, f2)
+        worst_e = max(worst_e, float(np.max(np.abs(e - gold[f"{case}_energy64"]) / np.diff(off))))
+        if not case.endswith("_exact"):
+            worst_f = max(worst_f, float(np.max(np.abs(f - gold[f"{case}_forces64"]))))
+    assert worst_e <= e_tol and worst_f <= f_tol, (worst_e, worst_f)
+    # and they really are a different arithmetic: coarser than the FP32-equivalent default
+    assert worst_e > E_TOL or worst_f > F_TOL
