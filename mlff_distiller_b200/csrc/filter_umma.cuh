@@ -237,20 +237,48 @@ __device__ __forceinline__ void split1(float x, int tc_mode, uint16_t& hi, uint1
     lo = (uint16_t)l;
 }
 
+// The filter of every layer depends on the pair distances only, so ONE launch evaluates the tables
+// of all layers: the grid is split into per-layer groups of persistent CTAs (sized by the layers'
+// chunk counts so the groups finish together).  For a small system that is one kernel latency per
+// step instead of L; for a large batch nothing changes but the launch count.
+constexpr int kFilterMaxLayers = 8;
+struct FilterLayerArgs {
+    FilterWeights w;
+    const uint8_t* w1_image;   // first-layer weight image (hi | lo)
+    const uint8_t* w2_images;  // second-layer chunk images
+    float* filt;               // [P, 3H]
+    float* dfilt;              // [P, 3H]
+    int skip_vector_gate;      // layer 0 of the model: the b gate is never read
+    int cta_begin;             // first CTA of this layer's group (groups are consecutive)
+};
+struct FilterBatchArgs {
+    FilterLayerArgs layer[kFilterMaxLayers];
+    int num_layers;
+};
+
 template <int H, int MODE = kTcSplit>
 __global__ void __launch_bounds__(kFilterUmmaThreads, 1)
 filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restrict__ num_pairs_ptr,
                          int num_pairs_arg, const DeviceStatus* __restrict__ status,
                          const float* __restrict__ centers, const float* __restrict__ gammas, int K,
-                         float rc, FilterWeights w, const uint8_t* __restrict__ w1_image,
-                         const uint8_t* __restrict__ w2_images, int skip_vector_gate,
-                         float* __restrict__ filt, float* __restrict__ dfilt) {
+                         float rc, const __grid_constant__ FilterBatchArgs batch) {
     constexpr int tc_mode = MODE;
     using G = UmmaGeom<H>;
     if (status != nullptr && status->overflow) return;
     const int P = (num_pairs_ptr != nullptr) ? *num_pairs_ptr : num_pairs_arg;
     const int num_tiles = (P + kUmmaPairs - 1) / kUmmaPairs;
-    if ((int)blockIdx.x >= num_tiles) return;
+    // this CTA's layer and its position inside the layer's group
+    int li = 0;
+    while (li + 1 < batch.num_layers && (int)blockIdx.x >= batch.layer[li + 1].cta_begin) ++li;
+    const int bx = (int)blockIdx.x - batch.layer[li].cta_begin;
+    const int gx = ((li + 1 < batch.num_layers) ? batch.layer[li + 1].cta_begin : (int)gridDim.x) - batch.layer[li].cta_begin;
+    if (bx >= num_tiles) return;
+    const FilterWeights w = batch.layer[li].w;
+    const uint8_t* __restrict__ w1_image = batch.layer[li].w1_image;
+    const uint8_t* __restrict__ w2_images = batch.layer[li].w2_images;
+    const int skip_vector_gate = batch.layer[li].skip_vector_gate;
+    float* __restrict__ filt = batch.layer[li].filt;
+    float* __restrict__ dfilt = batch.layer[li].dfilt;
 
     // Dynamic shared memory only (no static __shared__), so the 1024-byte alignment pad is
     // computed in the shared address space and every access below stays an LDS/STS.
@@ -272,7 +300,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
     // entirely; for smaller H the chunks mix gates, so only the stores are skipped.
     const bool skip_chunk1 = skip_vector_gate && H == 128;
     const int nchunks = skip_chunk1 ? 2 : G::NCH;
-    const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_tiles = (num_tiles - bx + gx - 1) / gx;
     constexpr bool single = tc_mode != kTcSplit;                   // one product, `hi` halves only
     constexpr uint32_t w2_bytes = single ? G::TILE : G::IMAGE;     // bytes of a weight chunk in use
     constexpr int first_pass = single ? 2 : 0;                     // passes: hi*lo, lo*hi, hi*hi
@@ -423,7 +451,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
         auto rbf_compute = [&](int it) {   // pure math (overlaps the tensor cores)
             if (tid < 4 * kUmmaPairs) {
                 const int p = tid >> 2, chunk = tid & 3;
-                const int gp = ((int)blockIdx.x + it * (int)gridDim.x) * kUmmaPairs + p;
+                const int gp = (bx + it * gx) * kUmmaPairs + p;
                 const float d = (gp < P) ? __ldg(pair_dist + gp) : rc;
                 const float kPi = 3.14159274101257324f;
                 const float arg = (kPi * d) / rc;
@@ -513,7 +541,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
         rbf_store();
         publish_tile(0);
         for (int it = 0; it < my_tiles; ++it) {
-            const int p0 = ((int)blockIdx.x + it * (int)gridDim.x) * kUmmaPairs;
+            const int p0 = (bx + it * gx) * kUmmaPairs;
             if (it + 1 < my_tiles) rbf_compute(it + 1);        // while the tensor cores work on chunk 0
             FT_MARK(2)
             // ---- epilogue of tile `it`: D[channel = lane][row = column] -> global ----

@@ -41,55 +41,11 @@ struct RowSegment {
     float4 geo;   // per lane: (u_x, u_y, u_z, d)
 };
 
-// Which rows a warp visits, in which order.
-//   grid-stride (offsets == nullptr): warp w of the grid owns rows w, w + stride, ...: the rows in
-//     flight on the chip are consecutive atoms, but one SM sees rows of ever-changing structures.
-//   structure-affine (batches of small structures): the BLOCK walks work units blockIdx.x,
-//     + gridDim.x, ... where a unit is one structure (or 1/parts of its rows) and the block's W warps
-//     take the unit's rows round-robin.  Every neighbour gather of the block then falls on the
-//     ~50 feature rows of ONE structure, which stay in the SM's L1 (each row is reused ~20x), so
-//     the gathers leave the L2 -> SM crossbar to the filter-table rows.  Warps never synchronise:
-//     a warp that runs out of rows moves on to the block's next unit, and the warp that gets the
-//     odd extra row rotates from unit to unit.
-struct RowCursor {
-    const int* offsets; int num_structs; int parts; int stride; int W; int pos;
-    int unit, lo, hi, rot;
-
-    __device__ __forceinline__ int open_units() {   // first row of this warp in `unit` or a later one
-        const int num_units = num_structs * parts;
-        while (unit < num_units) {
-            const int k = unit / parts, part = unit - k * parts;
-            const int slo = __ldg(offsets + k), shi = __ldg(offsets + k + 1);
-            const int chunk = (shi - slo + parts - 1) / parts;
-            lo = slo + part * chunk;
-            hi = min(shi, lo + chunk);
-            int p = pos - rot;
-            p += (p < 0) ? W : 0;
-            rot = (rot + max(hi - lo, 0)) % W;
-            if (lo + p < hi) return lo + p;
-            unit += (int)gridDim.x;
-        }
-        return -1;
-    }
-    __device__ __forceinline__ int first(int global_warp) {
-        if (offsets == nullptr) return global_warp;
-        unit = (int)blockIdx.x; rot = 0;
-        return open_units();
-    }
-    __device__ __forceinline__ int next(int row) {
-        if (offsets == nullptr) return row + stride;
-        if (row + W < hi) return row + W;
-        unit += (int)gridDim.x;
-        return open_units();
-    }
-};
-
-// Walks the rows of one warp as a stream of segments, with rowptr two rows ahead.
+// Walks the rows of one warp (grid-stride) as a stream of segments, with rowptr two rows ahead.
 template <bool WITH_REV>
 struct SegmentStream {
     const int* rowptr; const int* col; const int* pair; const int* rev; const float4* geo;
-    int num_atoms, lane;
-    RowCursor cursor;
+    int num_atoms, stride, lane;
     int la_row, la_a, la_b;   // look-ahead row and its rowptr pair (loads may still be in flight)
 
     __device__ __forceinline__ void fetch_lookahead(int row) {
@@ -112,7 +68,7 @@ struct SegmentStream {
         const int deg = la_b - la_a;
         s.n = min(deg, 32); s.rem = deg - s.n;
         load_lanes(s);
-        fetch_lookahead(la_row >= 0 ? cursor.next(la_row) : -1);
+        fetch_lookahead(la_row >= 0 ? la_row + stride : -1);
         return s;
     }
     __device__ __forceinline__ RowSegment next_of(const RowSegment& c) {
@@ -138,22 +94,20 @@ __device__ __forceinline__ float4 shfl4(const float4& v, int src) {
 // slower than plain loads, and blocks of 16 - 32 warps were slower than 8.
 constexpr int kPipeWarps = 8;
 constexpr int kFwdParts = 3, kBwdParts = 6;
-template <int D, int W = kPipeWarps>
-constexpr size_t message_forward_pipe_smem() { return (size_t)W * D * kFwdParts * 512; }
-template <int D, int W = kPipeWarps>
-constexpr size_t message_backward_pipe_smem() { return (size_t)W * D * kBwdParts * 512; }
+template <int D>
+constexpr size_t message_forward_pipe_smem() { return (size_t)kPipeWarps * D * kFwdParts * 512; }
+template <int D>
+constexpr size_t message_backward_pipe_smem() { return (size_t)kPipeWarps * D * kBwdParts * 512; }
 
 // Forward; contract of message_forward_kernel<128, LAYER0>.
-// `offsets` != nullptr selects the structure-affine row order (RowCursor) with W warps per block.
-template <bool LAYER0, int D, int W = kPipeWarps>
-__global__ void __launch_bounds__(32 * W)
+template <bool LAYER0, int D>
+__global__ void __launch_bounds__(32 * kPipeWarps)
 message_forward_pipe_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                             const int* __restrict__ pair, const float4* __restrict__ geo,
                             const float* __restrict__ filt, const float* __restrict__ s_in,
                             const float* __restrict__ v_in, float* __restrict__ s_msg,
                             float* __restrict__ v_msg, int num_atoms,
-                            const DeviceStatus* __restrict__ status,
-                            const int* __restrict__ offsets, int num_structs, int parts) {
+                            const DeviceStatus* __restrict__ status) {
     constexpr int H = 128;
     constexpr unsigned full = 0xffffffffu;
     if (status->overflow) return;
@@ -163,11 +117,10 @@ message_forward_pipe_kernel(const int* __restrict__ rowptr, const int* __restric
     const float4* ring = pipe_ring + (size_t)wib * (D * PARTS * 32) + lane;   // slot s, part p: ring[(s*PARTS+p)*32]
     const uint32_t ring_addr = smem_addr32(ring);
     const int c4 = lane * 4;
-    const int warp = blockIdx.x * W + wib, num_warps = gridDim.x * W;
+    const int warp = blockIdx.x * kPipeWarps + wib, num_warps = gridDim.x * kPipeWarps;
 
-    SegmentStream<false> stream{rowptr, col, pair, nullptr, geo, num_atoms, lane,
-                                RowCursor{offsets, num_structs, parts, num_warps, W, wib, 0, 0, 0, 0}, -1, 0, 0};
-    stream.fetch_lookahead(stream.cursor.first(warp));
+    SegmentStream<false> stream{rowptr, col, pair, nullptr, geo, num_atoms, num_warps, lane, -1, 0, 0};
+    stream.fetch_lookahead(warp);
     RowSegment cur = stream.from_lookahead();
     RowSegment nxt = stream.next_of(cur);
     int issued = 0;        // edges of cur ++ nxt already requested (index relative to cur's first edge)
@@ -249,8 +202,8 @@ message_forward_pipe_kernel(const int* __restrict__ rowptr, const int* __restric
 // message_backward_pairs_kernel<128, LAYER0, false> (message.cuh).  Ring slot = the six 512-byte
 // parts (a, b, c, a', b', c') of the pair's table rows; edges with j < i only request (a, b), and
 // for LAYER0 nothing at all.
-template <bool LAYER0, int D, int W = kPipeWarps>
-__global__ void __launch_bounds__(32 * W, 16 / W)
+template <bool LAYER0, int D>
+__global__ void __launch_bounds__(32 * kPipeWarps, 2)
 message_backward_pipe_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                              const int* __restrict__ pair, const int* __restrict__ rev,
                              const float4* __restrict__ geo, const float* __restrict__ filt,
@@ -258,8 +211,7 @@ message_backward_pipe_kernel(const int* __restrict__ rowptr, const int* __restri
                              const float* __restrict__ v_in, const float* __restrict__ sbar_m,
                              const float* __restrict__ vbar_m, float* __restrict__ sbar_in,
                              float* __restrict__ vbar_in, float4* __restrict__ edge_adj,
-                             int num_atoms, const DeviceStatus* __restrict__ status,
-                             const int* __restrict__ offsets, int num_structs, int parts) {
+                             int num_atoms, const DeviceStatus* __restrict__ status) {
     constexpr int H = 128;
     constexpr unsigned full = 0xffffffffu;
     if (status->overflow) return;
@@ -271,11 +223,10 @@ message_backward_pipe_kernel(const int* __restrict__ rowptr, const int* __restri
     const int c4 = lane * 4;
     const int held = ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
     const bool holder = (lane & 3) == 0;
-    const int warp = blockIdx.x * W + wib, num_warps = gridDim.x * W;
+    const int warp = blockIdx.x * kPipeWarps + wib, num_warps = gridDim.x * kPipeWarps;
 
-    SegmentStream<true> stream{rowptr, col, pair, rev, geo, num_atoms, lane,
-                               RowCursor{offsets, num_structs, parts, num_warps, W, wib, 0, 0, 0, 0}, -1, 0, 0};
-    stream.fetch_lookahead(stream.cursor.first(warp));
+    SegmentStream<true> stream{rowptr, col, pair, rev, geo, num_atoms, num_warps, lane, -1, 0, 0};
+    stream.fetch_lookahead(warp);
     RowSegment cur = stream.from_lookahead();
     RowSegment nxt = stream.next_of(cur);
     int issued = 0, drain_until = -1, put = 0, get = 0;

@@ -83,19 +83,17 @@ struct mlffd_ctx {
     bool enable_staging = false;     // env MLFFD_STAGING=1
     int readout_mode = 0;            // env MLFFD_READOUT: 0 = by size, 1 = tile, 2 = warp
     bool readout_configured = false; // smem attribute of readout_tile_kernel set on this device
-    uint32_t pipe_configured_fwd[3] = {0, 0, 0};   // bit per pipelined-kernel instantiation whose smem
-    uint32_t pipe_configured_bwd[2] = {0, 0};      // attribute is set on this device, by block size
+    uint32_t pipe_configured = 0;    // bit per pipelined-kernel instantiation whose smem attribute is set on this device
     int last_adj_slabs = 0;          // edge-adjoint slabs written by the last force evaluation (0 = none)
     int msg_bwd_mode = 2;            // env MLFFD_MSG_BWD = edges (0) | pairs (1) | pipe (2)
     int msg_fwd_mode = 1;            // env MLFFD_MSG_FWD = rows (0) | pipe (1)
-    int affine_fwd = 0;              // env MLFFD_AFFINE_FWD: warps per block of the structure-affine forward (0 = grid-stride: default, faster on C2)
-    int affine_bwd = 0;              // env MLFFD_AFFINE_BWD: same for the reverse kernel (0 | 8 | 16)
-    int affine_parts = 1;            // env MLFFD_AFFINE_PARTS: work units per structure
     int pipe_depth_fwd = 2;          // env MLFFD_PIPE_DEPTH_FWD: ring slots per warp
     int pipe_depth_bwd = 2;          // env MLFFD_PIPE_DEPTH_BWD
     std::string err;
     float* weights_d = nullptr;
     uint8_t* w2_images_d = nullptr;   // swizzled fp16 hi/lo 64 KB weight images (tensor-core path)
+    int filter_batch = 2;           // env MLFFD_FILTER_BATCH: 1 = all layers' filter tables in one launch, 0 = one launch per layer, 2 = one launch only for small systems
+    int small_rows = 2048;          // env MLFFD_SMALL_ROWS: at or below this many atoms the update block runs on ffma_rows_kernel
     int tc_mode = 0;                // kTcSplit | kTcF16 | kTcBF16 (filter_umma.cuh), from cfg.precision
     bool use_umma = false;          // tensor-core update block (H = 128)
     bool use_umma_filter = false;   // tensor-core filter table (H = 128, 64, 32)
@@ -236,20 +234,53 @@ int set_kernel_attributes(mlffd_ctx* ctx) {
     } while (0)
 
 // ---- per-H launch sequences -----------------------------------------------------------------
+// Tensor-core filter tables of layers [l0, l1) in one launch (filter_umma.cuh).  filt / dfilt
+// override the workspace tables for the single-layer stage entry point.
+template <int H>
+int launch_filter_umma(mlffd_ctx* ctx, int l0, int l1, const float* dist, const int* num_pairs_ptr,
+                       int num_pairs_arg, const DeviceStatus* status, float* filt, float* dfilt,
+                       int64_t pair_bound, cudaStream_t st) {
+    const int nl = l1 - l0;
+    const int tiles = (int)ceil_div(std::max<int64_t>(pair_bound, 1), kUmmaPairs);
+    FilterBatchArgs batch{};
+    batch.num_layers = nl;
+    // persistent CTAs per layer in proportion to the layer's 128-channel chunks (layer 0 skips the b gate)
+    int weight[kFilterMaxLayers], total_w = 0;
+    for (int i = 0; i < nl; ++i) {
+        const bool skip = (l0 + i == 0) && status != nullptr;
+        // measured on C2: a layer-0 tile (two of three chunks) costs ~0.75 of a full tile -- the RBF,
+        // first-layer and publish phases do not shrink with the chunk count
+        weight[i] = (skip && H == 128) ? 3 : 4;
+        total_w += weight[i];
+    }
+    const int budget = std::max(kNumSMs, nl);
+    int begin = 0;
+    for (int i = 0; i < nl; ++i) {
+        const int l = l0 + i;
+        int share = (i == nl - 1) ? budget - begin : std::max(1, (budget * weight[i] + total_w / 2) / total_w);
+        share = std::max(1, std::min(share, tiles));
+        FilterLayerArgs& a = batch.layer[i];
+        a.w = ctx->layer[l].filter;
+        a.w1_image = ctx->w2_images_d + ctx->img[l].filter1;
+        a.w2_images = ctx->w2_images_d + ctx->img[l].filter;
+        a.filt = filt ? filt : ctx->ws.filt[l];
+        a.dfilt = dfilt ? dfilt : ctx->ws.dfilt[l];
+        a.skip_vector_gate = (l == 0 && status != nullptr) ? 1 : 0;
+        a.cta_begin = begin;
+        begin += share;
+    }
+    TC_DISPATCH(ctx->tc_mode, filter_table_umma_kernel<H, MODE><<<begin, kFilterUmmaThreads, UmmaGeom<H>::total(), st>>>(
+        dist, num_pairs_ptr, num_pairs_arg, status, ctx->centers, ctx->gammas, ctx->K, ctx->cfg.cutoff, batch));
+    LAUNCHED(ctx, "filter_table_umma_kernel", MLFFD_STAGE_FILTER, st);
+    return MLFFD_OK;
+}
+
 template <int H>
 int launch_filter(mlffd_ctx* ctx, int l, const float* dist, const int* num_pairs_ptr,
                   int num_pairs_arg, const DeviceStatus* status, float* filt, float* dfilt,
                   int64_t pair_bound, cudaStream_t st) {
-    if (ctx->use_umma_filter) {
-        const int grid = clamp_grid(ceil_div(std::max<int64_t>(pair_bound, 1), kUmmaPairs), kNumSMs);
-        TC_DISPATCH(ctx->tc_mode, filter_table_umma_kernel<H, MODE><<<grid, kFilterUmmaThreads, UmmaGeom<H>::total(), st>>>(
-            dist, num_pairs_ptr, num_pairs_arg, status, ctx->centers, ctx->gammas, ctx->K,
-            ctx->cfg.cutoff, ctx->layer[l].filter, ctx->w2_images_d + ctx->img[l].filter1,
-            ctx->w2_images_d + ctx->img[l].filter,
-            (l == 0 && status != nullptr) ? 1 : 0, filt, dfilt));
-        LAUNCHED(ctx, "filter_table_umma_kernel", MLFFD_STAGE_FILTER, st);
-        return MLFFD_OK;
-    }
+    if (ctx->use_umma_filter)
+        return launch_filter_umma<H>(ctx, l, l + 1, dist, num_pairs_ptr, num_pairs_arg, status, filt, dfilt, pair_bound, st);
     const int blocks_per_sm = (filter_smem_bytes<H>() <= 110 * 1024) ? 2 : 1;
     const int grid = clamp_grid(ceil_div(std::max<int64_t>(pair_bound, 1), kFilterPairs),
                                 kNumSMs * blocks_per_sm);
@@ -260,86 +291,70 @@ int launch_filter(mlffd_ctx* ctx, int l, const float* dist, const int* num_pairs
     return MLFFD_OK;
 }
 
-// Structure-affine row order (message_pipe.cuh:RowCursor) pays when the batch holds many small
-// structures: enough work units to fill the chip, units short enough that a block's warps stay on
-// the same structure.  One block per SM slot; each block walks units blockIdx.x, + gridDim.x, ...
-inline bool use_affine(const mlffd_ctx* ctx, int warps, int n_structs, int N) {
-    return warps > 0 && n_structs * ctx->affine_parts >= 2 * kNumSMs && N / std::max(n_structs, 1) <= 512;
-}
-
-template <bool LAYER0, int D, int W>
-void launch_forward_pipe_w(mlffd_ctx* ctx, int l, int grid, int N, const int* offsets, int n_structs,
-                           cudaStream_t st) {
+template <bool LAYER0, int D>
+void launch_forward_pipe_d(mlffd_ctx* ctx, int l, int grid, int N, cudaStream_t st) {
     Workspace& ws = ctx->ws;
-    auto kernel = message_forward_pipe_kernel<LAYER0, D, W>;
-    constexpr size_t smem = message_forward_pipe_smem<D, W>();
+    auto kernel = message_forward_pipe_kernel<LAYER0, D>;
+    constexpr size_t smem = message_forward_pipe_smem<D>();
     // per context (device), not per process: a second context on another GPU needs the attribute too
-    constexpr int wbit = (W == 8) ? 0 : (W == 12) ? 1 : 2;
-    uint32_t& configured = ctx->pipe_configured_fwd[wbit];
-    constexpr uint32_t bit = 1u << (2 * D + (LAYER0 ? 1 : 0));
-    if (!(configured & bit)) {
+    constexpr uint32_t bit = 1u << (2 * D + (LAYER0 ? 1 : 0) + 0);
+    if (!(ctx->pipe_configured & bit)) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured |= bit;
+        ctx->pipe_configured |= bit;
     }
-    kernel<<<grid, 32 * W, smem, st>>>(ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l],
-                                     LAYER0 ? nullptr : ws.v_in[l], ws.s_msg[l], ws.v_msg[l], N,
-                                     ctx->status_d, offsets, n_structs, ctx->affine_parts);
+    kernel<<<grid, 32 * kPipeWarps, smem, st>>>(ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l],
+                                              LAYER0 ? nullptr : ws.v_in[l], ws.s_msg[l], ws.v_msg[l], N,
+                                              ctx->status_d);
 }
-void launch_forward_pipe(mlffd_ctx* ctx, int l, int grid, int N, const int* offsets, int n_structs,
-                         cudaStream_t st) {
-#define FWD_PIPE(D, W, G, OFF) (l == 0 ? launch_forward_pipe_w<true, D, W>(ctx, l, G, N, OFF, n_structs, st) \
-                                       : launch_forward_pipe_w<false, D, W>(ctx, l, G, N, OFF, n_structs, st))
-    if (use_affine(ctx, ctx->affine_fwd, n_structs, N)) {
-        // resident blocks per SM by registers (80 / thread): 3 x 8 warps, 2 x 12, 1 x 24
-        const int units = n_structs * ctx->affine_parts;
-        switch (ctx->affine_fwd) {
-            case 8:  FWD_PIPE(2, 8, std::min(units, kNumSMs * 3), offsets); break;
-            case 12: FWD_PIPE(2, 12, std::min(units, kNumSMs * 2), offsets); break;
-            default: FWD_PIPE(2, 24, std::min(units, kNumSMs), offsets); break;
-        }
-        return;
-    }
+void launch_forward_pipe(mlffd_ctx* ctx, int l, int grid, int N, cudaStream_t st) {
+#define FWD_PIPE(D) (l == 0 ? launch_forward_pipe_d<true, D>(ctx, l, grid, N, st) : launch_forward_pipe_d<false, D>(ctx, l, grid, N, st))
     switch (ctx->pipe_depth_fwd) {
-        case 3: FWD_PIPE(3, 8, grid, nullptr); break;
-        case 4: FWD_PIPE(4, 8, grid, nullptr); break;
-        case 8: FWD_PIPE(8, 8, grid, nullptr); break;
-        default: FWD_PIPE(2, 8, grid, nullptr); break;
+        case 3: FWD_PIPE(3); break;
+        case 4: FWD_PIPE(4); break;
+        case 8: FWD_PIPE(8); break;
+        default: FWD_PIPE(2); break;
     }
 #undef FWD_PIPE
 }
 
-template <bool LAYER0, int D, int W>
-void launch_backward_pipe_w(mlffd_ctx* ctx, int l, int grid, const float* sb, const float* vb, float* sb_in,
-                            float* vb_in, int N, const int* offsets, int n_structs, cudaStream_t st) {
+template <bool LAYER0, int D>
+void launch_backward_pipe_d(mlffd_ctx* ctx, int l, int grid, const float* sb, const float* vb, float* sb_in,
+                            float* vb_in, int N, cudaStream_t st) {
     Workspace& ws = ctx->ws;
-    auto kernel = message_backward_pipe_kernel<LAYER0, D, W>;
-    constexpr size_t smem = message_backward_pipe_smem<D, W>();
-    uint32_t& configured = ctx->pipe_configured_bwd[W == 8 ? 0 : 1];
-    constexpr uint32_t bit = 1u << (2 * D + (LAYER0 ? 1 : 0));
-    if (!(configured & bit)) {
+    auto kernel = message_backward_pipe_kernel<LAYER0, D>;
+    constexpr size_t smem = message_backward_pipe_smem<D>();
+    // per context (device), not per process: a second context on another GPU needs the attribute too
+    constexpr uint32_t bit = 1u << (2 * D + (LAYER0 ? 1 : 0) + 14);
+    if (!(ctx->pipe_configured & bit)) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured |= bit;
+        ctx->pipe_configured |= bit;
     }
-    kernel<<<grid, 32 * W, smem, st>>>(ws.rowptr, ws.col, ws.pair, ws.rev, ws.geo, ws.filt[l], ws.dfilt[l],
-                                     ws.s_in[l], LAYER0 ? nullptr : ws.v_in[l], sb, vb, sb_in, vb_in,
-                                     ws.edge_adj + (size_t)l * ws.cap_edges, N, ctx->status_d,
-                                     offsets, n_structs, ctx->affine_parts);
+    kernel<<<grid, 32 * kPipeWarps, smem, st>>>(ws.rowptr, ws.col, ws.pair, ws.rev, ws.geo, ws.filt[l], ws.dfilt[l],
+                                              ws.s_in[l], LAYER0 ? nullptr : ws.v_in[l], sb, vb, sb_in, vb_in,
+                                              ws.edge_adj + (size_t)l * ws.cap_edges, N, ctx->status_d);
 }
 void launch_backward_pipe(mlffd_ctx* ctx, int l, int grid, const float* sb, const float* vb, float* sb_in,
-                          float* vb_in, int N, const int* offsets, int n_structs, cudaStream_t st) {
-#define BWD_PIPE(D, W, G, OFF) (l == 0 ? launch_backward_pipe_w<true, D, W>(ctx, l, G, sb, vb, sb_in, vb_in, N, OFF, n_structs, st) \
-                                       : launch_backward_pipe_w<false, D, W>(ctx, l, G, sb, vb, sb_in, vb_in, N, OFF, n_structs, st))
-    if (use_affine(ctx, ctx->affine_bwd, n_structs, N)) {
-        const int units = n_structs * ctx->affine_parts;
-        if (ctx->affine_bwd == 8) BWD_PIPE(2, 8, std::min(units, kNumSMs * 2), offsets);
-        else BWD_PIPE(2, 16, std::min(units, kNumSMs), offsets);
-        return;
-    }
+                          float* vb_in, int N, cudaStream_t st) {
+#define BWD_PIPE(D) (l == 0 ? launch_backward_pipe_d<true, D>(ctx, l, grid, sb, vb, sb_in, vb_in, N, st) \
+                            : launch_backward_pipe_d<false, D>(ctx, l, grid, sb, vb, sb_in, vb_in, N, st))
     switch (ctx->pipe_depth_bwd) {
-        case 4: BWD_PIPE(4, 8, grid, nullptr); break;
-        default: BWD_PIPE(2, 8, grid, nullptr); break;
+        case 4: BWD_PIPE(4); break;
+        default: BWD_PIPE(2); break;
     }
 #undef BWD_PIPE
+}
+
+// small systems: update-block op on the many-block FFMA kernel (umma_rows.cuh:ffma_rows_kernel)
+template <class Op>
+void launch_ffma_rows(mlffd_ctx* ctx, const Op& op, int N, const float* wt, int ld, cudaStream_t st) {
+    static bool configured[16] = {};   // per device: the attribute is per (function, device)
+    auto kernel = ffma_rows_kernel<Op>;
+    constexpr size_t smem = ffma_rows_smem_bytes<Op>();
+    if (!configured[ctx->device & 15]) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[ctx->device & 15] = true;
+    }
+    kernel<<<dim3(ceil_div(N, kSkinnyRows), 4), kSkinnyThreads, smem, st>>>(op, N, wt, ld, ctx->status_d);
 }
 
 template <int H>
@@ -373,10 +388,21 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
         z, ctx->emb, ctx->cfg.max_z, ws.s_in[0], N);
     LAUNCHED(ctx, "embedding_kernel", MLFFD_STAGE_EMBEDDING, st);
 
-    for (int l = 0; l < L; ++l) {
-        int rc = launch_filter<H>(ctx, l, ws.pair_dist, &ctx->status_d->num_pairs, 0, status,
-                                  ws.filt[l], ws.dfilt[l], ws.cap_pairs, st);
+    // the filters depend on the distances only: with the tensor-core kernel all layers' tables come
+    // from one launch ahead of the layer loop
+    const bool filters_up_front = ctx->use_umma_filter &&
+                                  (ctx->filter_batch == 1 || (ctx->filter_batch == 2 && N <= ctx->small_rows));
+    if (filters_up_front) {
+        int rc = launch_filter_umma<H>(ctx, 0, L, ws.pair_dist, &ctx->status_d->num_pairs, 0, status,
+                                       nullptr, nullptr, ws.cap_pairs, st);
         if (rc) return rc;
+    }
+    for (int l = 0; l < L; ++l) {
+        if (!filters_up_front) {
+            int rc = launch_filter<H>(ctx, l, ws.pair_dist, &ctx->status_d->num_pairs, 0, status,
+                                      ws.filt[l], ws.dfilt[l], ws.cap_pairs, st);
+            if (rc) return rc;
+        }
         if (staged && l == 0)
             message_forward_staged_kernel<H, true><<<staged_grid, kStagedThreads, staged_smem, st>>>(
                 offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], nullptr,
@@ -386,7 +412,7 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
                 offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], ws.v_in[l],
                 ws.s_msg[l], ws.v_msg[l], ctx->status_d);
         else if (fwd_pipe) {
-            if constexpr (H == 128) launch_forward_pipe(ctx, l, msg_grid, N, offsets, n_structs, st);
+            if constexpr (H == 128) launch_forward_pipe(ctx, l, msg_grid, N, st);
         } else if (l == 0)
             message_forward_kernel<H, true><<<msg_grid, 256, 0, st>>>(
                 ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], nullptr, ws.s_msg[l],
@@ -398,7 +424,18 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
         LAUNCHED(ctx, "message_forward_kernel", MLFFD_STAGE_MESSAGE_FWD, st);
         bool upd_done = false;
         if constexpr (H == 128) {
-            if (ctx->use_umma) {
+            if (ctx->use_umma && N <= ctx->small_rows) {
+                const UpdateWeights& uw = ctx->layer[l].update;
+                launch_ffma_rows(ctx, UpdateFwd1Op{ws.s_msg[l], ws.v_msg[l], uw.m1, ws.y1[l]}, N, uw.M1t, H, st);
+                LAUNCHED(ctx, "ffma_rows_kernel<UpdateFwd1Op>", MLFFD_STAGE_UPDATE_FWD, st);
+                if (l == L - 1)
+                    launch_ffma_rows(ctx, UpdateFwd2Op<true>{ws.y1[l], ws.s_msg[l], ws.v_msg[l], uw.m2, uw.U, ws.s_in[l + 1], nullptr, nullptr},
+                                     N, uw.M2t, 3 * H, st);
+                else
+                    launch_ffma_rows(ctx, UpdateFwd2Op<false>{ws.y1[l], ws.s_msg[l], ws.v_msg[l], uw.m2, uw.U, ws.s_in[l + 1], ws.v_in[l + 1], ws.gates[l]},
+                                     N, uw.M2t, 3 * H, st);
+                upd_done = true;
+            } else if (ctx->use_umma) {
                 const UpdateWeights& uw = ctx->layer[l].update;
                 const int rows_grid = clamp_grid(ceil_div(N, 128), kNumSMs);
                 TC_DISPATCH(ctx->tc_mode, umma_rows_kernel<UpdateFwd1Op, MODE><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
@@ -431,7 +468,10 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     const bool want_forces = forces != nullptr;
     auto adj = [&](int l) { return ctx->debug_keep ? l : (l & 1); };
     // enough 64-atom tiles to fill the GPU: register-tiled GEMMs (env MLFFD_READOUT = tile | warp forces one)
-    if (H == 128 && (ctx->readout_mode == 1 || (ctx->readout_mode == 0 && N >= 64 * kNumSMs))) {
+    if (ctx->readout_mode == 0 && N <= ctx->small_rows) {
+        readout_block_kernel<H><<<ceil_div(N, 4), 256, 0, st>>>(ws.s_in[L], ctx->head, ws.eps,
+                                                               want_forces ? ws.sbar[adj(L - 1)] : nullptr, N, status);
+    } else if (H == 128 && (ctx->readout_mode == 1 || (ctx->readout_mode == 0 && N >= 64 * kNumSMs))) {
         if (!ctx->readout_configured) {
             cudaFuncSetAttribute(readout_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)readout_tile_smem_bytes());
             ctx->readout_configured = true;
@@ -452,7 +492,19 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
         float* vb = ws.vbar[adj(l)];
         bool bwd_done = false;
         if constexpr (H == 128) {
-            if (ctx->use_umma) {
+            if (ctx->use_umma && N <= ctx->small_rows) {
+                const UpdateWeights& uw = ctx->layer[l].update;
+                if (l == L - 1) {
+                    launch_ffma_rows(ctx, UpdateBwd1Op<true>{sb, vb, ws.v_msg[l], uw.U, ws.y1[l]}, N, uw.M2, H, st);
+                    LAUNCHED(ctx, "ffma_rows_kernel<UpdateBwd1Op>", MLFFD_STAGE_UPDATE_BWD, st);
+                    launch_ffma_rows(ctx, UpdateBwd2Op<true>{ws.y1[l], ws.v_msg[l], nullptr, uw.U, sb, vb}, N, uw.M1, 2 * H, st);
+                } else {
+                    launch_ffma_rows(ctx, UpdateBwd1Op<false>{sb, vb, ws.v_msg[l], uw.U, ws.y1[l]}, N, uw.M2, H, st);
+                    LAUNCHED(ctx, "ffma_rows_kernel<UpdateBwd1Op>", MLFFD_STAGE_UPDATE_BWD, st);
+                    launch_ffma_rows(ctx, UpdateBwd2Op<false>{ws.y1[l], ws.v_msg[l], ws.gates[l], uw.U, sb, vb}, N, uw.M1, 2 * H, st);
+                }
+                bwd_done = true;
+            } else if (ctx->use_umma) {
                 const UpdateWeights& uw = ctx->layer[l].update;
                 const int rows_grid = clamp_grid(ceil_div(N, 128), kNumSMs);
                 if (l == L - 1) {
@@ -504,7 +556,7 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
                     ctx->status_d);
             }
         } else if (bwd_pipe) {
-            if constexpr (H == 128) launch_backward_pipe(ctx, l, msg_grid, sb, vb, sb_in, vb_in, N, offsets, n_structs, st);
+            if constexpr (H == 128) launch_backward_pipe(ctx, l, msg_grid, sb, vb, sb_in, vb_in, N, st);
         } else if (ctx->msg_bwd_mode >= 1) {
             if (l == 0) MSG_BWD_PAIRS(true); else MSG_BWD_PAIRS(false);
         } else if (l == 0) { if (first) MSG_BWD(true, false); else MSG_BWD(true, true); }
@@ -535,6 +587,13 @@ int build_neighbors(mlffd_ctx* ctx, const float* pos, const int* offsets, int n_
     ctx->last_structs = n_structs;
     ctx->last_stream = st;
     mark(ctx, -1, st, 0);  // step start
+    if (N <= kSmallNeighborAtoms && ctx->neighbor_mode == 0 && ctx->small_rows > 0) {   // latency path: one launch
+        neighbor_small_kernel<<<1, 1024, 0, st>>>(pos, offsets, n_structs, cells, pbc, N, ctx->cfg.cutoff,
+                                                  (int)ws.cap_edges, ws.atom_struct, ws.rowptr, ws.lowptr, ws.col,
+                                                  ws.edge_dst, ws.geo, ws.rev, ws.pair, ws.pair_dist, ctx->status_d);
+        LAUNCHED(ctx, "neighbor_small_kernel", MLFFD_STAGE_NEIGHBOR, st);
+        return MLFFD_OK;
+    }
     atom_structure_kernel<<<clamp_grid(ceil_div(N, 256), kNumSMs * 8), 256, 0, st>>>(
         offsets, n_structs, N, ws.atom_struct);
     LAUNCHED(ctx, "atom_structure_kernel", MLFFD_STAGE_NEIGHBOR, st);
@@ -668,9 +727,8 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
         ctx->msg_bwd_mode = !std::strcmp(ns, "edges") ? 0 : !std::strcmp(ns, "pairs") ? 1 : 2;
     if (const char* ns = std::getenv("MLFFD_READOUT")) ctx->readout_mode = !std::strcmp(ns, "tile") ? 1 : 2;
     if (const char* ns = std::getenv("MLFFD_MSG_FWD")) ctx->msg_fwd_mode = !std::strcmp(ns, "rows") ? 0 : 1;
-    if (const char* ns = std::getenv("MLFFD_AFFINE_FWD")) ctx->affine_fwd = std::atoi(ns);
-    if (const char* ns = std::getenv("MLFFD_AFFINE_BWD")) ctx->affine_bwd = std::atoi(ns);
-    if (const char* ns = std::getenv("MLFFD_AFFINE_PARTS")) ctx->affine_parts = std::max(1, std::atoi(ns));
+    if (const char* ns = std::getenv("MLFFD_SMALL_ROWS")) ctx->small_rows = std::atoi(ns);
+    if (const char* ns = std::getenv("MLFFD_FILTER_BATCH")) ctx->filter_batch = std::atoi(ns);
     if (const char* ns = std::getenv("MLFFD_PIPE_DEPTH_FWD")) ctx->pipe_depth_fwd = std::atoi(ns);
     if (const char* ns = std::getenv("MLFFD_PIPE_DEPTH_BWD")) ctx->pipe_depth_bwd = std::atoi(ns);
     if (const char* nm = std::getenv("MLFFD_NEIGHBOR"))

@@ -194,6 +194,146 @@ __global__ void reverse_pair_kernel(const int* __restrict__ rowptr, const int* _
     if ((threadIdx.x & 31) == 0 && local_max > 0) atomicMax(&status->max_degree, local_max);
 }
 
+// Small systems (single-trajectory MD, N <= kSmallNeighborAtoms): the whole list in ONE single-block
+// launch -- structure ids, count pass, both scans, status, fill pass, reverse / pair indices --
+// instead of five kernels and two memsets (each graph node costs 2 - 3 us even when empty).  Same
+// pair test, same order-preserving compaction, therefore the same bits as the multi-kernel path.
+constexpr int kSmallNeighborAtoms = 64;
+
+__global__ void __launch_bounds__(1024)
+neighbor_small_kernel(const float* __restrict__ pos, const int* __restrict__ offsets, int num_structures,
+                      const float* __restrict__ cells, const uint8_t* __restrict__ pbc, int num_atoms,
+                      float cutoff, int edge_capacity, int* __restrict__ atom_struct,
+                      int* __restrict__ rowptr, int* __restrict__ lowptr, int* __restrict__ col,
+                      int* __restrict__ edge_dst, float4* __restrict__ geo, int* __restrict__ rev,
+                      int* __restrict__ pair, float* __restrict__ pair_dist,
+                      DeviceStatus* __restrict__ status) {
+    __shared__ int struct_s[kSmallNeighborAtoms];
+    __shared__ int row_s[kSmallNeighborAtoms + 1], low_s[kSmallNeighborAtoms + 1];   // degrees, then exclusive prefixes
+    __shared__ int warp_a[32], warp_b[32], warp_m[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned full = 0xffffffffu;
+    __shared__ float x_s[kSmallNeighborAtoms], y_s[kSmallNeighborAtoms], z_s[kSmallNeighborAtoms];
+    if (tid < num_atoms) {   // positions once into shared memory: the pair loops below are latency chains
+        x_s[tid] = __ldg(pos + 3 * tid); y_s[tid] = __ldg(pos + 3 * tid + 1); z_s[tid] = __ldg(pos + 3 * tid + 2);
+    }
+    if (tid < num_atoms) {   // structure of every atom (binary search over offsets)
+        int lo = 0, hi = num_structures;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(offsets + mid) <= tid) lo = mid; else hi = mid;
+        }
+        struct_s[tid] = lo;
+        atom_struct[tid] = lo;
+    }
+    __syncthreads();
+    // pass == 0 counts, pass == 1 fills; a warp owns destination rows warp, warp + 32, ...
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int j = warp; j < num_atoms; j += 32) {
+            const int b = struct_s[j];
+            const int lo = __ldg(offsets + b), hi = __ldg(offsets + b + 1);
+            const float xj = x_s[j], yj = y_s[j], zj = z_s[j];
+            unsigned pmask = 0;
+            const float* cell18 = nullptr;
+            if (pbc != nullptr) {
+                pmask = (pbc[3 * b] ? 1u : 0u) | (pbc[3 * b + 1] ? 2u : 0u) | (pbc[3 * b + 2] ? 4u : 0u);
+                cell18 = cells + 18 * b;
+            }
+            int count = 0, count_low = 0;
+            const int base = pass ? row_s[j] : 0;
+            for (int i0 = lo; i0 < hi; i0 += 32) {
+                const int i = i0 + lane;
+                bool ok = false;
+                float dx = 0.f, dy = 0.f, dz = 0.f, d = 0.f;
+                if (i < hi && i != j) {
+                    dx = __fsub_rn(x_s[i], xj);      // x_src - x_dst
+                    dy = __fsub_rn(y_s[i], yj);
+                    dz = __fsub_rn(z_s[i], zj);
+                    if (pmask) min_image(dx, dy, dz, cell18, pmask);
+                    d = pair_distance(dx, dy, dz);
+                    ok = d <= cutoff;
+                }
+                const unsigned m = __ballot_sync(full, ok);
+                if (pass) {
+                    if (ok) {
+                        const int e = base + count + __popc(m & lt_mask);
+                        const float q = __fadd_rn(d, kUnitEps);
+                        col[e] = i;
+                        edge_dst[e] = j;
+                        geo[e] = make_float4(__fdiv_rn(dx, q), __fdiv_rn(dy, q), __fdiv_rn(dz, q), d);
+                    }
+                } else {
+                    count_low += __popc(__ballot_sync(full, ok && i < j));
+                }
+                count += __popc(m);
+            }
+            if (!pass && lane == 0) { row_s[j] = count; low_s[j] = count_low; }
+        }
+        if (pass) break;
+        __syncthreads();
+        // exclusive scans of the degrees over num_atoms + 1 entries (one per thread), max degree
+        const int n = num_atoms + 1;
+        const int da = (tid < num_atoms) ? row_s[tid] : 0, db = (tid < num_atoms) ? low_s[tid] : 0;
+        int ia = da, ib = db, mx = da;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ta = __shfl_up_sync(full, ia, o), tb = __shfl_up_sync(full, ib, o);
+            if (lane >= o) { ia += ta; ib += tb; }
+            mx = max(mx, __shfl_xor_sync(full, mx, o));
+        }
+        if (lane == 31) { warp_a[warp] = ia; warp_b[warp] = ib; warp_m[warp] = mx; }
+        __syncthreads();
+        if (warp == 0) {
+            int wa = warp_a[lane], wb = warp_b[lane], wm = warp_m[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ta = __shfl_up_sync(full, wa, o), tb = __shfl_up_sync(full, wb, o);
+                if (lane >= o) { wa += ta; wb += tb; }
+                wm = max(wm, __shfl_xor_sync(full, wm, o));
+            }
+            warp_a[lane] = wa; warp_b[lane] = wb; warp_m[lane] = wm;   // inclusive over warps
+        }
+        __syncthreads();
+        const int pa = ia - da + (warp ? warp_a[warp - 1] : 0), pb = ib - db + (warp ? warp_b[warp - 1] : 0);
+        const int num_edges = warp_a[31];
+        __syncthreads();   // everyone has read the degrees before they become prefixes
+        if (tid < n) {
+            row_s[tid] = pa; low_s[tid] = pb;
+            rowptr[tid] = pa; lowptr[tid] = pb;
+        }
+        if (tid == 0) {
+            status->num_edges = num_edges;
+            status->num_pairs = warp_b[31];
+            status->overflow = (num_edges > edge_capacity) ? 1 : 0;
+            if (num_edges > edge_capacity) status->overflow_events += 1;
+            status->max_degree = warp_m[0];
+            status->hint_violation = 0;
+        }
+        __syncthreads();
+        if (num_edges > edge_capacity) return;   // uniform: outputs invalid, the host grows and re-runs
+    }
+    __syncthreads();   // the block's own global writes (col, geo) are visible to all its threads
+    const int num_edges = row_s[num_atoms];
+    for (int e = tid; e < num_edges; e += 1024) {
+        const int i = col[e], j = edge_dst[e];
+        int lo = row_s[i], hi = row_s[i + 1] - 1;
+        while (lo < hi) {  // sources ascending -> lower_bound of j in row i
+            const int mid = (lo + hi) >> 1;
+            if (col[mid] < j) lo = mid + 1; else hi = mid;
+        }
+        rev[e] = lo;
+        int p;
+        if (i < j) {
+            p = low_s[j] + (e - row_s[j]);
+            pair_dist[p] = geo[e].w;
+        } else {
+            p = low_s[i] + (lo - row_s[i]);
+        }
+        pair[e] = p;
+    }
+}
+
 // edge_index [2, cap] int64 in the reference's order: row 0 = src, row 1 = dst, lexicographic.
 // By symmetry the k-th CSR entry (row j, col i) is the k-th lexicographic pair (src=j, dst=i).
 __global__ void export_edges_kernel(const int* __restrict__ col, const int* __restrict__ edge_dst,

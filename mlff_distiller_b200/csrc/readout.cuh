@@ -143,6 +143,127 @@ readout_kernel(const float* __restrict__ s, HeadWeights w, float* __restrict__ e
     }
 }
 
+// Latency variant for small systems (single-trajectory MD): one BLOCK per 4 atoms, every small
+// GEMV of the head split over all 256 threads (output x K-slice, partial sums combined through
+// shared memory), so the dependent chain is <= H/8 FMAs per layer instead of H with one warp per 4
+// atoms (readout_kernel: 43 us for a 3-atom system, measured).  Same math, same outputs.
+template <int H>
+__global__ void __launch_bounds__(256)
+readout_block_kernel(const float* __restrict__ s, HeadWeights w, float* __restrict__ eps,
+                     float* __restrict__ sbar, int num_atoms, const DeviceStatus* __restrict__ status) {
+    constexpr int H2 = H / 2, H4 = H / 4, AT = 4, T = 256;
+    if (status->overflow) return;
+    __shared__ float s_sh[AT][H];
+    __shared__ float y1_sh[AT][H2];
+    __shared__ float h1_sh[AT][H2];    // activations, then adjoints of y1
+    __shared__ float y2b_sh[AT][H4];   // adjoints of the layer-2 pre-activations
+    __shared__ float part[T * AT];     // [slice][atom][output]
+    const int t = threadIdx.x;
+    const int atom0 = (int)blockIdx.x * AT;
+    if (atom0 >= num_atoms) return;
+    for (int idx = t; idx < AT * H; idx += T) {
+        const int a = idx / H, c = idx - a * H;
+        s_sh[a][c] = (atom0 + a < num_atoms) ? __ldg(s + (size_t)(atom0 + a) * H + c) : 0.f;
+    }
+    __syncthreads();
+    {   // layer 1: H -> H/2
+        constexpr int NSL = (T / H2 < H) ? T / H2 : H, KPER = H / NSL;
+        const int o = t % H2, sl = t / H2;
+        float y[AT] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < (sl < NSL ? KPER : 0); ++kk) {
+            const int k = sl * KPER + kk;
+            const float wv = __ldg(w.A1t + k * H2 + o);
+#pragma unroll
+            for (int a = 0; a < AT; ++a) y[a] = fmaf(s_sh[a][k], wv, y[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < AT; ++a) if (sl < NSL) part[(sl * AT + a) * H2 + o] = y[a];
+        __syncthreads();
+        if (t < AT * H2) {
+            const int a = t / H2, oo = t - a * H2;
+            float yy = __ldg(w.a1 + oo);
+#pragma unroll
+            for (int q = 0; q < NSL; ++q) yy += part[(q * AT + a) * H2 + oo];
+            y1_sh[a][oo] = yy;
+            h1_sh[a][oo] = siluf_(yy);
+        }
+        __syncthreads();
+    }
+    {   // layer 2: H/2 -> H/4, layer 3: H/4 -> 1
+        constexpr int NSL = (T / H4 < H2) ? T / H4 : H2, KPER = H2 / NSL;
+        const int o = t % H4, sl = t / H4;
+        float y[AT] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < (sl < NSL ? KPER : 0); ++kk) {
+            const int k = sl * KPER + kk;
+            const float wv = __ldg(w.A2t + k * H4 + o);
+#pragma unroll
+            for (int a = 0; a < AT; ++a) y[a] = fmaf(h1_sh[a][k], wv, y[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < AT; ++a) if (sl < NSL) part[(sl * AT + a) * H4 + o] = y[a];
+        __syncthreads();
+        if (t < AT * H4) {   // H4 consecutive threads of one warp per atom
+            const int a = t / H4, oo = t - a * H4;
+            float yy = __ldg(w.a2 + oo);
+#pragma unroll
+            for (int q = 0; q < NSL; ++q) yy += part[(q * AT + a) * H4 + oo];
+            const float a3 = __ldg(w.A3 + oo);
+            y2b_sh[a][oo] = a3 * silu_gradf_(yy);
+            const float e = group_sum<H4>(siluf_(yy) * a3);
+            if (oo == 0 && atom0 + a < num_atoms) eps[atom0 + a] = e + __ldg(w.a3);
+        }
+        __syncthreads();
+    }
+    if (sbar == nullptr) return;
+    {   // y1_bar = (A2^T y2_bar) * SiLU'(y1)
+        constexpr int NSL = (T / H2 < H4) ? T / H2 : H4, OPER = H4 / NSL;
+        const int k = t % H2, sl = t / H2;
+        float hb[AT] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int oo = 0; oo < (sl < NSL ? OPER : 0); ++oo) {
+            const int o = sl * OPER + oo;
+            const float wv = __ldg(w.A2 + o * H2 + k);
+#pragma unroll
+            for (int a = 0; a < AT; ++a) hb[a] = fmaf(y2b_sh[a][o], wv, hb[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < AT; ++a) if (sl < NSL) part[(sl * AT + a) * H2 + k] = hb[a];
+        __syncthreads();
+        if (t < AT * H2) {
+            const int a = t / H2, kk = t - a * H2;
+            float v = 0.f;
+#pragma unroll
+            for (int q = 0; q < NSL; ++q) v += part[(q * AT + a) * H2 + kk];
+            h1_sh[a][kk] = v * silu_gradf_(y1_sh[a][kk]);
+        }
+        __syncthreads();
+    }
+    {   // s_bar = A1^T y1_bar
+        constexpr int NSL = (T / H < H2) ? T / H : H2, KPER = H2 / NSL;
+        const int c = t % H, sl = t / H;
+        float sb[AT] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < (sl < NSL ? KPER : 0); ++kk) {
+            const int k = sl * KPER + kk;
+            const float wv = __ldg(w.A1 + k * H + c);
+#pragma unroll
+            for (int a = 0; a < AT; ++a) sb[a] = fmaf(h1_sh[a][k], wv, sb[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < AT; ++a) if (sl < NSL) part[(sl * AT + a) * H + c] = sb[a];
+        __syncthreads();
+        for (int idx = t; idx < AT * H; idx += T) {
+            const int a = idx / H, cc = idx - a * H;
+            float v = 0.f;
+#pragma unroll
+            for (int q = 0; q < NSL; ++q) v += part[(q * AT + a) * H + cc];
+            if (atom0 + a < num_atoms) sbar[(size_t)(atom0 + a) * H + cc] = v;
+        }
+    }
+}
+
 // Tiled variant of readout_kernel for H = 128: 64 atoms per block, the four small GEMMs (head
 // forward H -> H/2 -> H/4, reverse H/4 -> H/2 -> H) on the register-tiled FFMA block of
 // tile_gemm.cuh with weights staged in shared memory, so every weight fetched feeds 4 x RN FMAs

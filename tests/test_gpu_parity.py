@@ -556,3 +556,79 @@ def test_single_pass_tensor_core_modes_within_stated_bounds(variant_name, mode):
     assert worst_e <= e_tol and worst_f <= f_tol, (worst_e, worst_f)
     # and they really are a different arithmetic: coarser than the FP32-equivalent default
     assert worst_e > E_TOL or worst_f > F_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# small-system latency path (single-trajectory MD) vs the throughput path
+# ---------------------------------------------------------------------------------------------
+def _with_env(env, variant="original", **kw):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        bundle = _model(variant, **kw)
+        bundle[0].engine()   # the context reads its tuning variables when it is created
+        return bundle
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_small_system_kernels_match_throughput_kernels_and_golden():
+    """N <= 2048 atoms takes the latency path (one-launch neighbour list for N <= 64, all layers'
+    filter tables in one launch, many-block FFMA update block, block-per-4-atoms read-out);
+    MLFFD_SMALL_ROWS=0 forces the throughput kernels (tcgen05 update block, warp read-out,
+    multi-kernel neighbour list).  Both must meet the FP32 bounds on every golden case, produce the
+    same edges bit for bit, and agree with each other far inside the tolerance."""
+    small, _, _ = _model("original", precision="tc")
+    big, _, _ = _with_env({"MLFFD_SMALL_ROWS": "0", "MLFFD_FILTER_BATCH": "0"}, precision="tc")
+    gold = load_golden("original")
+    for case in golden_cases(gold):
+        z, pos, off = gold[f"{case}_numbers"], gold[f"{case}_positions"], gold[f"{case}_offsets"]
+        e_s, f_s = _run(small, z, pos, off)
+        edges_s = small.engine().export_edges().cpu().numpy()
+        e_b, f_b = _run(big, z, pos, off)
+        edges_b = big.engine().export_edges().cpu().numpy()
+        assert np.array_equal(edges_s, edges_b), case
+        natoms = np.diff(off)
+        for e, f in ((e_s, f_s), (e_b, f_b)):
+            assert np.max(np.abs(e - gold[f"{case}_energy64"]) / natoms) <= E_TOL, case
+            if not case.endswith("_exact"):
+                ref_noise = float(np.max(np.abs(gold[f"{case}_forces32"] - gold[f"{case}_forces64"])))
+                assert np.max(np.abs(f - gold[f"{case}_forces64"])) <= max(F_TOL, 2 * ref_noise), case
+        assert np.max(np.abs(e_s - e_b) / natoms) <= 5e-6, case   # single atom: 2.9e-6 (split-FP16 rounding of the tensor-core path)
+        if not case.endswith("_exact"):
+            assert np.max(np.abs(f_s - f_b)) <= 4e-5, case
+
+
+def test_small_neighbor_kernel_periodic_and_batched_bit_exact():
+    """The one-launch neighbour kernel (N <= 64) against the multi-kernel sweep: periodic cell and
+    a batch of tiny structures, every index array identical."""
+    from mlff_distiller_b200 import synthetic
+    from mlff_distiller_b200.student_model import StudentForceField
+    small, _, _ = _model("ultra_tiny")
+    sweep, _, _ = _with_env({"MLFFD_NEIGHBOR": "sweep"}, "ultra_tiny")
+    rng = np.random.default_rng(5)
+    structs = synthetic.druglike_batch(3, first=40, n=16)
+    z, pos, off = synthetic.concatenate(structs)
+    cell = np.array([[11.0, 0.0, 0.0], [1.5, 10.5, 0.0], [0.5, -1.0, 12.0]])
+    cases = [(z, pos.astype(np.float32), off, None, None),
+             (z[:40], (pos[:40] + rng.normal(0, 0.2, (40, 3))).astype(np.float32), np.array([0, 40]), cell[None], np.array([[True, True, False]]))]
+    for zc, pc, oc, cells, pbc in cases:
+        out = []
+        for model in (small, sweep):
+            model.pbc_mode = "minimum_image"
+            p_d = torch.from_numpy(pc).cuda()
+            o_d = torch.from_numpy(np.asarray(oc, dtype=np.int32)).cuda()
+            c_d = b_d = None
+            if cells is not None:
+                c_d, b_d = StudentForceField.pack_cells(torch.from_numpy(cells), torch.from_numpy(pbc), len(oc) - 1, "cuda:0")
+            eng = model.engine()
+            eng.ensure(len(zc), len(oc) - 1)
+            eng.neighbor_list_async(p_d, o_d, len(oc) - 1, c_d, b_d)
+            out.append({k: eng.debug_buffer(k).cpu().numpy() for k in ("rowptr", "col", "rev", "pair", "edge_dst", "geo", "pair_dist")})
+        assert out[0]["col"].size > 0
+        for k in out[0]:
+            assert np.array_equal(out[0][k], out[1][k]), k
