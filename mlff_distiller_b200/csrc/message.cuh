@@ -291,7 +291,7 @@ message_backward_pairs_kernel(const int* __restrict__ rowptr, const int* __restr
                 if (upper) {
                     r = __ldg(rev + e);
                     const float4 g = __ldg(geo + e);    // unit vector of (j -> i)
-                    const float4 gr = __ldg(geo + r);   // unit vector of (i -> j)
+                    const float4 gr = make_float4(-g.x, -g.y, -g.z, g.w);   // unit vector of (i -> j) = exact negation of (j -> i)
                     const float4 fc = ldg4(filt + prow + 2 * H);
                     const float4 dfa = ldg4(dfilt + prow);
                     const float4 dfc = ldg4(dfilt + prow + 2 * H);
