@@ -201,7 +201,7 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * kAccUnscale);
-                op.store(c, q * 32 + lane, row0 + cs * 32, num_rows, r, prev);
+                op.template store<32>(c, q * 32 + lane, row0 + cs * 32, num_rows, r, prev);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) prev[j] = r[j];
             }
@@ -219,12 +219,12 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
 // Same Ops, latency-optimised for a few hundred rows (single-trajectory MD: BASELINE configs C1 /
 // C3).  The tensor-core kernel above handles a 128-row tile per CTA and streams every 64 KB weight
 // image through one SM: with 3 - 300 rows that is one to three CTAs each walking a serial
-// load -> MMA -> epilogue chain (13 - 20 us per launch, measured).  Here a block owns 32 rows x 32
+// load -> MMA -> epilogue chain (13 - 20 us per launch, measured).  Here a block owns 16 rows x 32
 // output channels (of every 128-channel chunk), its 8 warps split K, and the weight matrix is read
-// by (rows / 32) x 4 blocks in parallel straight from L2 in the [in][out] layout (coalesced over
+// by (rows / 16) x 4 blocks in parallel straight from L2 in the [in][out] layout (coalesced over
 // channels), so one launch is a few microseconds.  FP32 FFMA: same accuracy class as the split
 // tensor-core products.
-constexpr int kSkinnyRows = 32, kSkinnyThreads = 256;
+constexpr int kSkinnyRows = 16, kSkinnyThreads = 256;   // 16 rows x 32 channels per block, 2 rows per epilogue warp
 template <class Op>
 constexpr size_t ffma_rows_smem_bytes() {
     return sizeof(float) * (size_t)(kSkinnyRows * (Op::KS * 128 + 4) + 8 * kSkinnyRows * 32);
@@ -236,41 +236,43 @@ __global__ void __launch_bounds__(kSkinnyThreads)
 ffma_rows_kernel(Op op, int num_rows, const float* __restrict__ wt, int ld,
                  const DeviceStatus* __restrict__ status) {
     constexpr int KS = Op::KS, NC = Op::NC, K = KS * 128, XS = K + 4, KW = K / 8;
+    constexpr int TR = kSkinnyRows, WR = TR / 8;   // rows per tile, rows per epilogue warp
     if (status != nullptr && status->overflow) return;
     extern __shared__ __align__(16) float skinny_smem[];
-    float* x_s = skinny_smem;                      // [32 rows][XS]
-    float* red = skinny_smem + kSkinnyRows * XS;   // [8 warps][32 rows][32 channels]
+    float* x_s = skinny_smem;             // [TR rows][XS]
+    float* red = skinny_smem + TR * XS;   // [8 warps][TR rows][32 channels]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row0 = (int)blockIdx.x * kSkinnyRows, cg = (int)blockIdx.y;
+    const int row0 = (int)blockIdx.x * TR, cg = (int)blockIdx.y;
     if (row0 >= num_rows) return;
-    // every weight this thread needs (<= 48 values), requested before anything else so the L2
+    // every weight this thread needs for the first chunk, requested before anything else so the L2
     // latency overlaps the produce phase: the kernel is a latency chain, not a throughput problem
+    // (ncu: 2 warps per scheduler, ~7 cycles between issues, 5 % of the SM's throughput)
     const int kbeg = warp * KW;
     const float* wp = wt + (size_t)kbeg * ld + cg * 32 + lane;
     float wcur[KW], wnxt[KW];
 #pragma unroll
     for (int k = 0; k < KW; ++k) { wcur[k] = __ldg(wp + (size_t)k * ld); wnxt[k] = 0.f; }
-    const int rows_here = min(kSkinnyRows, num_rows - row0);
+    const int rows_here = min(TR, num_rows - row0);
     for (int idx = tid; idx < rows_here * (K / 4); idx += kSkinnyThreads) {
         const int r = idx / (K / 4), k4 = idx - r * (K / 4);
         const int ks = k4 >> 5, k0 = (k4 & 31) * 4;
         *reinterpret_cast<float4*>(x_s + r * XS + ks * 128 + k0) = op.produce(row0 + r, num_rows, ks, k0);
     }
     __syncthreads();
-    uint32_t prev[32];
+    uint32_t prev[WR];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) prev[j] = 0u;
+    for (int j = 0; j < WR; ++j) prev[j] = 0u;
 #pragma unroll 1   // straight-line code that runs once is instruction-fetch bound: keep the body small
     for (int c = 0; c < NC; ++c) {
         if (c + 1 < NC) {   // next chunk's weights travel while this chunk is computed
 #pragma unroll
             for (int k = 0; k < KW; ++k) wnxt[k] = __ldg(wp + (size_t)k * ld + (c + 1) * 128);
         }
-        float acc[32];
+        float acc[TR];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+        for (int j = 0; j < TR; ++j) acc[j] = 0.f;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {   // rows in groups of 8; groups beyond the tile's rows are skipped
+        for (int g = 0; g < TR / 8; ++g) {   // rows in groups of 8; groups beyond the tile's rows are skipped
             if (g * 8 < rows_here) {
 #pragma unroll
                 for (int k = 0; k < KW; k += 4) {
@@ -283,26 +285,24 @@ ffma_rows_kernel(Op op, int num_rows, const float* __restrict__ wt, int ld,
                 }
             }
         }
-        // combine the 8 K-slices and run the op's epilogue: warp w owns rows 4w .. 4w+3 of the tile
+        // combine the 8 K-slices and run the op's epilogue: warp w owns rows WR w .. WR w + WR - 1
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < rows_here) red[(warp * 32 + j) * 32 + lane] = acc[j];
+        for (int j = 0; j < TR; ++j)
+            if (j < rows_here) red[(warp * TR + j) * 32 + lane] = acc[j];
         __syncthreads();
-        if (warp * 4 < rows_here) {
-            uint32_t r[32];
+        if (warp * WR < rows_here) {
+            uint32_t r[WR];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float sum = 0.f;
-                if ((j >> 2) == warp) {
-                    sum = red[j * 32 + lane];
+            for (int jj = 0; jj < WR; ++jj) {
+                const int j = warp * WR + jj;
+                float sum = red[j * 32 + lane];
 #pragma unroll
-                    for (int w = 1; w < 8; ++w) sum += red[(w * 32 + j) * 32 + lane];
-                }
-                r[j] = __float_as_uint(sum);
+                for (int w = 1; w < 8; ++w) sum += red[(w * TR + j) * 32 + lane];
+                r[jj] = __float_as_uint(sum);
             }
-            op.store(c, cg * 32 + lane, row0, min(num_rows, row0 + 4 * warp + 4), r, prev, 4 * warp);
+            op.template store<WR>(c, cg * 32 + lane, row0 + warp * WR, num_rows, r, prev);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) prev[j] = r[j];
+            for (int j = 0; j < WR; ++j) prev[j] = r[j];
         }
         if (c + 1 < NC) __syncthreads();
 #pragma unroll
@@ -327,11 +327,13 @@ struct UpdateFwd1Op {
         return make_float4(sqrtf(vx.x * vx.x + vy.x * vy.x + vz.x * vz.x), sqrtf(vx.y * vx.y + vy.y * vy.y + vz.y * vz.y),
                            sqrtf(vx.z * vx.z + vy.z * vy.z + vz.z * vz.z), sqrtf(vx.w * vx.w + vy.w * vy.w + vz.w * vz.w));
     }
-    __device__ __forceinline__ void store(int, int ch, int row0, int n, const uint32_t (&r)[32], const uint32_t (&)[32], int jlo = 0) const {
+    template <int R>
+    __device__ __forceinline__ void store(int, int ch, int row0, int n, const uint32_t (&r)[R], const uint32_t (&)[R]) const {
+        constexpr int B8 = R < 8 ? R : 8, B4 = R < 4 ? R : 4;   // rows whose loads are issued together
         const float b = __ldg(m1 + ch);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (row0 + j < n && j >= jlo) y1[(size_t)(row0 + j) * 128 + ch] = __uint_as_float(r[j]) + b;
+        for (int j = 0; j < R; ++j)
+            if (row0 + j < n) y1[(size_t)(row0 + j) * 128 + ch] = __uint_as_float(r[j]) + b;
     }
 };
 
@@ -347,20 +349,22 @@ struct UpdateFwd2Op {
         const float4 y = ldg4(y1 + (size_t)row * 128 + k0);
         return make_float4(siluf_(y.x), siluf_(y.y), siluf_(y.z), siluf_(y.w));
     }
-    __device__ __forceinline__ void store(int c, int ch, int row0, int n, const uint32_t (&r)[32], const uint32_t (&prev)[32], int jlo = 0) const {
+    template <int R>
+    __device__ __forceinline__ void store(int c, int ch, int row0, int n, const uint32_t (&r)[R], const uint32_t (&prev)[R]) const {
+        constexpr int B8 = R < 8 ? R : 8, B4 = R < 4 ? R : 4;   // rows whose loads are issued together
         if (c == 0) {
             const float b = __ldg(m2 + ch);
             // loads of a batch of rows are issued together, then the stores: a load placed after a
             // store through another pointer cannot be hoisted by the compiler (possible alias)
 #pragma unroll
-            for (int jb = 0; jb < 32; jb += 8) {
+            for (int jb = 0; jb < R; jb += B8) {
                 float sv[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    sv[j] = (row0 + jb + j < n && jb + j >= jlo) ? __ldg(s_msg + (size_t)(row0 + jb + j) * 128 + ch) : 0.f;
+                for (int j = 0; j < B8; ++j)
+                    sv[j] = (row0 + jb + j < n) ? __ldg(s_msg + (size_t)(row0 + jb + j) * 128 + ch) : 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (row0 + jb + j < n && jb + j >= jlo)
+                for (int j = 0; j < B8; ++j)
+                    if (row0 + jb + j < n)
                         s_out[(size_t)(row0 + jb + j) * 128 + ch] = sv[j] + __uint_as_float(r[jb + j]) + b;
             }
         } else if (c == 2) {   // prev = g1 accumulators (chunk 1), r = g2
@@ -369,17 +373,17 @@ struct UpdateFwd2Op {
 #pragma unroll
             for (int k = 0; k < 9; ++k) u[k] = __ldg(U + k);
 #pragma unroll
-            for (int jb = 0; jb < 32; jb += 8) {
+            for (int jb = 0; jb < R; jb += B8) {
                 float vx[8], vy[8], vz[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const bool ok = row0 + jb + j < n && jb + j >= jlo;
+                for (int j = 0; j < B8; ++j) {
+                    const bool ok = row0 + jb + j < n;
                     const float* vp = v_msg + (size_t)(row0 + jb + j) * 384 + ch;
                     vx[j] = ok ? __ldg(vp) : 0.f; vy[j] = ok ? __ldg(vp + 128) : 0.f; vz[j] = ok ? __ldg(vp + 256) : 0.f;
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (row0 + jb + j < n && jb + j >= jlo) {
+                for (int j = 0; j < B8; ++j)
+                    if (row0 + jb + j < n) {
                         const size_t row = (size_t)(row0 + jb + j);
                         const float g1 = __uint_as_float(prev[jb + j]) + b1, g2 = __uint_as_float(r[jb + j]) + b2;
                         gates[row * 256 + ch] = g1;
@@ -420,15 +424,17 @@ struct UpdateBwd1Op {
         return make_float4(mix(bx.x, by.x, bz.x, vx.x, vy.x, vz.x), mix(bx.y, by.y, bz.y, vx.y, vy.y, vz.y),
                            mix(bx.z, by.z, bz.z, vx.z, vy.z, vz.z), mix(bx.w, by.w, bz.w, vx.w, vy.w, vz.w));
     }
-    __device__ __forceinline__ void store(int, int ch, int row0, int n, const uint32_t (&r)[32], const uint32_t (&)[32], int jlo = 0) const {
+    template <int R>
+    __device__ __forceinline__ void store(int, int ch, int row0, int n, const uint32_t (&r)[R], const uint32_t (&)[R]) const {
+        constexpr int B8 = R < 8 ? R : 8, B4 = R < 4 ? R : 4;   // rows whose loads are issued together
 #pragma unroll
-        for (int jb = 0; jb < 32; jb += 8) {
+        for (int jb = 0; jb < R; jb += B8) {
             float yv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) yv[j] = (row0 + jb + j < n && jb + j >= jlo) ? y1[(size_t)(row0 + jb + j) * 128 + ch] : 0.f;
+            for (int j = 0; j < B8; ++j) yv[j] = (row0 + jb + j < n) ? y1[(size_t)(row0 + jb + j) * 128 + ch] : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (row0 + jb + j < n && jb + j >= jlo)
+            for (int j = 0; j < B8; ++j)
+                if (row0 + jb + j < n)
                     y1[(size_t)(row0 + jb + j) * 128 + ch] = __uint_as_float(r[jb + j]) * silu_gradf_(yv[j]);
         }
     }
@@ -444,16 +450,18 @@ struct UpdateBwd2Op {
         if (row >= n) return make4(0.f);
         return ldg4(ybar + (size_t)row * 128 + k0);
     }
-    __device__ __forceinline__ void store(int c, int ch, int row0, int n, const uint32_t (&r)[32], const uint32_t (&)[32], int jlo = 0) const {
+    template <int R>
+    __device__ __forceinline__ void store(int c, int ch, int row0, int n, const uint32_t (&r)[R], const uint32_t (&)[R]) const {
+        constexpr int B8 = R < 8 ? R : 8, B4 = R < 4 ? R : 4;   // rows whose loads are issued together
         if (c == 0) {
 #pragma unroll
-            for (int jb = 0; jb < 32; jb += 8) {
+            for (int jb = 0; jb < R; jb += B8) {
                 float sv[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) sv[j] = (row0 + jb + j < n && jb + j >= jlo) ? sbar[(size_t)(row0 + jb + j) * 128 + ch] : 0.f;
+                for (int j = 0; j < B8; ++j) sv[j] = (row0 + jb + j < n) ? sbar[(size_t)(row0 + jb + j) * 128 + ch] : 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (row0 + jb + j < n && jb + j >= jlo) sbar[(size_t)(row0 + jb + j) * 128 + ch] = sv[j] + __uint_as_float(r[jb + j]);
+                for (int j = 0; j < B8; ++j)
+                    if (row0 + jb + j < n) sbar[(size_t)(row0 + jb + j) * 128 + ch] = sv[j] + __uint_as_float(r[jb + j]);
             }
             return;
         }
@@ -461,11 +469,11 @@ struct UpdateBwd2Op {
 #pragma unroll
         for (int k = 0; k < 9; ++k) u[k] = __ldg(U + k);
 #pragma unroll
-        for (int jb = 0; jb < 32; jb += 4) {
+        for (int jb = 0; jb < R; jb += B4) {
             float vx[4], vy[4], vz[4], bx[4], by[4], bz[4], g1[4], g2[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool ok = row0 + jb + j < n && jb + j >= jlo;
+            for (int j = 0; j < B4; ++j) {
+                const bool ok = row0 + jb + j < n;
                 const size_t row = (size_t)(row0 + jb + j);
                 const float* vp = v_msg + row * 384 + ch;
                 vx[j] = ok ? __ldg(vp) : 0.f; vy[j] = ok ? __ldg(vp + 128) : 0.f; vz[j] = ok ? __ldg(vp + 256) : 0.f;
@@ -477,8 +485,8 @@ struct UpdateBwd2Op {
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (row0 + jb + j < n && jb + j >= jlo) {
+            for (int j = 0; j < B4; ++j)
+                if (row0 + jb + j < n) {
                     const float nrm = sqrtf(vx[j] * vx[j] + vy[j] * vy[j] + vz[j] * vz[j]);
                     const float sc = (nrm > 0.f) ? __uint_as_float(r[jb + j]) / nrm : 0.f;
                     float ox = sc * vx[j], oy = sc * vy[j], oz = sc * vz[j];
