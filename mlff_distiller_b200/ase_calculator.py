@@ -82,7 +82,7 @@ class StudentForceFieldCalculator(_AseCalculator):
                  use_compile: bool = False, use_fp16: bool = False, use_jit: bool = False,
                  jit_path: Optional[Union[str, Path]] = None, use_torch_cluster: bool = True,
                  use_analytical_forces: bool = False, *, precision: str = "tc",
-                 pbc_mode: str = "ignore", **kwargs):
+                 pbc_mode: str = "ignore", use_graph: bool = True, **kwargs):
         super().__init__(**kwargs)
         self.checkpoint_path = Path(checkpoint_path)
         self.device = torch.device(device)
@@ -98,6 +98,7 @@ class StudentForceFieldCalculator(_AseCalculator):
         self.use_analytical_forces = use_analytical_forces
         self.precision = precision
         self.pbc_mode = pbc_mode
+        self.use_graph = use_graph   # replay single-structure steps as one CUDA graph (second call on)
         self.max_atoms_per_call = 262144   # micro-batch bound of the batched interface (~30 GB workspace)
         self.implemented_properties = ["energy", "forces"]
         if self.enable_stress:
@@ -112,9 +113,7 @@ class StudentForceFieldCalculator(_AseCalculator):
         self._n_calls = 0
         self._total_time = 0.0
         self._call_times: List[float] = []
-        self._numbers_cache = None  # (host numbers copy, device int32 tensor)
-        self._pin_pos = None
-        self._pin_out = None
+        self._numbers_cache = None  # per-system device / pinned buffers and captured graphs of the single path
         logger.info("Initialized StudentForceFieldCalculator: device=%s, precision=%s, pbc_mode=%s",
                     self.device, precision, pbc_mode)
 
@@ -219,29 +218,84 @@ class StudentForceFieldCalculator(_AseCalculator):
                         f"({2 * self.model.cutoff:.2f} Å); axis {k} has {height:.3f} Å")
 
     def _evaluate_single(self, positions, numbers, cell, pbc, want_virial: bool = False):
+        """One structure.  The first call for a system runs eagerly (sizes the workspace, grows it
+        on overflow); from the second call on the whole step -- pinned H2D of the positions, the
+        ~30 kernels, status words and D2H of the results -- is ONE CUDA-graph replay: launching
+        the kernels one by one from Python costs more host time (~110 us) than a small system
+        needs on the device (92 us for H2O).  ``use_graph=False`` keeps every call eager."""
         dev = self.device
         n = len(numbers)
-        if (self._numbers_cache is None or len(self._numbers_cache[0]) != n
-                or not np.array_equal(self._numbers_cache[0], numbers)):
-            z_d = torch.from_numpy(np.ascontiguousarray(numbers, dtype=np.int32)).to(dev)
-            off_d = torch.tensor([0, n], dtype=torch.int32, device=dev)
-            self._numbers_cache = (np.array(numbers), z_d, off_d)
-            self._pin_pos = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-            self._pin_out = torch.empty(3 * n + 10, dtype=torch.float32).pin_memory()
-        _, z_d, off_d = self._numbers_cache
-        self._pin_pos.copy_(torch.from_numpy(np.ascontiguousarray(positions, dtype=np.float64)))
-        pos_d = self._pin_pos.to(dev, non_blocking=True)
-        cells_d = pbc_d = None
-        if self.pbc_mode == "minimum_image" and pbc.any():
-            cells_d, pbc_d = StudentForceField.pack_cells(torch.from_numpy(cell), torch.from_numpy(pbc), 1, dev)
-        e_d, f_d = self.model.energy_and_forces_packed(z_d, pos_d, off_d, 1, cells_d, pbc_d)
-        parts = [e_d.reshape(1), f_d.reshape(-1)]
-        if want_virial:
-            parts.append(self.model.virial_of_last_call(off_d, 1).reshape(-1))
-        out_d = torch.cat(parts)
-        self._pin_out[:out_d.numel()].copy_(out_d, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        out = self._pin_out.numpy()
+        periodic = self.pbc_mode == "minimum_image" and bool(pbc.any())
+        cell_key = np.asarray(cell, dtype=np.float64).tobytes() + np.asarray(pbc, dtype=bool).tobytes() if periodic else b""
+        c = self._numbers_cache
+        if (c is None or len(c["numbers"]) != n or not np.array_equal(c["numbers"], numbers)
+                or c["cell_key"] != cell_key):
+            cells_d = pbc_d = None
+            if periodic:
+                cells_d, pbc_d = StudentForceField.pack_cells(torch.from_numpy(np.asarray(cell)), torch.from_numpy(np.asarray(pbc)), 1, dev)
+            c = self._numbers_cache = {
+                "numbers": np.array(numbers), "cell_key": cell_key,
+                "z_d": torch.from_numpy(np.ascontiguousarray(numbers, dtype=np.int32)).to(dev),
+                "off_d": torch.tensor([0, n], dtype=torch.int32, device=dev),
+                "pos_d": torch.empty((n, 3), dtype=torch.float32, device=dev),
+                "e_d": torch.empty(1, dtype=torch.float32, device=dev),
+                "f_d": torch.empty((n, 3), dtype=torch.float32, device=dev),
+                "w_d": torch.empty((1, 3, 3), dtype=torch.float32, device=dev),
+                "cells_d": cells_d, "pbc_d": pbc_d,
+                "pin_pos": torch.empty((n, 3), dtype=torch.float32).pin_memory(),
+                "pin_out": torch.empty(3 * n + 10, dtype=torch.float32).pin_memory(),
+                "pin_status": torch.zeros(6, dtype=torch.int32).pin_memory(),
+                "graphs": {}, "warm": False, "graph_key": None,
+            }
+            c["status_np"], c["out_np"], c["pin_pos_np"] = c["pin_status"].numpy(), c["pin_out"].numpy(), c["pin_pos"].numpy()
+        c["pin_pos_np"][...] = positions   # FP64 -> FP32 conversion straight into the pinned buffer
+        eng = self.model.engine()
+        stream = torch.cuda.current_stream(dev)
+
+        def enqueue_step():
+            c["pos_d"].copy_(c["pin_pos"], non_blocking=True)
+            eng.energy_forces_async(c["z_d"], c["pos_d"], c["off_d"], 1, c["e_d"], c["f_d"], c["cells_d"], c["pbc_d"])
+            if want_virial:
+                eng.virial_async(c["off_d"], 1, c["w_d"])
+            eng.status_async(c["pin_status"])
+            c["pin_out"][0:1].copy_(c["e_d"], non_blocking=True)
+            c["pin_out"][1:3 * n + 1].copy_(c["f_d"].view(-1), non_blocking=True)
+            if want_virial:
+                c["pin_out"][3 * n + 1:3 * n + 10].copy_(c["w_d"].view(-1), non_blocking=True)
+
+        graph_key = (id(eng), eng.cap_atoms, eng.cap_edges, eng.cap_structs)
+        if c["graph_key"] != graph_key:       # workspace (re)allocated: captured pointers are stale
+            c["graphs"], c["graph_key"] = {}, graph_key
+        done = False
+        if self.use_graph and c["warm"] and c["graph_key"] == graph_key:
+            g = c["graphs"].get(want_virial)
+            if g is None:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(stream)
+                with torch.cuda.stream(side):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        enqueue_step()
+                stream.wait_stream(side)
+                c["graphs"][want_virial] = g
+            g.replay()
+            stream.synchronize()
+            done = not (c["status_np"][2] or c["status_np"][5])   # overflow: fall through to the eager path
+        if not done:
+            eng.set_structure_hint(0)
+            eng.ensure(n, 1, self.model._edges_per_atom)
+            for _ in range(3):
+                enqueue_step()
+                stream.synchronize()
+                if not (c["status_np"][2] or c["status_np"][5]):
+                    break
+                num_edges = int(c["status_np"][0])
+                eng.reserve(n, int(num_edges * 1.25) + 64, 1)
+                self.model._edges_per_atom = max(self.model._edges_per_atom, int(num_edges * 1.25 / max(n, 1)) + 1)
+            else:
+                raise RuntimeError("edge workspace overflow persisted after growing")
+            c["warm"] = True
+        out = c["out_np"]
         virial = out[3 * n + 1:3 * n + 10].reshape(3, 3).astype(np.float64) if want_virial else None
         return float(out[0]), out[1:3 * n + 1].reshape(n, 3).copy(), virial
 

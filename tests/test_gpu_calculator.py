@@ -261,3 +261,26 @@ def test_use_jit_reads_the_torchscript_archive_and_wrapper_differentiates(calc, 
     forces = -torch.autograd.grad(energy, pos)[0]
     assert abs(float(energy) - b.get_potential_energy()) < 1e-5
     assert np.abs(forces.cpu().numpy() - b.get_forces()).max() < 1e-6
+
+
+def test_single_structure_graph_replay_matches_eager(calc):
+    """From the second call on a single-structure step is one CUDA-graph replay; it must return
+    exactly what the eager launch sequence returns, follow changing positions, switch systems,
+    and survive a workspace regrowth caused by another (larger) request in between."""
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+    eager = StudentForceFieldCalculator(GOLDEN / "weights_original.npz", device="cuda", use_graph=False)
+    rng = np.random.default_rng(3)
+    mol = synthetic.druglike_batch(1, first=11)[0]
+    base = mol.get_positions().copy()
+    for step in range(5):
+        mol.set_positions(base + rng.normal(0, 0.02, base.shape))
+        a, b = mol.copy(), mol.copy()
+        a.calc, b.calc = calc, eager
+        assert a.get_potential_energy() == b.get_potential_energy(), step
+        assert np.array_equal(a.get_forces(), b.get_forces()), step
+        if step == 2:   # another system and a big batch in between: new buffers, regrown workspace
+            w = synthetic.water()
+            w.calc = calc
+            w.get_forces()
+            calc.calculate_batch(synthetic.druglike_batch(64, first=500))
+    assert calc._numbers_cache["graphs"], "the replay path was never taken"

@@ -47,7 +47,9 @@ def nve(calc, atoms, steps, temperature, seed, dt_fs=0.5):
         calc.calculate(work, ["energy", "forces"])
         return calc.results["energy"], calc.results["forces"]
 
-    force_fn(atoms.get_positions())  # warm-up / workspace sizing
+    for _ in range(3):   # warm-up: workspace sizing (eager), graph capture, first replay
+        force_fn(atoms.get_positions() + 1e-6)
+        force_fn(atoms.get_positions())
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     out = md.velocity_verlet(force_fn, atoms.get_positions(), v0, masses, steps, dt_fs)
