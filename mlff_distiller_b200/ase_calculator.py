@@ -371,6 +371,15 @@ class StudentForceFieldCalculator(_AseCalculator):
                     e_parts.append(e)
                     f_parts.append(f)
             return np.concatenate(e_parts), np.concatenate(f_parts)
+        if cells is None or pbcs is None or not np.any(pbcs):
+            # open boundaries: one batch through the pipelined interface's slot machinery -- copies on
+            # the copy streams, status words behind the step, ONE host synchronisation
+            try:
+                return next(iter(self.evaluate_stream([(numbers, positions, counts)])))
+            except ValueError:
+                raise
+            except Exception as e:
+                raise RuntimeError(f"Failed to calculate properties for {len(numbers)} atoms: {e}") from e
         dev = self.device
         nb, n = len(counts), len(numbers)
         st = self._batch_staging(n, nb)
