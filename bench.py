@@ -15,6 +15,8 @@ Rank 0 prints ONE JSON line.
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -416,10 +418,25 @@ def run_b200(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # stdout carries exactly ONE JSON line: anything a library prints while the job runs (NCCL's version
+    # banner on the first collective, for one) is sent to stderr by pointing fd 1 at fd 2 until the end
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    lines = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+    if lines:
+        print(lines[-1], flush=True)
 
 
 if __name__ == "__main__":

@@ -126,3 +126,41 @@ def test_use_jit_flag_errors_like_the_reference(tmp_path):
         StudentForceFieldCalculator(tmp_path / "x.pt", device="cuda", use_jit=True)
     with pytest.raises(FileNotFoundError, match="TorchScript model not found"):
         StudentForceFieldCalculator(tmp_path / "x.pt", device="cuda", use_jit=True, jit_path=tmp_path / "missing_jit.pt")
+
+
+def test_validate_arrays_messages_without_gpu():
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+
+    class Fake:
+        max_z = 100
+
+    calc = object.__new__(StudentForceFieldCalculator)
+    calc.model = Fake()
+    z, pos = np.array([1, 8, 1, 6]), np.zeros((4, 3))
+    calc._validate_arrays(z, pos, np.array([3, 1]))
+    with pytest.raises(ValueError, match="empty structure"):
+        calc._validate_arrays(z, pos, np.array([4, 0]))
+    with pytest.raises(ValueError, match="disagree"):
+        calc._validate_arrays(z, pos, np.array([2, 1]))
+    with pytest.raises(ValueError, match="Invalid atomic numbers"):
+        calc._validate_arrays(np.array([1, 8, 1, 101]), pos, np.array([4]))
+    with pytest.raises(ValueError, match="NaN"):
+        calc._validate_arrays(z, np.full((4, 3), np.inf), np.array([4]))
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver parses stdout of bench.py: one JSON line, nothing else (library banners go to stderr)."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    proc = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                          capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [l for l in proc.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "structures_per_second_energy_forces"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"].startswith("C2") and d["higher_is_better"] is True
