@@ -17,7 +17,7 @@ from typing import List, Optional
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libmlffd.so"
 SOURCES = ["mlffd.cu"]
-HEADERS = ["common.cuh", "neighbor.cuh", "cell_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh", "message_pipe.cuh", "message_staged.cuh",
+HEADERS = ["common.cuh", "neighbor.cuh", "cell_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh", "message_pipe.cuh", "message_team.cuh", "message_staged.cuh",
            "update.cuh", "readout.cuh", "md.cuh", "../../include/mlffd.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

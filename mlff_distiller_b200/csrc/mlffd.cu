@@ -24,6 +24,7 @@
 #include "md.cuh"
 #include "message.cuh"
 #include "message_pipe.cuh"
+#include "message_team.cuh"
 #include "message_staged.cuh"
 #include "neighbor.cuh"
 #include "readout.cuh"
@@ -92,6 +93,7 @@ struct mlffd_ctx {
     std::string err;
     float* weights_d = nullptr;
     uint8_t* w2_images_d = nullptr;   // swizzled fp16 hi/lo 64 KB weight images (tensor-core path)
+    int msg_team = 8;               // env MLFFD_MSG_TEAM (4 | 8; 0 = row-per-warp kernels): warps sharing a CSR row in the small-system message kernels (0 / 1 = off)
     int filter_batch = 2;           // env MLFFD_FILTER_BATCH: 1 = all layers' filter tables in one launch, 0 = one launch per layer, 2 = one launch only for small systems
     int small_rows = 2048;          // env MLFFD_SMALL_ROWS: at or below this many atoms the update block runs on ffma_rows_kernel
     int tc_mode = 0;                // kTcSplit | kTcF16 | kTcBF16 (filter_umma.cuh), from cfg.precision
@@ -381,6 +383,9 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     // 1 = every pair once, 2 = pair once + cp.async ring (H = 128); 1 and 2 write per-layer slabs
     const bool bwd_pipe = !staged && ctx->msg_bwd_mode == 2 && H == 128;
     const bool fwd_pipe = !staged && ctx->msg_fwd_mode == 1 && H == 128;
+    // small systems: a team of kTeam warps per CSR row (needs the per-layer adjoint slabs of the pair-once modes)
+    const bool team = !staged && (ctx->msg_team == 4 || ctx->msg_team == 8) && N <= ctx->small_rows && ctx->msg_bwd_mode >= 1;
+    const int team_grid = clamp_grid(ceil_div(N, M::APW), kNumSMs * 16);
     const bool adj_slabs = !staged && ctx->msg_bwd_mode >= 1;
     const int staged_grid = staged ? clamp_grid(n_structs, kNumSMs * (int)std::min<size_t>(8, (227 * 1024) / staged_smem)) : 1;
 
@@ -411,7 +416,15 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
             message_forward_staged_kernel<H, false><<<staged_grid, kStagedThreads, staged_smem, st>>>(
                 offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], ws.v_in[l],
                 ws.s_msg[l], ws.v_msg[l], ctx->status_d);
-        else if (fwd_pipe) {
+        else if (team) {   // small system: a team of warps per CSR row (message_team.cuh)
+#define MSG_FWD_TEAM(LAYER0, TT)                                                                       \
+    message_forward_team_kernel<H, LAYER0, TT><<<team_grid, 32 * TT, 0, st>>>(                         \
+        ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], LAYER0 ? nullptr : ws.v_in[l],     \
+        ws.s_msg[l], ws.v_msg[l], N, status)
+            if (ctx->msg_team == 8) { if (l == 0) MSG_FWD_TEAM(true, 8); else MSG_FWD_TEAM(false, 8); }
+            else                    { if (l == 0) MSG_FWD_TEAM(true, 4); else MSG_FWD_TEAM(false, 4); }
+#undef MSG_FWD_TEAM
+        } else if (fwd_pipe) {
             if constexpr (H == 128) launch_forward_pipe(ctx, l, msg_grid, N, st);
         } else if (l == 0)
             message_forward_kernel<H, true><<<msg_grid, 256, 0, st>>>(
@@ -555,6 +568,14 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
                     offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.filt[l], sb, vb, sb_in, vb_in,
                     ctx->status_d);
             }
+        } else if (team) {
+#define MSG_BWD_TEAM(LAYER0, TT)                                                                          \
+    message_backward_pairs_team_kernel<H, LAYER0, TT><<<team_grid, 32 * TT, 0, st>>>(                     \
+        ws.rowptr, ws.col, ws.pair, ws.rev, ws.geo, ws.filt[l], ws.dfilt[l], ws.s_in[l], ws.v_in[l], sb,  \
+        vb, sb_in, vb_in, ws.edge_adj + (size_t)l * ws.cap_edges, N, status)
+            if (ctx->msg_team == 8) { if (l == 0) MSG_BWD_TEAM(true, 8); else MSG_BWD_TEAM(false, 8); }
+            else                    { if (l == 0) MSG_BWD_TEAM(true, 4); else MSG_BWD_TEAM(false, 4); }
+#undef MSG_BWD_TEAM
         } else if (bwd_pipe) {
             if constexpr (H == 128) launch_backward_pipe(ctx, l, msg_grid, sb, vb, sb_in, vb_in, N, st);
         } else if (ctx->msg_bwd_mode >= 1) {
@@ -729,6 +750,7 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     if (const char* ns = std::getenv("MLFFD_MSG_FWD")) ctx->msg_fwd_mode = !std::strcmp(ns, "rows") ? 0 : 1;
     if (const char* ns = std::getenv("MLFFD_SMALL_ROWS")) ctx->small_rows = std::atoi(ns);
     if (const char* ns = std::getenv("MLFFD_FILTER_BATCH")) ctx->filter_batch = std::atoi(ns);
+    if (const char* ns = std::getenv("MLFFD_MSG_TEAM")) ctx->msg_team = std::atoi(ns);
     if (const char* ns = std::getenv("MLFFD_PIPE_DEPTH_FWD")) ctx->pipe_depth_fwd = std::atoi(ns);
     if (const char* ns = std::getenv("MLFFD_PIPE_DEPTH_BWD")) ctx->pipe_depth_bwd = std::atoi(ns);
     if (const char* nm = std::getenv("MLFFD_NEIGHBOR"))

@@ -329,7 +329,7 @@ struct UpdateFwd1Op {
     }
     template <int R>
     __device__ __forceinline__ void store(int, int ch, int row0, int n, const uint32_t (&r)[R], const uint32_t (&)[R]) const {
-        constexpr int B8 = R < 8 ? R : 8, B4 = R < 4 ? R : 4;   // rows whose loads are issued together
+        [[maybe_unused]] constexpr int B8 = R < 8 ? R : 8, B4 = R < 4 ? R : 4;   // rows whose loads are issued together
         const float b = __ldg(m1 + ch);
 #pragma unroll
         for (int j = 0; j < R; ++j)
@@ -351,7 +351,7 @@ struct UpdateFwd2Op {
     }
     template <int R>
     __device__ __forceinline__ void store(int c, int ch, int row0, int n, const uint32_t (&r)[R], const uint32_t (&prev)[R]) const {
-        constexpr int B8 = R < 8 ? R : 8, B4 = R < 4 ? R : 4;   // rows whose loads are issued together
+        [[maybe_unused]] constexpr int B8 = R < 8 ? R : 8, B4 = R < 4 ? R : 4;   // rows whose loads are issued together
         if (c == 0) {
             const float b = __ldg(m2 + ch);
             // loads of a batch of rows are issued together, then the stores: a load placed after a
@@ -426,7 +426,7 @@ struct UpdateBwd1Op {
     }
     template <int R>
     __device__ __forceinline__ void store(int, int ch, int row0, int n, const uint32_t (&r)[R], const uint32_t (&)[R]) const {
-        constexpr int B8 = R < 8 ? R : 8, B4 = R < 4 ? R : 4;   // rows whose loads are issued together
+        [[maybe_unused]] constexpr int B8 = R < 8 ? R : 8, B4 = R < 4 ? R : 4;   // rows whose loads are issued together
 #pragma unroll
         for (int jb = 0; jb < R; jb += B8) {
             float yv[8];
@@ -452,7 +452,7 @@ struct UpdateBwd2Op {
     }
     template <int R>
     __device__ __forceinline__ void store(int c, int ch, int row0, int n, const uint32_t (&r)[R], const uint32_t (&)[R]) const {
-        constexpr int B8 = R < 8 ? R : 8, B4 = R < 4 ? R : 4;   // rows whose loads are issued together
+        [[maybe_unused]] constexpr int B8 = R < 8 ? R : 8, B4 = R < 4 ? R : 4;   // rows whose loads are issued together
         if (c == 0) {
 #pragma unroll
             for (int jb = 0; jb < R; jb += B8) {

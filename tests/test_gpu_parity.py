@@ -439,6 +439,7 @@ def test_staged_message_kernels_bit_identical(variant_name):
     p_d = torch.from_numpy(pos).to(dev)
     o_d = torch.from_numpy(off.astype(np.int32)).to(dev)
     def run(env, max_atoms):
+        env = {"MLFFD_MSG_TEAM": "0", **env}   # row-per-warp kernels whatever the batch size
         os.environ.update(env)
         try:
             model, state, cfg = _model(variant_name)
@@ -476,6 +477,7 @@ def test_message_kernel_variants_agree(variant_name):
     o_d = torch.from_numpy(off.astype(np.int32)).to(dev)
 
     def run(env):
+        env = {"MLFFD_MSG_TEAM": "0", **env}   # row-per-warp kernels whatever the batch size
         os.environ.update(env)
         try:
             model, state, cfg = _model(variant_name)
@@ -632,3 +634,28 @@ def test_small_neighbor_kernel_periodic_and_batched_bit_exact():
         assert out[0]["col"].size > 0
         for k in out[0]:
             assert np.array_equal(out[0][k], out[1][k]), k
+
+
+@pytest.mark.parametrize("variant_name", ["original", "tiny", "ultra_tiny"])
+def test_team_message_kernels_match_row_per_warp_kernels(variant_name):
+    """Small systems: a team of four warps shares every CSR row (message_team.cuh).  Same arithmetic
+    as the row-per-warp kernels up to the order of the four partial sums; deterministic."""
+    from mlff_distiller_b200 import synthetic
+    structs = (synthetic.druglike_batch(12, first=640, ragged=True) + [synthetic.water(), synthetic.Structure([6], [[0, 0, 0]])]
+               + [synthetic.alkane_chain(60)])
+    z, pos, off = synthetic.concatenate(structs)
+    # rattled: on the exact mirror-symmetric chain the vector features cancel to rounding noise and
+    # d|v|/dv is arbitrary (DESIGN section 3), so any change of summation order moves the forces
+    pos = (pos + np.random.default_rng(21).normal(0.0, 0.05, pos.shape)).astype(np.float32)
+    team, state, cfg = _with_env({"MLFFD_MSG_TEAM": "4"}, variant_name)
+    rows, _, _ = _with_env({"MLFFD_MSG_TEAM": "0"}, variant_name)
+    e_t, f_t = _run(team, z, pos, off)
+    e_t2, f_t2 = _run(team, z, pos, off)
+    e_r, f_r = _run(rows, z, pos, off)
+    assert np.array_equal(e_t, e_t2) and np.array_equal(f_t, f_t2)
+    assert not np.array_equal(f_t, f_r) or variant_name != "original"   # really a different kernel
+    assert np.max(np.abs(e_t - e_r) / np.diff(off)) <= 2e-6
+    assert np.max(np.abs(f_t - f_r)) <= 2e-5
+    e_ref, f_ref = po.evaluate(state, cfg["cutoff"], z, pos, off, dtype=torch.float64, dense_graph=False)
+    assert np.max(np.abs(e_t - e_ref) / np.diff(off)) <= E_TOL
+    assert np.max(np.abs(f_t - f_ref)) <= F_TOL
