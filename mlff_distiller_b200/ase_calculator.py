@@ -267,7 +267,7 @@ class StudentForceFieldCalculator(_AseCalculator):
         if c["graph_key"] != graph_key:       # workspace (re)allocated: captured pointers are stale
             c["graphs"], c["graph_key"] = {}, graph_key
         done = False
-        if self.use_graph and c["warm"] and c["graph_key"] == graph_key:
+        if self.use_graph and c["warm"] and c["graph_key"] == graph_key and not eng.profiling:
             g = c["graphs"].get(want_virial)
             if g is None:
                 side = torch.cuda.Stream(device=dev)

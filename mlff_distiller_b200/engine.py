@@ -57,6 +57,7 @@ class Engine:
             msg = self.lib.mlffd_last_error(None).decode()
             raise _lib.MlffdError(rc, msg)
         self._ctx = handle
+        self.profiling = False
         self.cap_atoms = self.cap_edges = self.cap_structs = 0
 
     # -- lifetime ---------------------------------------------------------------------------
@@ -136,6 +137,7 @@ class Engine:
     def profile_enable(self, enable: bool = True):
         """Reset launch counters; with ``enable`` also time every stage with CUDA events."""
         self._check(self.lib.mlffd_profile_enable(self._ctx, 1 if enable else 0))
+        self.profiling = bool(enable)   # per-kernel events cannot be recorded inside a graph capture
 
     def profile_read(self) -> dict:
         """{'launches': int, 'stages': {name: {'ms': float, 'launches': int}}} since enable."""

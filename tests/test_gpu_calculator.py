@@ -296,3 +296,23 @@ def test_single_structure_graph_replay_matches_eager(calc):
             w.get_forces()
             calc.calculate_batch(synthetic.druglike_batch(64, first=500))
     assert calc._numbers_cache["graphs"], "the replay path was never taken"
+
+
+def test_calculate_with_stage_profiling_enabled(calc):
+    """Per-kernel profiling events cannot be recorded inside a graph capture: while profiling is on
+    the single-structure path stays eager (and still returns the same numbers)."""
+    atoms = synthetic.benzene()
+    atoms.calc = calc
+    ref = atoms.get_forces().copy()
+    eng = calc.model.engine()
+    eng.profile_enable(True)
+    try:
+        for k in range(3):
+            b = synthetic.benzene()
+            b.set_positions(b.get_positions() + 1e-3 * k)   # translation: same forces, new call
+            b.calc = calc
+            assert np.abs(b.get_forces() - ref).max() < 2e-5
+        prof = eng.profile_read()
+    finally:
+        eng.profile_enable(False)
+    assert prof["launches"] > 0 and prof["stages"]["message_fwd"]["ms"] > 0.0
