@@ -34,14 +34,22 @@ md_kick_kernel(long long n3, double* __restrict__ vel, const float* __restrict__
         vel[i] += 0.5 * dt * (double)forces[i] * inv_mass[i / 3];
 }
 
+// KICK (small systems): the second half kick happens in the same single block, element by element
+// before it enters the kinetic energy -- one launch instead of two, same values in the same order.
+template <bool KICK>
 __global__ void __launch_bounds__(1024)
-md_energy_kernel(long long n3, const double* __restrict__ vel, const double* __restrict__ inv_mass,
+md_energy_kernel(long long n3, double* __restrict__ vel, const float* __restrict__ forces,
+                 const double* __restrict__ inv_mass, double dt,
                  const float* __restrict__ energy, int num_structures, double* __restrict__ series,
                  int* __restrict__ counter, int capacity) {
     __shared__ double red[32];
     double ke = 0.0;
     for (long long i = threadIdx.x; i < n3; i += blockDim.x) {
-        const double v = vel[i];
+        double v = vel[i];
+        if (KICK) {
+            v += 0.5 * dt * (double)forces[i] * inv_mass[i / 3];
+            vel[i] = v;
+        }
         ke += 0.5 * v * v / inv_mass[i / 3];
     }
     double pe = 0.0;

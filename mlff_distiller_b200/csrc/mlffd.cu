@@ -1238,9 +1238,14 @@ extern "C" int mlffd_md_kick_energy(int64_t num_atoms, double* vel_d, const floa
         return MLFFD_EINVAL;
     const long long n3 = 3 * (long long)num_atoms;
     cudaStream_t st = (cudaStream_t)stream;
-    md_kick_kernel<<<clamp_grid(ceil_div(n3, 256), kNumSMs * 8), 256, 0, st>>>(n3, vel_d, forces_d, inv_mass_d, dt);
-    md_energy_kernel<<<1, 1024, 0, st>>>(n3, vel_d, inv_mass_d, energy_d, num_structures, series_d,
-                                         counter_d, capacity);
+    if (n3 <= 8192) {   // small system: kick and energy bookkeeping in one single-block launch
+        md_energy_kernel<true><<<1, 1024, 0, st>>>(n3, vel_d, forces_d, inv_mass_d, dt, energy_d, num_structures,
+                                                   series_d, counter_d, capacity);
+    } else {
+        md_kick_kernel<<<clamp_grid(ceil_div(n3, 256), kNumSMs * 8), 256, 0, st>>>(n3, vel_d, forces_d, inv_mass_d, dt);
+        md_energy_kernel<false><<<1, 1024, 0, st>>>(n3, vel_d, forces_d, inv_mass_d, dt, energy_d, num_structures,
+                                                    series_d, counter_d, capacity);
+    }
     return cudaGetLastError() == cudaSuccess ? MLFFD_OK : MLFFD_ECUDA;
 }
 
