@@ -98,7 +98,8 @@ class StudentForceFieldCalculator(_AseCalculator):
         self.use_analytical_forces = use_analytical_forces
         self.precision = precision
         self.pbc_mode = pbc_mode
-        self.use_graph = use_graph   # replay single-structure steps as one CUDA graph (second call on)
+        self.use_graph = use_graph   # replay single-structure steps as one CUDA graph once a system keeps coming back
+        self.graph_after_calls = 3   # eager calls for a system before its step is captured
         self.max_atoms_per_call = 262144   # micro-batch bound of the batched interface (~30 GB workspace)
         self.implemented_properties = ["energy", "forces"]
         if self.enable_stress:
@@ -218,8 +219,8 @@ class StudentForceFieldCalculator(_AseCalculator):
                         f"({2 * self.model.cutoff:.2f} Å); axis {k} has {height:.3f} Å")
 
     def _evaluate_single(self, positions, numbers, cell, pbc, want_virial: bool = False):
-        """One structure.  The first call for a system runs eagerly (sizes the workspace, grows it
-        on overflow); from the second call on the whole step -- pinned H2D of the positions, the
+        """One structure.  The first calls for a system run eagerly (size the workspace, grow it
+        on overflow); from the fourth call on the whole step -- pinned H2D of the positions, the
         ~30 kernels, status words and D2H of the results -- is ONE CUDA-graph replay: launching
         the kernels one by one from Python costs more host time (~110 us) than a small system
         needs on the device (92 us for H2O).  ``use_graph=False`` keeps every call eager."""
@@ -245,7 +246,7 @@ class StudentForceFieldCalculator(_AseCalculator):
                 "pin_pos": torch.empty((n, 3), dtype=torch.float32).pin_memory(),
                 "pin_out": torch.empty(3 * n + 10, dtype=torch.float32).pin_memory(),
                 "pin_status": torch.zeros(6, dtype=torch.int32).pin_memory(),
-                "graphs": {}, "warm": False, "graph_key": None,
+                "graphs": {}, "warm": False, "graph_key": None, "calls": 0,
             }
             c["status_np"], c["out_np"], c["pin_pos_np"] = c["pin_status"].numpy(), c["pin_out"].numpy(), c["pin_pos"].numpy()
         c["pin_pos_np"][...] = positions   # FP64 -> FP32 conversion straight into the pinned buffer
@@ -267,7 +268,11 @@ class StudentForceFieldCalculator(_AseCalculator):
         if c["graph_key"] != graph_key:       # workspace (re)allocated: captured pointers are stale
             c["graphs"], c["graph_key"] = {}, graph_key
         done = False
-        if self.use_graph and c["warm"] and c["graph_key"] == graph_key and not eng.profiling:
+        c["calls"] += 1
+        # capturing costs tens of milliseconds: only for a system that keeps coming back (MD, relaxation),
+        # not for a screening loop that sees every structure once or twice
+        if (self.use_graph and c["warm"] and c["calls"] > self.graph_after_calls and c["graph_key"] == graph_key
+                and not eng.profiling):
             g = c["graphs"].get(want_virial)
             if g is None:
                 side = torch.cuda.Stream(device=dev)

@@ -47,7 +47,7 @@ def nve(calc, atoms, steps, temperature, seed, dt_fs=0.5):
         calc.calculate(work, ["energy", "forces"])
         return calc.results["energy"], calc.results["forces"]
 
-    for _ in range(3):   # warm-up: workspace sizing (eager), graph capture, first replay
+    for _ in range(3):   # warm-up: workspace sizing (eager calls), graph capture on the fourth call, replays
         force_fn(atoms.get_positions() + 1e-6)
         force_fn(atoms.get_positions())
     torch.cuda.synchronize()
