@@ -93,6 +93,7 @@ struct mlffd_ctx {
     std::string err;
     float* weights_d = nullptr;
     uint8_t* w2_images_d = nullptr;   // swizzled fp16 hi/lo 64 KB weight images (tensor-core path)
+    int skinny8_rows = 1024;        // env MLFFD_SKINNY8_ROWS: atoms at or below which ffma_rows_kernel uses 8-row tiles
     int msg_team = 8;               // env MLFFD_MSG_TEAM (4 | 8; 0 = row-per-warp kernels): warps sharing a CSR row in the small-system message kernels (0 / 1 = off)
     int filter_batch = 2;           // env MLFFD_FILTER_BATCH: 1 = all layers' filter tables in one launch, 0 = one launch per layer, 2 = one launch only for small systems
     int small_rows = 2048;          // env MLFFD_SMALL_ROWS: at or below this many atoms the update block runs on ffma_rows_kernel
@@ -347,16 +348,22 @@ void launch_backward_pipe(mlffd_ctx* ctx, int l, int grid, const float* sb, cons
 }
 
 // small systems: update-block op on the many-block FFMA kernel (umma_rows.cuh:ffma_rows_kernel)
-template <class Op>
-void launch_ffma_rows(mlffd_ctx* ctx, const Op& op, int N, const float* wt, int ld, cudaStream_t st) {
+template <class Op, int TR>
+void launch_ffma_rows_t(mlffd_ctx* ctx, const Op& op, int N, const float* wt, int ld, cudaStream_t st) {
     static bool configured[16] = {};   // per device: the attribute is per (function, device)
-    auto kernel = ffma_rows_kernel<Op>;
-    constexpr size_t smem = ffma_rows_smem_bytes<Op>();
+    auto kernel = ffma_rows_kernel<Op, TR>;
+    constexpr size_t smem = ffma_rows_smem_bytes<Op, TR>();
     if (!configured[ctx->device & 15]) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured[ctx->device & 15] = true;
     }
-    kernel<<<dim3(ceil_div(N, kSkinnyRows), 4), kSkinnyThreads, smem, st>>>(op, N, wt, ld, ctx->status_d);
+    kernel<<<dim3(ceil_div(N, TR), 4), kSkinnyThreads, smem, st>>>(op, N, wt, ld, ctx->status_d);
+}
+template <class Op>
+void launch_ffma_rows(mlffd_ctx* ctx, const Op& op, int N, const float* wt, int ld, cudaStream_t st) {
+    // 8-row tiles (one row per epilogue warp) while they still fit the chip in about one wave
+    if (N <= ctx->skinny8_rows) launch_ffma_rows_t<Op, 8>(ctx, op, N, wt, ld, st);
+    else launch_ffma_rows_t<Op, 16>(ctx, op, N, wt, ld, st);
 }
 
 template <int H>
@@ -751,6 +758,7 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     if (const char* ns = std::getenv("MLFFD_SMALL_ROWS")) ctx->small_rows = std::atoi(ns);
     if (const char* ns = std::getenv("MLFFD_FILTER_BATCH")) ctx->filter_batch = std::atoi(ns);
     if (const char* ns = std::getenv("MLFFD_MSG_TEAM")) ctx->msg_team = std::atoi(ns);
+    if (const char* ns = std::getenv("MLFFD_SKINNY8_ROWS")) ctx->skinny8_rows = std::atoi(ns);
     if (const char* ns = std::getenv("MLFFD_PIPE_DEPTH_FWD")) ctx->pipe_depth_fwd = std::atoi(ns);
     if (const char* ns = std::getenv("MLFFD_PIPE_DEPTH_BWD")) ctx->pipe_depth_bwd = std::atoi(ns);
     if (const char* nm = std::getenv("MLFFD_NEIGHBOR"))

@@ -224,19 +224,19 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
 // by (rows / 16) x 4 blocks in parallel straight from L2 in the [in][out] layout (coalesced over
 // channels), so one launch is a few microseconds.  FP32 FFMA: same accuracy class as the split
 // tensor-core products.
-constexpr int kSkinnyRows = 16, kSkinnyThreads = 256;   // 16 rows x 32 channels per block, 2 rows per epilogue warp
-template <class Op>
+constexpr int kSkinnyThreads = 256;   // TR (8 | 16) rows x 32 channels per block, TR / 8 rows per epilogue warp
+template <class Op, int TR>
 constexpr size_t ffma_rows_smem_bytes() {
-    return sizeof(float) * (size_t)(kSkinnyRows * (Op::KS * 128 + 4) + 8 * kSkinnyRows * 32);
+    return sizeof(float) * (size_t)(TR * (Op::KS * 128 + 4) + 8 * TR * 32);
 }
 
 // wt: the op's weight matrix as [in][out] with row stride ld (UpdateWeights: M1t / M2t / M2 / M1)
-template <class Op>
+template <class Op, int TR>
 __global__ void __launch_bounds__(kSkinnyThreads)
 ffma_rows_kernel(Op op, int num_rows, const float* __restrict__ wt, int ld,
                  const DeviceStatus* __restrict__ status) {
     constexpr int KS = Op::KS, NC = Op::NC, K = KS * 128, XS = K + 4, KW = K / 8;
-    constexpr int TR = kSkinnyRows, WR = TR / 8;   // rows per tile, rows per epilogue warp
+    constexpr int WR = TR / 8;   // rows per epilogue warp
     if (status != nullptr && status->overflow) return;
     extern __shared__ __align__(16) float skinny_smem[];
     float* x_s = skinny_smem;             // [TR rows][XS]
