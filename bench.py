@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--precision", choices=["fp32", "tc", "tc_fp16", "tc_bf16"], default="tc",
                     help="fp32 = FFMA dense layers; tc = tcgen05 tensor cores with 2-term FP16 split (FP32-equivalent, "
                          "the headline); tc_fp16 / tc_bf16 = single-pass products with looser stated bounds (NOT the headline)")
+    ap.add_argument("--filter-mode", choices=["spline", "table"], default="spline",
+                    help="spline = per-model filter splines evaluated in the message kernels (default); "
+                         "table = per-step [P,3H] filter tables in HBM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -267,7 +270,7 @@ def run_b200(args):
     pos_sets64 = [pos64 + rng.normal(0.0, 0.01, pos64.shape) for _ in range(POSITION_SETS)]
 
     calc = StudentForceFieldCalculator(ROOT / "tests" / "golden" / VARIANT_FILES[args.variant], device=str(dev),
-                                      precision=args.precision)
+                                      precision=args.precision, filter_mode=args.filter_mode)
     model = calc.model
     eng = model.engine()
     cfg = model.config

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MLFFD_ABI_VERSION 1
+#define MLFFD_ABI_VERSION 2
 
 enum {
     MLFFD_OK = 0,
@@ -49,6 +49,20 @@ enum {
                                  precision class of TF32), FP32 accumulation; looser bounds */
 };
 
+/* How the radial filter f_l(d) = W2 SiLU(W1 phi~(d) + b1) + b2 (student_model.py:318-322, 350) reaches
+ * the message kernels.  It depends on the distance only, never on the structure. */
+enum {
+    MLFFD_FILTER_SPLINE = 0, /* default: a quintic B-spline of every component function on [0, cutoff]
+                                (256 intervals) built once per model in FP64; the message kernels keep a
+                                32-channel slice of it in shared memory and evaluate value and
+                                d-derivative per edge.  Nothing per-pair is written to HBM.  Stated bound:
+                                |f - spline| <= 2e-7, |f' - spline'| <= 1e-5 / Angstrom as functions (FP64
+                                evaluation); <= 2e-6 / 2e-5 evaluated in FP32 on the device. */
+    MLFFD_FILTER_TABLE = 1   /* the two dense layers evaluated per undirected pair and step into a
+                                [P,3H] table (+ derivative) in HBM that the message kernels stream
+                                (tensor cores per `precision`). */
+};
+
 /* Hyper-parameters = the `config` dict of StudentForceField.save
  * (src/mlff_distiller/models/student_model.py:1087-1094). */
 typedef struct mlffd_config {
@@ -58,6 +72,7 @@ typedef struct mlffd_config {
     int32_t max_z;            /* embedding has max_z + 1 rows */
     float cutoff;             /* r_c in Angstrom */
     int32_t precision;        /* MLFFD_PREC_* */
+    int32_t filter_mode;      /* MLFFD_FILTER_* */
 } mlffd_config;
 
 /* Read back by mlffd_get_status (synchronises the stream of the last call). */
@@ -130,7 +145,7 @@ int mlffd_export_edges(mlffd_ctx* ctx, int64_t* edge_index_d, int64_t capacity_e
  *   z_d        [N] i32 atomic numbers (0..max_z)
  *   energy_d   [B] f32 out: total energy per structure (eV)
  *   forces_d   [N,3] f32 out: -dE/dx (eV/A); NULL = energy only (no reverse pass)
- * Runs neighbour build, filter tables, L x (message, update), readout and the analytical
+ * Runs neighbour build, (filter tables,) L x (message, update), readout and the analytical
  * reverse pass, all on `stream`, no host synchronisation.  Check mlffd_get_status().overflow
  * after synchronising: if set, the outputs are invalid; reserve more edges and call again.
  */
@@ -172,9 +187,17 @@ int mlffd_filter_table(mlffd_ctx* ctx, int32_t layer, const float* dist_d, int64
                        float* filter_d, float* dfilter_d, void* stream);
 
 /*
+ * Stage entry point (parity tests): the same quantities as mlffd_filter_table, evaluated from the
+ * per-model filter spline the MLFFD_FILTER_SPLINE message kernels use (value and exact derivative of
+ * the interpolant).  Works in either filter mode.
+ */
+int mlffd_filter_spline(mlffd_ctx* ctx, int32_t layer, const float* dist_d, int64_t num_pairs,
+                        float* filter_d, float* dfilter_d, void* stream);
+
+/*
  * Test hook: device pointer + element count of an internal buffer of the last call
  * (synchronises).  Names: "rowptr","col","rev","pair","edge_dst","geo" (float4 ux,uy,uz,d),
- * "pair_dist", "filter"/"dfilter" (layer), "s_in"/"v_in"/"s_msg"/"v_msg"/"y1"/"gates" (layer),
+ * "pair_dist", "filter"/"dfilter" (layer; MLFFD_FILTER_TABLE only), "s_in"/"v_in"/"s_msg"/"v_msg"/"y1"/"gates" (layer),
  * "s_out", "atom_energy", "sbar"/"vbar" (adjoints of s_msg / v_msg of `layer`; all layers are
  * kept only when the context was created with MLFFD_DEBUG_KEEP=1 in the environment, otherwise
  * two sets ping-pong), "edge_adj" (float4 dE/du_x, dE/du_y, dE/du_z, dE/dd through the filters).

@@ -17,7 +17,7 @@ from typing import List, Optional
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libmlffd.so"
 SOURCES = ["mlffd.cu"]
-HEADERS = ["common.cuh", "neighbor.cuh", "cell_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh", "message_pipe.cuh", "message_team.cuh", "message_staged.cuh",
+HEADERS = ["common.cuh", "neighbor.cuh", "cell_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh", "message_pipe.cuh", "message_team.cuh", "message_staged.cuh", "message_spline.cuh", "spline_table.h",
            "update.cuh", "readout.cuh", "md.cuh", "../../include/mlffd.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -29,18 +29,21 @@ EXPORTS = [
     "mlffd_energy_forces", "mlffd_get_status", "mlffd_filter_table", "mlffd_debug_buffer",
     "mlffd_profile_enable", "mlffd_profile_read", "mlffd_stage_name",
     "mlffd_md_kick_drift", "mlffd_md_kick_energy", "mlffd_set_structure_hint", "mlffd_virial",
-    "mlffd_status_async",
+    "mlffd_status_async", "mlffd_filter_spline",
 ]
 NUM_STAGES = 10
 
 MLFFD_OK, MLFFD_EINVAL, MLFFD_ECUDA, MLFFD_ECAPACITY, MLFFD_ENOMEM = 0, -1, -2, -3, -4
 PRECISIONS = {"fp32": 0, "tc": 1, "tc_bf16": 3, "tc_fp16": 4}
+FILTER_MODES = {"spline": 0, "table": 1}
+ABI_VERSION = 2
 
 
 class MlffdConfig(ctypes.Structure):
     _fields_ = [("hidden_dim", ctypes.c_int32), ("num_rbf", ctypes.c_int32),
                 ("num_interactions", ctypes.c_int32), ("max_z", ctypes.c_int32),
-                ("cutoff", ctypes.c_float), ("precision", ctypes.c_int32)]
+                ("cutoff", ctypes.c_float), ("precision", ctypes.c_int32),
+                ("filter_mode", ctypes.c_int32)]
 
 
 class MlffdStatus(ctypes.Structure):
@@ -130,6 +133,8 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     lib.mlffd_status_async.argtypes = [vp, vp, vp]
     lib.mlffd_filter_table.restype = ctypes.c_int
     lib.mlffd_filter_table.argtypes = [vp, i32, vp, i64, vp, vp, vp]
+    lib.mlffd_filter_spline.restype = ctypes.c_int
+    lib.mlffd_filter_spline.argtypes = [vp, i32, vp, i64, vp, vp, vp]
     lib.mlffd_debug_buffer.restype = ctypes.c_int
     lib.mlffd_debug_buffer.argtypes = [vp, ctypes.c_char_p, i32, ctypes.POINTER(vp),
                                        ctypes.POINTER(i64), ctypes.POINTER(i32)]
@@ -148,7 +153,7 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     lib.mlffd_md_kick_drift.argtypes = [i64, vp, vp, vp, vp, f64, vp, vp]
     lib.mlffd_md_kick_energy.restype = ctypes.c_int
     lib.mlffd_md_kick_energy.argtypes = [i64, vp, vp, vp, f64, vp, i32, vp, vp, i32, vp]
-    if lib.mlffd_version() != 1:
+    if lib.mlffd_version() != ABI_VERSION:
         raise RuntimeError("libmlffd.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib

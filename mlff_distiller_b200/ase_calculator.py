@@ -82,7 +82,8 @@ class StudentForceFieldCalculator(_AseCalculator):
                  use_compile: bool = False, use_fp16: bool = False, use_jit: bool = False,
                  jit_path: Optional[Union[str, Path]] = None, use_torch_cluster: bool = True,
                  use_analytical_forces: bool = False, *, precision: str = "tc",
-                 pbc_mode: str = "ignore", use_graph: bool = True, **kwargs):
+                 pbc_mode: str = "ignore", use_graph: bool = True, filter_mode: str = "spline",
+                 **kwargs):
         super().__init__(**kwargs)
         self.checkpoint_path = Path(checkpoint_path)
         self.device = torch.device(device)
@@ -97,6 +98,7 @@ class StudentForceFieldCalculator(_AseCalculator):
         self.use_torch_cluster = use_torch_cluster
         self.use_analytical_forces = use_analytical_forces
         self.precision = precision
+        self.filter_mode = filter_mode
         self.pbc_mode = pbc_mode
         self.use_graph = use_graph   # replay single-structure steps as one CUDA graph once a system keeps coming back
         self.graph_after_calls = 3   # eager calls for a system before its step is captured
@@ -139,7 +141,8 @@ class StudentForceFieldCalculator(_AseCalculator):
                 f"Please ensure the model has been trained and checkpoint saved.")
         try:
             model = StudentForceField.load(source, device=str(self.device),
-                                           precision=self.precision, pbc_mode=self.pbc_mode)
+                                           precision=self.precision, pbc_mode=self.pbc_mode,
+                                           filter_mode=self.filter_mode)
             model.eval()
             model.engine()  # fail loudly now if the CUDA library / device is missing
             return model

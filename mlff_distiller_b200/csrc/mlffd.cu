@@ -26,6 +26,7 @@
 #include "message_pipe.cuh"
 #include "message_team.cuh"
 #include "message_staged.cuh"
+#include "message_spline.cuh"
 #include "neighbor.cuh"
 #include "readout.cuh"
 #include "update.cuh"
@@ -49,6 +50,7 @@ struct Workspace {
     int *atom_struct = nullptr, *deg = nullptr, *deg_low = nullptr, *rowptr = nullptr, *lowptr = nullptr;
     int *col = nullptr, *edge_dst = nullptr, *rev = nullptr, *pair = nullptr;
     float4 *geo = nullptr, *edge_adj = nullptr;
+    float4* erec = nullptr;   // [E][4] per-edge records of the spline message kernels (message_spline.cuh)
     double* virial64 = nullptr;      // [cap_structs][9] FP64 accumulators of mlffd_virial
     float* pair_dist = nullptr;
     // cell list (large structures)
@@ -93,6 +95,11 @@ struct mlffd_ctx {
     std::string err;
     float* weights_d = nullptr;
     uint8_t* w2_images_d = nullptr;   // swizzled fp16 hi/lo 64 KB weight images (tensor-core path)
+    bool spline = true;               // cfg.filter_mode == MLFFD_FILTER_SPLINE: no per-step filter tables
+    float* spline_d = nullptr;        // [L][H/32][kSplineRows][3][32] filter spline coefficients (always built)
+    float spline_inv_h = 0.f;         // intervals per Angstrom
+    int adj_slabs_per_layer = 1;      // edge-adjoint slabs one layer's reverse kernel writes (H/32 in spline mode)
+    int spline_fwd_shape = 0, spline_bwd_shape = 0;   // env MLFFD_SPLINE_FWD / _BWD: launch shape of the spline message kernels
     int skinny8_rows = 1024;        // env MLFFD_SKINNY8_ROWS: atoms at or below which ffma_rows_kernel uses 8-row tiles
     int msg_team = 8;               // env MLFFD_MSG_TEAM (4 | 8; 0 = row-per-warp kernels): warps sharing a CSR row in the small-system message kernels (0 / 1 = off)
     int filter_batch = 2;           // env MLFFD_FILTER_BATCH: 1 = all layers' filter tables in one launch, 0 = one launch per layer, 2 = one launch only for small systems
@@ -366,6 +373,81 @@ void launch_ffma_rows(mlffd_ctx* ctx, const Op& op, int N, const float* wt, int 
     else launch_ffma_rows_t<Op, 16>(ctx, op, N, wt, ld, st);
 }
 
+// ---- spline-filter message kernels (message_spline.cuh): one (slice, partition) per CTA -------
+inline int spline_grid(int N, int slices, int groups, int ctas_per_sm) {
+    const int blocks = ceil_div(std::max(N, 1), groups);
+    const int parts = std::max(1, std::min(blocks, (kNumSMs * ctas_per_sm) / slices));
+    return parts * slices;
+}
+const float* spline_layer_table(const mlffd_ctx* ctx, int l) {
+    return ctx->spline_d + (size_t)l * 3 * ctx->H * kSplineRows;
+}
+template <int THREADS, int CTAS>
+cudaError_t launch_spline_forward_t(mlffd_ctx* ctx, int l, int N, cudaStream_t st) {
+    Workspace& ws = ctx->ws;
+    const int grid = spline_grid(N, ctx->H / kSliceChannels, THREADS / 8, CTAS);
+    static bool configured[16] = {};   // the attribute is per (function, device)
+    if (!configured[ctx->device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(spline_message_forward_kernel<true, THREADS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSplineSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spline_message_forward_kernel<false, THREADS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSplineSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured[ctx->device & 15] = true;
+    }
+    if (l == 0)
+        spline_message_forward_kernel<true, THREADS, CTAS><<<grid, THREADS, kSplineSmemBytes, st>>>(
+            spline_layer_table(ctx, l), ctx->H, ws.rowptr, ws.erec, ws.s_in[l], nullptr,
+            ws.s_msg[l], ws.v_msg[l], N, ctx->status_d);
+    else
+        spline_message_forward_kernel<false, THREADS, CTAS><<<grid, THREADS, kSplineSmemBytes, st>>>(
+            spline_layer_table(ctx, l), ctx->H, ws.rowptr, ws.erec, ws.s_in[l], ws.v_in[l],
+            ws.s_msg[l], ws.v_msg[l], N, ctx->status_d);
+    return cudaSuccess;
+}
+template <int THREADS, int CTAS>
+cudaError_t launch_spline_backward_t(mlffd_ctx* ctx, int l, const float* sb, const float* vb, float* sb_in, float* vb_in,
+                                     int N, cudaStream_t st) {
+    Workspace& ws = ctx->ws;
+    const int slices = ctx->H / kSliceChannels;
+    const int grid = spline_grid(N, slices, THREADS / 8, CTAS);
+    static bool configured[16] = {};
+    if (!configured[ctx->device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(spline_message_backward_kernel<true, THREADS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSplineSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spline_message_backward_kernel<false, THREADS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSplineSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured[ctx->device & 15] = true;
+    }
+    float4* slab = ws.edge_adj + (size_t)l * slices * ws.cap_edges;
+    if (l == 0)
+        spline_message_backward_kernel<true, THREADS, CTAS><<<grid, THREADS, kSplineSmemBytes, st>>>(
+            spline_layer_table(ctx, l), ctx->H, ws.rowptr, ws.erec, ws.s_in[l], nullptr,
+            sb, vb, sb_in, vb_in, slab, (size_t)ws.cap_edges, N, ctx->status_d);
+    else
+        spline_message_backward_kernel<false, THREADS, CTAS><<<grid, THREADS, kSplineSmemBytes, st>>>(
+            spline_layer_table(ctx, l), ctx->H, ws.rowptr, ws.erec, ws.s_in[l], ws.v_in[l],
+            sb, vb, sb_in, vb_in, slab, (size_t)ws.cap_edges, N, ctx->status_d);
+    return cudaSuccess;
+}
+// launch shapes: (threads per CTA, resident CTAs per SM); env MLFFD_SPLINE_FWD / MLFFD_SPLINE_BWD pick one
+cudaError_t launch_spline_forward(mlffd_ctx* ctx, int l, int N, cudaStream_t st) {
+    switch (ctx->spline_fwd_shape) {
+        case 1: return launch_spline_forward_t<768, 1>(ctx, l, N, st);
+        case 2: return launch_spline_forward_t<384, 2>(ctx, l, N, st);
+        case 3: return launch_spline_forward_t<1024, 1>(ctx, l, N, st);
+        default: return launch_spline_forward_t<512, 2>(ctx, l, N, st);
+    }
+}
+cudaError_t launch_spline_backward(mlffd_ctx* ctx, int l, const float* sb, const float* vb, float* sb_in, float* vb_in,
+                                   int N, cudaStream_t st) {
+    switch (ctx->spline_bwd_shape) {
+        case 1: return launch_spline_backward_t<768, 1>(ctx, l, sb, vb, sb_in, vb_in, N, st);
+        case 2: return launch_spline_backward_t<384, 2>(ctx, l, sb, vb, sb_in, vb_in, N, st);
+        case 3: return launch_spline_backward_t<256, 2>(ctx, l, sb, vb, sb_in, vb_in, N, st);
+        case 4: return launch_spline_backward_t<640, 1>(ctx, l, sb, vb, sb_in, vb_in, N, st);
+        case 5: return launch_spline_backward_t<576, 1>(ctx, l, sb, vb, sb_in, vb_in, N, st);
+        default: return launch_spline_backward_t<512, 1>(ctx, l, sb, vb, sb_in, vb_in, N, st);
+    }
+}
+
 template <int H>
 int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets, int n_structs,
               float* energy, float* forces, cudaStream_t st) {
@@ -399,10 +481,16 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     embedding_kernel<H><<<clamp_grid(ceil_div((int64_t)N * (H / 4), 256), kNumSMs * 8), 256, 0, st>>>(
         z, ctx->emb, ctx->cfg.max_z, ws.s_in[0], N);
     LAUNCHED(ctx, "embedding_kernel", MLFFD_STAGE_EMBEDDING, st);
+    if (ctx->spline) {   // per-edge spline basis weights: once per step, read by every layer in both directions
+        spline_basis_kernel<<<clamp_grid(ceil_div(std::max<int64_t>(ws.cap_edges, 1), 256), kNumSMs * 8), 256, 0, st>>>(
+            ws.col, ws.geo, ctx->spline_inv_h, ws.erec, status);
+        LAUNCHED(ctx, "spline_basis_kernel", MLFFD_STAGE_FILTER, st);
+    }
 
     // the filters depend on the distances only: with the tensor-core kernel all layers' tables come
     // from one launch ahead of the layer loop
-    const bool filters_up_front = ctx->use_umma_filter &&
+    const bool spline = ctx->spline;
+    const bool filters_up_front = !spline && ctx->use_umma_filter &&
                                   (ctx->filter_batch == 1 || (ctx->filter_batch == 2 && N <= ctx->small_rows));
     if (filters_up_front) {
         int rc = launch_filter_umma<H>(ctx, 0, L, ws.pair_dist, &ctx->status_d->num_pairs, 0, status,
@@ -410,12 +498,14 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
         if (rc) return rc;
     }
     for (int l = 0; l < L; ++l) {
-        if (!filters_up_front) {
+        if (!spline && !filters_up_front) {
             int rc = launch_filter<H>(ctx, l, ws.pair_dist, &ctx->status_d->num_pairs, 0, status,
                                       ws.filt[l], ws.dfilt[l], ws.cap_pairs, st);
             if (rc) return rc;
         }
-        if (staged && l == 0)
+        if (spline) {
+            CUDA_TRY(ctx, launch_spline_forward(ctx, l, N, st));
+        } else if (staged && l == 0)
             message_forward_staged_kernel<H, true><<<staged_grid, kStagedThreads, staged_smem, st>>>(
                 offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], nullptr,
                 ws.s_msg[l], ws.v_msg[l], ctx->status_d);
@@ -566,7 +656,9 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     message_backward_edges_staged_kernel<H, LAYER0, ACC><<<staged_grid, kStagedThreads, staged_smem, st>>>(             \
         offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.dfilt[l], ws.s_in[l],   \
         ws.v_in[l], sb, vb, ws.edge_adj, ctx->status_d)
-        if (staged) {
+        if (spline) {
+            CUDA_TRY(ctx, launch_spline_backward(ctx, l, sb, vb, sb_in, vb_in, N, st));
+        } else if (staged) {
             if (l == 0) { if (first) MSG_BWD_EDGES(true, false); else MSG_BWD_EDGES(true, true); }
             else        { if (first) MSG_BWD_EDGES(false, false); else MSG_BWD_EDGES(false, true); }
             if (l > 0) {
@@ -594,10 +686,10 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
 #undef MSG_BWD
         LAUNCHED(ctx, "message_backward_kernel", MLFFD_STAGE_MESSAGE_BWD, st);
     }
-    ctx->last_adj_slabs = adj_slabs ? L : 1;
-    force_kernel<<<warp_grid, 256, 0, st>>>(ws.rowptr, ws.rev, ws.geo, ws.edge_adj, adj_slabs ? L : 1,
+    ctx->last_adj_slabs = spline ? L * ctx->adj_slabs_per_layer : (adj_slabs ? L : 1);
+    force_kernel<<<warp_grid, 256, 0, st>>>(ws.rowptr, ws.rev, ws.geo, ws.edge_adj, ctx->last_adj_slabs,
                                             (size_t)ws.cap_edges,
-                                            ctx->debug_keep ? ws.edge_adj + (size_t)L * ws.cap_edges : nullptr,
+                                            ctx->debug_keep ? ws.edge_adj + (size_t)L * ctx->adj_slabs_per_layer * ws.cap_edges : nullptr,
                                             forces, N, status);
     LAUNCHED(ctx, "force_kernel", MLFFD_STAGE_FORCE, st);
     return MLFFD_OK;
@@ -725,6 +817,8 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     if (config->precision != MLFFD_PREC_FP32 && config->precision != MLFFD_PREC_TC_FP16X2 &&
         config->precision != MLFFD_PREC_TC_FP16 && config->precision != MLFFD_PREC_TC_BF16)
         return fail(nullptr, MLFFD_EINVAL, "precision must be MLFFD_PREC_FP32, _TC_FP16X2, _TC_FP16 or _TC_BF16");
+    if (config->filter_mode != MLFFD_FILTER_SPLINE && config->filter_mode != MLFFD_FILTER_TABLE)
+        return fail(nullptr, MLFFD_EINVAL, "filter_mode must be MLFFD_FILTER_SPLINE or MLFFD_FILTER_TABLE");
     const size_t per_layer = (size_t)H * K + H + 3 * H * H + 3 * H + 2 * H * H + H + 3 * H * H + 3 * H + 9;
     const size_t expect = (size_t)(config->max_z + 1) * H + 2 * K + L * per_layer +
                           (size_t)(H / 2) * H + H / 2 + (size_t)(H / 4) * (H / 2) + H / 4 + H / 4 + 1;
@@ -807,6 +901,7 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
         g_create_error = msg;
         if (ctx->weights_d) cudaFree(ctx->weights_d);
         if (ctx->w2_images_d) cudaFree(ctx->w2_images_d);
+        if (ctx->spline_d) cudaFree(ctx->spline_d);
         if (ctx->status_d) cudaFree(ctx->status_d);
         delete ctx;
         return code;
@@ -818,6 +913,26 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     e = cudaMalloc(&ctx->status_d, sizeof(DeviceStatus));
     if (e != cudaSuccess) return bail(MLFFD_ENOMEM, cudaGetErrorString(e));
     cudaMemset(ctx->status_d, 0, sizeof(DeviceStatus));
+    {   // per-model filter splines (spline_table.h), FP64 on the host, once
+        ctx->spline = config->filter_mode == MLFFD_FILTER_SPLINE;
+        ctx->adj_slabs_per_layer = ctx->spline ? H / kSliceChannels : 1;
+        ctx->spline_inv_h = (float)kSplineIntervals / config->cutoff;
+        const float* centers_h = weights_host + (size_t)(config->max_z + 1) * H;
+        const float* q = centers_h + 2 * K;
+        std::vector<float> all;
+        for (int l = 0; l < L; ++l) {
+            const float *W1 = q, *b1 = W1 + (size_t)H * K, *W2 = b1 + H, *b2 = W2 + (size_t)3 * H * H;
+            const std::vector<float> t = build_filter_spline(H, K, config->cutoff, centers_h, gam.data(), W1, b1, W2, b2);
+            all.insert(all.end(), t.begin(), t.end());
+            q += per_layer;
+        }
+        e = cudaMalloc(&ctx->spline_d, all.size() * sizeof(float));
+        if (e != cudaSuccess) return bail(MLFFD_ENOMEM, cudaGetErrorString(e));
+        e = cudaMemcpy(ctx->spline_d, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
+        if (const char* ns = std::getenv("MLFFD_SPLINE_FWD")) ctx->spline_fwd_shape = std::atoi(ns);
+        if (const char* ns = std::getenv("MLFFD_SPLINE_BWD")) ctx->spline_bwd_shape = std::atoi(ns);
+    }
     if (config->precision != MLFFD_PREC_FP32) {
         ctx->tc_mode = config->precision == MLFFD_PREC_TC_FP16 ? kTcF16
                      : config->precision == MLFFD_PREC_TC_BF16 ? kTcBF16 : kTcSplit;
@@ -925,6 +1040,7 @@ extern "C" void mlffd_model_destroy(mlffd_ctx* ctx) {
     if (ctx->ws.arena) cudaFree(ctx->ws.arena);
     if (ctx->weights_d) cudaFree(ctx->weights_d);
     if (ctx->w2_images_d) cudaFree(ctx->w2_images_d);
+    if (ctx->spline_d) cudaFree(ctx->spline_d);
     if (ctx->status_d) cudaFree(ctx->status_d);
     delete ctx;
 }
@@ -958,7 +1074,10 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
     const size_t o_rev = plan.take(sizeof(int) * E);
     const size_t o_pair = plan.take(sizeof(int) * E);
     const size_t o_geo = plan.take(sizeof(float4) * E);
-    const size_t o_adj = plan.take(sizeof(float4) * E * (L + 1));   // per-layer slabs + debug sum
+    // per-layer (spline mode: per-layer, per-slice) slabs + debug sum
+    const size_t o_adj = plan.take(sizeof(float4) * E * ((size_t)L * ctx->adj_slabs_per_layer + 1));
+    const size_t o_erec = plan.take(ctx->spline ? sizeof(float4) * 4 * E : 0);
+    const int64_t PT = ctx->spline ? 0 : P;   // the per-step filter tables exist in MLFFD_FILTER_TABLE mode only
     const size_t o_pdist = plan.take(sizeof(float) * P);
     const size_t o_eps = plan.take(sizeof(float) * N);
     const size_t o_virial = plan.take(sizeof(double) * 9 * max_structures);
@@ -981,8 +1100,8 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
         o_sbar[kMaxLayers], o_vbar[kMaxLayers];
     const int adj_sets = ctx->debug_keep ? L : std::min(L, 2);
     for (int l = 0; l < L; ++l) {
-        o_filt[l] = plan.take(sizeof(float) * P * 3 * H);
-        o_dfilt[l] = plan.take(sizeof(float) * P * 3 * H);
+        o_filt[l] = plan.take(sizeof(float) * PT * 3 * H);
+        o_dfilt[l] = plan.take(sizeof(float) * PT * 3 * H);
         o_s_in[l] = plan.take(sizeof(float) * N * H);
         o_v_in[l] = (l > 0) ? plan.take(sizeof(float) * N * 3 * H) : 0;
         o_s_msg[l] = plan.take(sizeof(float) * N * H);
@@ -1013,6 +1132,7 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
     ws.col = (int*)(base + o_col); ws.edge_dst = (int*)(base + o_edge_dst);
     ws.rev = (int*)(base + o_rev); ws.pair = (int*)(base + o_pair);
     ws.geo = (float4*)(base + o_geo); ws.edge_adj = (float4*)(base + o_adj);
+    ws.erec = (float4*)(base + o_erec);
     ws.pair_dist = (float*)(base + o_pdist);
     ws.eps = (float*)(base + o_eps);
     ws.virial64 = (double*)(base + o_virial);
@@ -1133,6 +1253,19 @@ extern "C" int mlffd_filter_table(mlffd_ctx* ctx, int32_t layer, const float* di
     }
 }
 
+extern "C" int mlffd_filter_spline(mlffd_ctx* ctx, int32_t layer, const float* dist_d, int64_t num_pairs,
+                                   float* filter_d, float* dfilter_d, void* stream) {
+    if (!ctx) return MLFFD_EINVAL;
+    if (!dist_d || !filter_d || !dfilter_d || layer < 0 || layer >= ctx->L || num_pairs < 0)
+        return fail(ctx, MLFFD_EINVAL, "mlffd_filter_spline: bad argument");
+    if (num_pairs == 0) return MLFFD_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    spline_filter_eval_kernel<<<clamp_grid(ceil_div(num_pairs * 3 * ctx->H, 256), kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(
+        spline_layer_table(ctx, layer), ctx->H, ctx->spline_inv_h, dist_d, (long long)num_pairs, filter_d, dfilter_d);
+    LAUNCH_CHECK(ctx, "spline_filter_eval_kernel");
+    return MLFFD_OK;
+}
+
 extern "C" int mlffd_virial(mlffd_ctx* ctx, const int32_t* offsets_d, int32_t num_structures,
                             float* virial_d, void* stream) {
     if (!ctx) return MLFFD_EINVAL;
@@ -1175,11 +1308,13 @@ extern "C" int mlffd_debug_buffer(mlffd_ctx* ctx, const char* name, int32_t laye
     else if (n == "pair") { p = ws.pair; cnt = E; }
     else if (n == "edge_dst") { p = ws.edge_dst; cnt = E; }
     else if (n == "geo") { p = ws.geo; cnt = E; es = 16; }
-    else if (n == "edge_adj") { p = ws.edge_adj + (size_t)ctx->L * ws.cap_edges; cnt = E; es = 16; }
+    else if (n == "edge_adj") { p = ws.edge_adj + (size_t)ctx->L * ctx->adj_slabs_per_layer * ws.cap_edges; cnt = E; es = 16; }
     else if (n == "pair_dist") { p = ws.pair_dist; cnt = P; }
     else if (n == "atom_energy") { p = ws.eps; cnt = N; }
     else if (n == "s_out") { p = ws.s_in[L]; cnt = N * H; }
     else if (!layer_ok) return fail(ctx, MLFFD_EINVAL, "mlffd_debug_buffer: bad layer");
+    else if ((n == "filter" || n == "dfilter") && ctx->spline)
+        return fail(ctx, MLFFD_EINVAL, "mlffd_debug_buffer: no filter table in MLFFD_FILTER_SPLINE mode");
     else if (n == "filter") { p = ws.filt[layer]; cnt = P * 3 * H; }
     else if (n == "dfilter") { p = ws.dfilt[layer]; cnt = P * 3 * H; }
     else if (n == "s_in") { p = ws.s_in[layer]; cnt = N * H; }

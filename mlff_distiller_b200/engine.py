@@ -34,7 +34,7 @@ class Engine:
     """
 
     def __init__(self, state: Mapping[str, np.ndarray], cfg: ModelConfig, device="cuda",
-                 precision: str = "fp32"):
+                 precision: str = "fp32", filter_mode: str = "spline"):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("the B200 energy+force path needs a CUDA device (no CPU fallback)")
@@ -44,12 +44,16 @@ class Engine:
             self.device = torch.device("cuda", torch.cuda.current_device())
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        if filter_mode not in _lib.FILTER_MODES:
+            raise ValueError(f"filter_mode must be one of {sorted(_lib.FILTER_MODES)}")
         self.lib = _lib.load()
         self.cfg = cfg
         self.precision = precision
+        self.filter_mode = filter_mode
         blob = np.ascontiguousarray(pack_weights(state, cfg), dtype=np.float32)
         c = _lib.MlffdConfig(cfg.hidden_dim, cfg.num_rbf, cfg.num_interactions, cfg.max_z,
-                             float(cfg.cutoff), _lib.PRECISIONS[precision])
+                             float(cfg.cutoff), _lib.PRECISIONS[precision],
+                             _lib.FILTER_MODES[filter_mode])
         handle = ctypes.c_void_p()
         rc = self.lib.mlffd_model_create(ctypes.byref(handle), self.device.index, ctypes.byref(c),
                                          blob.ctypes.data_as(ctypes.c_void_p), blob.size)
@@ -169,6 +173,18 @@ class Engine:
         self._check(self.lib.mlffd_filter_table(self._ctx, int(layer), dist.data_ptr(),
                                                 dist.numel(), f.data_ptr(), df.data_ptr(),
                                                 self._stream()))
+        return f, df
+
+    def filter_spline(self, layer: int, dist: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Value and d-derivative of the per-model filter spline (what the spline-mode message
+        kernels evaluate in shared memory) at ``dist``: two [P, 3H] tensors."""
+        h = self.cfg.hidden_dim
+        dist = dist.to(device=self.device, dtype=torch.float32).contiguous()
+        f = torch.empty((dist.numel(), 3 * h), dtype=torch.float32, device=self.device)
+        df = torch.empty_like(f)
+        self._check(self.lib.mlffd_filter_spline(self._ctx, int(layer), dist.data_ptr(),
+                                                 dist.numel(), f.data_ptr(), df.data_ptr(),
+                                                 self._stream()))
         return f, df
 
     def debug_buffer(self, name: str, layer: int = 0) -> torch.Tensor:

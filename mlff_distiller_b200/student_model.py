@@ -116,7 +116,7 @@ class StudentForceField(nn.Module):
     def __init__(self, hidden_dim: int = 128, num_interactions: int = 3, num_rbf: int = 20,
                  cutoff: float = 5.0, max_z: int = 118, learnable_rbf: bool = False,
                  use_torch_cluster: bool = True, *, precision: str = "tc",
-                 pbc_mode: str = "ignore"):
+                 pbc_mode: str = "ignore", filter_mode: str = "spline"):
         super().__init__()
         if pbc_mode not in ("ignore", "minimum_image"):
             raise ValueError("pbc_mode must be 'ignore' or 'minimum_image'")
@@ -128,6 +128,7 @@ class StudentForceField(nn.Module):
         self.use_torch_cluster = use_torch_cluster  # accepted for compatibility; unused
         self.precision = precision
         self.pbc_mode = pbc_mode
+        self.filter_mode = filter_mode   # 'spline' (per-model filter splines in shared memory) | 'table'
         self.embedding = nn.Embedding(max_z + 1, hidden_dim)
         self.rbf = _RBFBuffers(num_rbf, cutoff, learnable_rbf)
         self.interactions = nn.ModuleList(
@@ -191,12 +192,12 @@ class StudentForceField(nn.Module):
         if self.embedding.weight.dtype != torch.float32:
             raise RuntimeError("the CUDA path computes in float32; got " +
                                str(self.embedding.weight.dtype))
-        key = (dev, self.precision)
+        key = (dev, self.precision, self.filter_mode)
         if self._engine is None or self._engine_key != key:
             state = {k: v.detach().cpu().numpy() for k, v in self.state_dict().items()}
             if self._engine is not None:
                 self._engine.close()
-            self._engine = Engine(state, self.config, dev, self.precision)
+            self._engine = Engine(state, self.config, dev, self.precision, self.filter_mode)
             self._engine_key = key
         return self._engine
 

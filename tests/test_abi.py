@@ -30,14 +30,14 @@ def test_header_and_binding_agree(lib):
 
 
 def test_version_and_stage_names(lib):
-    assert lib.mlffd_version() == 1
+    assert lib.mlffd_version() == _lib.ABI_VERSION == 2
     names = [lib.mlffd_stage_name(i).decode() for i in range(_lib.NUM_STAGES)]
     assert names[:4] == ["neighbor", "embedding", "filter", "message_fwd"]
     assert lib.mlffd_stage_name(99) == b""
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_lib.MlffdConfig) == 24
+    assert ctypes.sizeof(_lib.MlffdConfig) == 28
     assert ctypes.sizeof(_lib.MlffdStatus) == 56
     assert ctypes.sizeof(_lib.MlffdProfile) == 8 + 8 * _lib.NUM_STAGES * 2
 
@@ -53,6 +53,10 @@ def test_bad_arguments_are_rejected_before_any_gpu_work(lib):
     rc = lib.mlffd_model_create(ctypes.byref(h), 0, ctypes.byref(cfg),
                                 blob.ctypes.data_as(ctypes.c_void_p), blob.size)
     assert rc == _lib.MLFFD_EINVAL and b"expected 427332" in lib.mlffd_last_error(None)
+    cfg = _lib.MlffdConfig(128, 20, 3, 100, 5.0, 0, 7)  # unknown filter mode
+    rc = lib.mlffd_model_create(ctypes.byref(h), 0, ctypes.byref(cfg),
+                                blob.ctypes.data_as(ctypes.c_void_p), blob.size)
+    assert rc == _lib.MLFFD_EINVAL and b"filter_mode" in lib.mlffd_last_error(None)
     assert lib.mlffd_workspace_reserve(None, 1, 1, 1) == _lib.MLFFD_EINVAL
 
 

@@ -104,6 +104,36 @@ def test_filter_table_matches_oracle(model_bundle):
         assert float((df.double().cpu() - jac).abs().max()) < 5e-5 * max(dscale, 1.0), l
 
 
+def test_filter_spline_matches_oracle(model_bundle):
+    """The per-model quintic B-spline of the filter (what the default message kernels evaluate from
+    shared memory) against the FP64 filter of the reference and its exact d-derivative.  The spline as a
+    function is within 2e-7 / 1e-5 per Angstrom of the filter (tests/test_spline_host.py, FP64 evaluation);
+    evaluated in FP32 on the device the stated bound is |f - spline| <= 2e-6 max(|f|, 1),
+    |f' - spline'| <= 2e-5 max(|f'|, 1) -- ten times tighter than what the filter-table kernels are held to."""
+    model, state, cfg = model_bundle
+    eng = model.engine()
+    w64 = po.to_torch_weights(state, torch.float64)
+    rc = cfg["cutoff"]
+    d = torch.cat([torch.linspace(0.05, rc, 6000), torch.tensor([rc, rc - 1e-6, 0.9572, 1e-3])]).float()
+    for l in range(cfg["num_interactions"]):
+        f, df = eng.filter_spline(l, d)
+        p = f"interactions.{l}.message.rbf_to_scalar."
+
+        def filt_fn(x):
+            rbf = po.edge_features(w64, torch.stack([x, torch.zeros_like(x), torch.zeros_like(x)], 1), rc)[2]
+            return torch.nn.functional.linear(
+                torch.nn.functional.silu(torch.nn.functional.linear(rbf, w64[p + "0.weight"], w64[p + "0.bias"])),
+                w64[p + "2.weight"], w64[p + "2.bias"])
+
+        dd = d.double()
+        filt, jac = torch.autograd.functional.jvp(filt_fn, dd, torch.ones_like(dd))
+        scale = max(float(filt.abs().max()), 1.0)
+        dscale = max(float(jac.abs().max()), 1.0)
+        assert float((f.double().cpu() - filt).abs().max()) < 2e-6 * scale, l
+        # at d == rc the reference's mask kills the derivative; the spline's one-sided derivative is ~1e-8
+        assert float((df.double().cpu() - jac).abs().max()) < 2e-5 * dscale, l
+
+
 def _oracle_stages(state, cfg, z, pos, off):
     w = po.to_torch_weights(state, torch.float64)
     e, f, keep = po.energy_and_forces_with_adjoints(
@@ -120,10 +150,18 @@ def test_stage_intermediates_and_adjoints_tensor_core():
     _stage_check("original", "tc")
 
 
-def _stage_check(variant, precision):
+def test_stage_intermediates_and_adjoints_filter_table(variant):
+    _stage_check(variant, "fp32", "table")
+
+
+def test_stage_intermediates_and_adjoints_filter_table_tensor_core():
+    _stage_check("original", "tc", "table")
+
+
+def _stage_check(variant, precision, filter_mode="spline"):
     os.environ["MLFFD_DEBUG_KEEP"] = "1"
     try:
-        model, state, cfg = _model(variant, precision=precision)
+        model, state, cfg = _model(variant, precision=precision, filter_mode=filter_mode)
         gold = load_golden(variant)
         case = "ragged"
         z, pos, off = gold[f"{case}_numbers"], gold[f"{case}_positions"], gold[f"{case}_offsets"]
@@ -148,7 +186,10 @@ def _stage_check(variant, precision):
         check("dist", geo[:, 3], keep["d"].detach(), 1e-6)
         pair = eng.debug_buffer("pair").long()[rev]
         for l in range(L):
-            filt = eng.debug_buffer("filter", l).reshape(-1, 3 * H)[pair]
+            if filter_mode == "table":
+                filt = eng.debug_buffer("filter", l).reshape(-1, 3 * H)[pair]
+            else:   # nothing per-pair is materialised: evaluate the spline the message kernels use
+                filt = eng.filter_spline(l, geo[:, 3].contiguous())[0]
             ref = keep[f"filter{l}"].detach().clone()
             if l == 0:  # vector gate b is skipped for layer 0 (v_in == 0)
                 filt = filt.clone(); filt[:, H:2 * H] = 0; ref[:, H:2 * H] = 0
@@ -174,7 +215,7 @@ def _stage_check(variant, precision):
         # oracle directly; forces cover it.
         check("forces", torch.from_numpy(f), f64, 2e-5)
         OUT.mkdir(exist_ok=True)
-        (OUT / f"stages_{variant}_{precision}.json").write_text(json.dumps(report, indent=1))
+        (OUT / f"stages_{variant}_{precision}_{filter_mode}.json").write_text(json.dumps(report, indent=1))
         bad = {k: v for k, v in report.items() if not v["ok"]}
         assert not bad, bad
     finally:
@@ -442,7 +483,7 @@ def test_staged_message_kernels_bit_identical(variant_name):
         env = {"MLFFD_MSG_TEAM": "0", **env}   # row-per-warp kernels whatever the batch size
         os.environ.update(env)
         try:
-            model, state, cfg = _model(variant_name)
+            model, state, cfg = _model(variant_name, filter_mode="table")
             model.engine()   # the context reads its MLFFD_* knobs when it is created
         finally:
             for k in env:
@@ -480,7 +521,7 @@ def test_message_kernel_variants_agree(variant_name):
         env = {"MLFFD_MSG_TEAM": "0", **env}   # row-per-warp kernels whatever the batch size
         os.environ.update(env)
         try:
-            model, state, cfg = _model(variant_name)
+            model, state, cfg = _model(variant_name, filter_mode="table")
             model.engine()
         finally:
             for k in env:
@@ -544,7 +585,8 @@ LOOSE_BOUNDS = {            # (eV / atom, eV / A) against the reference's FP64 o
 @pytest.mark.parametrize("variant_name", ["original", "tiny"])
 def test_single_pass_tensor_core_modes_within_stated_bounds(variant_name, mode):
     e_tol, f_tol = LOOSE_BOUNDS[mode]
-    model, state, cfg = _model(variant_name, precision=mode)
+    # the single-pass products act on the dense filter layers: those run per step in table mode only
+    model, state, cfg = _model(variant_name, precision=mode, filter_mode="table")
     gold = load_golden(variant_name)
     worst_e = worst_f = 0.0
     for case in golden_cases(gold):
@@ -647,8 +689,8 @@ def test_team_message_kernels_match_row_per_warp_kernels(variant_name):
     # rattled: on the exact mirror-symmetric chain the vector features cancel to rounding noise and
     # d|v|/dv is arbitrary, so any change of summation order moves the forces
     pos = (pos + np.random.default_rng(21).normal(0.0, 0.05, pos.shape)).astype(np.float32)
-    team, state, cfg = _with_env({"MLFFD_MSG_TEAM": "4"}, variant_name)
-    rows, _, _ = _with_env({"MLFFD_MSG_TEAM": "0"}, variant_name)
+    team, state, cfg = _with_env({"MLFFD_MSG_TEAM": "4"}, variant_name, filter_mode="table")
+    rows, _, _ = _with_env({"MLFFD_MSG_TEAM": "0"}, variant_name, filter_mode="table")
     e_t, f_t = _run(team, z, pos, off)
     e_t2, f_t2 = _run(team, z, pos, off)
     e_r, f_r = _run(rows, z, pos, off)
