@@ -53,7 +53,15 @@ def parse_args():
     ap.add_argument("--filter-mode", choices=["spline", "table"], default="spline",
                     help="spline = per-model filter splines evaluated in the message kernels (default); "
                          "table = per-step [P,3H] filter tables in HBM")
+    ap.add_argument("--mode", choices=["batch", "sweep"], default="batch",
+                    help="batch = the headline: C2, one 1024-structure batch per GPU per step (weak scaling). "
+                         "sweep = BASELINE config 5: ONE host-side list of ragged structures (n ~ U{20..80}) partitioned "
+                         "over the ranks, staged, evaluated and gathered back in input order (strong scaling)")
+    ap.add_argument("--sweep-structures", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the records measured outside the C2 timed region (md: C1/C3/C4 single-trajectory latency, "
+                         "variants: Tiny / Ultra-tiny on C2 shapes)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -70,7 +78,9 @@ def workload_config(args, world):
                         f"energy+forces, PaiNN student '{args.variant}'",
             "variant": args.variant, "precision": args.precision, "structures_per_gpu": args.batch, "atoms_per_structure": args.atoms,
             "global_batch": args.batch * world, "parallelism": f"structure-sharded x{world}, no collective",
-            "l2_policy": "per-step working set (filter tables + features, >4 GB) exceeds the 126 MB L2; "
+            "filter_mode": args.filter_mode,
+            "l2_policy": "per-step working set (per-layer feature / adjoint rows, edge records and edge-adjoint slabs: "
+                         "> 1 GB; with --filter-mode table > 4 GB) exceeds the 126 MB L2; "
                          f"{POSITION_SETS} rotating perturbed input sets"}
 
 
@@ -87,8 +97,10 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------
 # algorithmic work per step (SURVEY 8d per-unit figures)
 # ------------------------------------------------------------------------------------------
-def algorithmic_work(N, E, P, H, K, L):
+def algorithmic_work(N, E, P, H, K, L, filter_mode="table"):
     w = {}
+    if filter_mode == "spline":
+        return algorithmic_work_spline(N, E, P, H, K, L)
     f_flops = f_bytes = 0
     for l in range(L):
         nout = 2 * H if l == 0 else 3 * H           # layer 0 never reads the b gate (v_in = 0)
@@ -127,6 +139,29 @@ def algorithmic_work(N, E, P, H, K, L):
     w["force"] = {"flops": E * 40, "bytes": E * (4 + 16 + 16 * L) + N * 12}   # rev, geo, L adjoint slabs
     w["embedding"] = {"flops": 0, "bytes": N * (4 + 2 * H * 4)}
     w["energy_sum"] = {"flops": N, "bytes": N * 4}
+    return w
+
+
+def algorithmic_work_spline(N, E, P, H, K, L):
+    """Spline filter mode: nothing per-pair exists in HBM.  Message kernels: compulsory
+    HBM bytes as BASELINE.md section 4 defines them (feature rows in and out once, per-edge records once per
+    channel slice) and, because that is not what bounds them, the L1 / shared-memory data-pipe wavefronts
+    (128 B each) they issue per directed edge and 32-channel slice: 6 spline knots x 3 filter components of
+    LDS.128 (layer 0: x 2), the neighbour gathers and the edge-record reads."""
+    w = algorithmic_work(N, E, P, H, K, L, "table")
+    slices = H // 32
+    w["filter"] = {"flops": E * 60, "bytes": E * (4 + 16 + 64)}   # spline_basis_kernel: col + geo in, 4 x float4 record out
+    mf_b = mb_b = mf_w = mb_w = 0
+    for l in range(L):
+        feat = (1 if l == 0 else 4) * H * 4                      # s (+ v) row of an atom
+        mf_b += slices * E * 48 + N * (feat + 4 * H * 4 + feat)   # records (3 entries) per slice; own row in, row out
+        mb_b += slices * E * (64 + 16) + N * (4 * H * 4 + (0 if l == 0 else 4 * H * 4 + 4 * H * 4))
+        lds = 12 if l == 0 else 18
+        mf_w += E * slices * (lds + (1 if l == 0 else 4) + 3)
+        mb_w += E * slices * (lds + (1 if l == 0 else 8) + 4 + 1)
+    w["message_fwd"] = {"flops": w["message_fwd"]["flops"] + E * L * 3 * H * 12, "bytes": mf_b, "l1_wavefronts": mf_w}
+    w["message_bwd"] = {"flops": w["message_bwd"]["flops"] + E * L * 3 * H * 24, "bytes": mb_b, "l1_wavefronts": mb_w}
+    w["force"] = {"flops": E * 40, "bytes": E * (4 + 16 + 2 * 16 * L * slices) + N * 12}   # rev, geo, L x slices adjoint slabs of e and rev(e)
     return w
 
 
@@ -195,22 +230,37 @@ def cpu_chunk_runner(args):
         z, pos, off = synthetic.concatenate(structs)
         e, f = po.energy_and_forces(w, torch.from_numpy(z), torch.from_numpy(pos.astype(np.float32)),
                                     cfg["cutoff"], po.batch_from_offsets(off))
-        return float(e.sum()), f
+        return e.numpy().astype(np.float64), f.numpy().astype(np.float64)
 
     return run_chunk, torch.get_num_threads()
 
 
-def cpu_baseline(args):
+def cpu_baseline(args, gpu_reference=None):
+    """Times the CPU restatement of the reference on a bounded sample of the workload and -- with the
+    GPU energies / forces of the same (unperturbed) structures in ``gpu_reference`` -- turns the outputs it
+    computes anyway into the ``parity`` record of the JSON line."""
     run_chunk, threads = cpu_chunk_runner(args)
     run_chunk(0)  # warm-up
     done, t0 = 0, time.perf_counter()
+    max_de = max_df = 0.0
     while time.perf_counter() - t0 < args.cpu_seconds and done < args.batch:
-        run_chunk(done)
+        e, f = run_chunk(done)
+        if gpu_reference is not None:
+            e_gpu, f_gpu = gpu_reference
+            a0 = done * args.atoms
+            max_de = max(max_de, float(np.max(np.abs(e - e_gpu[done:done + REFERENCE_CHUNK])) / args.atoms))
+            max_df = max(max_df, float(np.max(np.abs(f - f_gpu[a0:a0 + f.shape[0]]))))
         done += REFERENCE_CHUNK
     dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
+    base = {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"first {done} structures of the workload in chunks of {REFERENCE_CHUNK} "
                       f"(oracle/painn_oracle.py = torch CPU restatement of the reference, autograd forces), {dt:.1f} s"}
+    parity = None
+    if gpu_reference is not None:
+        parity = {"structures": done, "max_dE_per_atom_eV": max_de, "max_dF_eV_per_A": max_df,
+                  "tol_dE_per_atom_eV": 1e-5, "tol_dF_eV_per_A": 1e-4, "ok": bool(max_de <= 1e-5 and max_df <= 1e-4),
+                  "against": "CPU restatement of the reference (FP32) on the first structures of the C2 batch, unperturbed inputs"}
+    return base, parity
 
 
 def run_reference(args):
@@ -235,6 +285,206 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+
+# ------------------------------------------------------------------------------------------
+# records measured OUTSIDE the C2 timed region (the second half of BASELINE.json's metric and the
+# other model variants): single-trajectory MD latency for C1 / C3 / C4 and Tiny / Ultra-tiny on C2
+# ------------------------------------------------------------------------------------------
+def md_record(args, dev):
+    """us/step and ns/day at 0.5 fs for C1 (H2O), C3 (300-atom chain), C4 (9 999-atom periodic water box,
+    neighbour list rebuilt every step): through StudentForceFieldCalculator.calculate() in a host
+    velocity-Verlet loop (what an ASE MD loop does) and with the integrator on the device."""
+    import torch
+    from mlff_distiller_b200 import md, synthetic
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+
+    def run_case(atoms, temperature, host_steps, device_steps, pbc_mode="ignore", cell=None, pbc=None):
+        calc = StudentForceFieldCalculator(ROOT / "tests" / "golden" / VARIANT_FILES["original"], device=str(dev),
+                                          precision=args.precision, filter_mode=args.filter_mode, pbc_mode=pbc_mode)
+        masses = atoms.get_masses()
+        v0 = md.maxwell_boltzmann(masses, temperature, np.random.default_rng(42), atoms.get_positions(), zero_rotation=True)
+        work = atoms.copy()
+
+        def force_fn(x):
+            work.set_positions(x)
+            calc.calculate(work, ["energy", "forces"])
+            return calc.results["energy"], calc.results["forces"]
+
+        for _ in range(3):   # workspace sizing, then graph capture on the fourth call for the system
+            force_fn(atoms.get_positions() + 1e-6)
+            force_fn(atoms.get_positions())
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        host = md.velocity_verlet(force_fn, atoms.get_positions(), v0, masses, host_steps, 0.5)
+        host_dt = time.perf_counter() - t0
+        sim = md.DeviceMD(calc.model, atoms.numbers, atoms.get_positions(), v0, masses, 0.5, cell=cell, pbc=pbc)
+        sim.run(20)          # graph capture + warm-up (part of the trajectory)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        out = sim.run(device_steps - 20)
+        dev_dt = time.perf_counter() - t0
+        sps_h, sps_d = host_steps / host_dt, (device_steps - 20) / dev_dt
+        return {"atoms": len(atoms), "edges": int(calc.model.engine().status().num_edges),
+                "calculate": {"steps": host_steps, "us_per_step": 1e6 / sps_h, "ns_per_day": md.ns_per_day(sps_h),
+                              "drift_percent": host["drift_percent"]},
+                "on_device": {"steps": device_steps, "us_per_step": 1e6 / sps_d, "ns_per_day": md.ns_per_day(sps_d),
+                              "drift_percent": out["drift_percent"]}}
+
+    rec = {"dt_fs": 0.5, "ns_per_day_formula": "steps/s * dt_fs * 86400 * 1e-6"}
+    rec["C1_h2o"] = run_case(synthetic.water(), 300.0, 1000, 1000)
+    chain = synthetic.alkane_chain(100)
+    chain.positions = chain.positions + np.random.default_rng(8).normal(0.0, 0.02, chain.positions.shape)
+    rec["C3_chain300"] = run_case(chain, 300.0, 1000, 1000)
+    box = synthetic.water_box()
+    rec["C4_water_box_10k"] = run_case(box, 300.0, 20, 120, pbc_mode="minimum_image", cell=box.cell, pbc=box.pbc)
+    rec["C4_water_box_10k"]["note"] = ("raw random-orientation box (max |F| ~ 36 eV/A): the step time is the figure, "
+                                       "the drift of such a start is not meaningful")
+    return rec
+
+
+def variants_record(args, dev, steps=20):
+    """Tiny and Ultra-tiny on the same C2 shapes, device-resident structures/s (BASELINE config 5 names them)."""
+    import torch
+    from mlff_distiller_b200 import synthetic
+    from mlff_distiller_b200.student_model import StudentForceField
+    structs = synthetic.druglike_batch(args.batch, first=0, n=args.atoms)
+    numbers, pos64, offsets = synthetic.concatenate(structs)
+    z_d = torch.from_numpy(numbers.astype(np.int32)).to(dev)
+    off_d = torch.from_numpy(offsets.astype(np.int32)).to(dev)
+    rng = np.random.default_rng(99)
+    pos_d = [torch.from_numpy((pos64 + rng.normal(0.0, 0.01, pos64.shape)).astype(np.float32)).to(dev) for _ in range(POSITION_SETS)]
+    out = {}
+    for variant in ("tiny", "ultra_tiny"):
+        model = StudentForceField.load(ROOT / "tests" / "golden" / VARIANT_FILES[variant], device=str(dev),
+                                       precision=args.precision, filter_mode=args.filter_mode)
+        eng = model.engine()
+        B, N = len(structs), len(numbers)
+        energy = torch.empty(B, dtype=torch.float32, device=dev)
+        forces = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        model.energy_and_forces_packed(z_d, pos_d[0], off_d, B)
+        for i in range(3):
+            eng.energy_forces_async(z_d, pos_d[i % POSITION_SETS], off_d, B, energy, forces)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        a.record()
+        for i in range(steps):
+            eng.energy_forces_async(z_d, pos_d[i % POSITION_SETS], off_d, B, energy, forces)
+        b.record()
+        torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b) / steps
+        out[variant] = {"structures_per_s": B / (ms * 1e-3), "ms_per_step": ms, "steps": steps}
+    return out
+
+
+
+# ------------------------------------------------------------------------------------------
+# sweep mode (BASELINE config 5): strong scaling of one host-side structure list
+# ------------------------------------------------------------------------------------------
+def _sweep_chunk(job):
+    first, count = job
+    from mlff_distiller_b200 import synthetic
+    structs = synthetic.druglike_batch(count, first=first, ragged=True)
+    numbers, pos, offsets = synthetic.concatenate(structs)
+    return first, numbers.astype(np.int16), pos.astype(np.float32), np.diff(offsets).astype(np.int32)
+
+
+def sweep_shard(first, count, workers):
+    """This rank's contiguous shard of the global list, generated by a pool of host processes."""
+    from concurrent.futures import ProcessPoolExecutor
+    jobs = [(a, min(512, first + count - a)) for a in range(first, first + count, 512)]
+    if workers <= 1 or len(jobs) <= 1:
+        parts = [_sweep_chunk(j) for j in jobs]
+    else:
+        with ProcessPoolExecutor(max_workers=workers) as pool:
+            parts = list(pool.map(_sweep_chunk, jobs))
+    parts.sort(key=lambda p: p[0])
+    return (np.concatenate([p[1] for p in parts]).astype(np.int64), np.concatenate([p[2] for p in parts]).astype(np.float64),
+            np.concatenate([p[3] for p in parts]).astype(np.int64))
+
+
+def run_sweep(args):
+    import torch
+    import torch.distributed as dist
+    from mlff_distiller_b200 import sharding
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a GPU (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    total = args.sweep_structures
+    # every rank derives the global size list (the shards are a pure function of it) and generates its own shard
+    sizes = np.array([int(np.random.default_rng(500000 + s).integers(20, 81)) for s in range(total)], dtype=np.int64)
+    a, b = sharding.shard_slice(sizes, rank, world)
+    numbers, pos, counts = sweep_shard(a, b - a, max(1, (os.cpu_count() or 2) // world))
+    assert np.array_equal(counts, sizes[a:b])
+    calc = StudentForceFieldCalculator(ROOT / "tests" / "golden" / VARIANT_FILES[args.variant], device=str(dev),
+                                      precision=args.precision, filter_mode=args.filter_mode)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    warm = max(1, min(int(np.searchsorted(offs, calc.max_atoms_per_call, side="right")) - 1, len(counts)))
+    for _ in range(2):   # sizes the workspace, the pinned staging and (N > 1) the gather buffers
+        calc.evaluate_arrays(numbers[: offs[warm]], pos[: offs[warm]], counts[:warm])
+    if world > 1:
+        sharding.gather_in_order(np.zeros(b - a, np.float32), np.zeros((int(counts.sum()), 3), np.float32), sizes, device=dev)
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng = calc.model.engine()
+    eng.profile_enable(False)
+    reps = max(1, args.steps // 25)     # one pass is a whole sweep; the default K = 100 gives 4 passes
+    times, t_eval = [], []
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        e, f = calc.evaluate_arrays(numbers, pos, counts)           # H2D, steps and D2H of every micro-batch
+        t1 = time.perf_counter()
+        if world > 1:
+            e_all, f_all = sharding.gather_in_order(e, f, sizes, device=dev)   # ordered gather of energies and forces
+        else:
+            e_all, f_all = e, f
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([time.perf_counter() - t0, t1 - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        times.append(float(dt[0].item()))
+        t_eval.append(float(dt[1].item()))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.profile_read()["launches"]
+    assert len(e_all) == total and len(f_all) == int(sizes.sum())
+    if rank == 0:
+        best = int(np.argmin(times))
+        value = total / times[best]
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": reps, "warmup": 2,
+               "ms_per_step": 1e3 * times[best], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"C5: screening sweep of {total} ragged drug-like structures (n ~ U{{20..80}}, "
+                                      f"{int(sizes.sum())} atoms), energy+forces, PaiNN student '{args.variant}', ONE host-side "
+                                      "list partitioned over the ranks by atom count, results gathered in input order",
+                          "variant": args.variant, "precision": args.precision, "filter_mode": args.filter_mode,
+                          "parallelism": f"structure-sharded x{world}; data path without collective, one ordered "
+                                         "all_gather of energies + forces at the end",
+                          "l2_policy": "every micro-batch is new data (>100 MB of inputs and results per pass)"},
+               "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(16 * sizes.sum() + 4 * total),
+                       "d2h_bytes_per_step": int(12 * sizes.sum() + 4 * total),
+                       "api": "StudentForceFieldCalculator.evaluate_arrays(host arrays) per rank + sharding.gather_in_order"},
+               "gpu_launches": launches, "clocks": clocks,
+               "phases_s": {"evaluate_max_over_ranks": t_eval[best], "ordered_gather": times[best] - t_eval[best]},
+               "all_pass_seconds": times,
+               "energy_checksum": float(np.asarray(e_all, dtype=np.float64).sum())}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------
@@ -355,6 +605,31 @@ def run_b200(args):
     e2e_value = world * B * args.steps / timed(run_stream)
     blocking_steps = max(3, min(args.steps, 30))
     e2e_blocking = world * B * blocking_steps / timed(run_blocking)
+
+    # (c) the reference's own batched entry point: calculate_batch(list of 1024 structure objects)
+    #     (inference/ase_calculator.py:590-645): per-object marshalling, validation, H2D, step, D2H and
+    #     the per-structure result dicts are all inside the timed region
+    atom_lists = []
+    for k in range(min(POSITION_SETS, 2)):
+        lst = [s.copy() for s in structs]
+        for s_obj, lo, hi in zip(lst, offsets[:-1], offsets[1:]):
+            s_obj.set_positions(pos_sets64[k][lo:hi])
+        atom_lists.append(lst)
+    calc.calculate_batch(atom_lists[0])
+    batch_steps = max(3, min(args.steps, 20))
+    last = [None]
+
+    def run_calculate_batch():
+        for i in range(batch_steps):
+            last[0] = calc.calculate_batch(atom_lists[i % len(atom_lists)])
+
+    e2e_calculate_batch = world * B * batch_steps / timed(run_calculate_batch)
+    assert len(last[0]) == B and last[0][0]["forces"].shape == (int(counts[0]), 3)
+
+    # parity at the benchmarked size: one evaluation of the UNPERTURBED batch, compared below with what the
+    # CPU baseline computes for the same structures
+    e_chk, f_chk = model.energy_and_forces_packed(z_d, torch.from_numpy(pos64.astype(np.float32)).to(dev), off_d, B)
+    gpu_reference = (e_chk.double().cpu().numpy(), f_chk.double().cpu().numpy())
     h2d = world * (4 * N + 12 * N + 4 * (B + 1))   # numbers i32 + positions f32 + offsets i32, all ranks
     d2h = world * (4 * B + 12 * N)                 # energies f32 + forces f32, all ranks
 
@@ -365,7 +640,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel ----
     peaks = measured_peaks()
-    work = algorithmic_work(N, E, P, cfg.hidden_dim, cfg.num_rbf, cfg.num_interactions)
+    work = algorithmic_work(N, E, P, cfg.hidden_dim, cfg.num_rbf, cfg.num_interactions, args.filter_mode)
     stages = {}
     for name, s in prof["stages"].items():
         if s["launches"] == 0:
@@ -381,6 +656,8 @@ def run_b200(args):
     # the roofline that bounds the kernel is the SLOWER of (FLOPs / tensor peak) and (bytes / HBM peak)
     t_tensor = work[top]["flops"] / (peaks["bf16_tflops"] * 1e12)
     t_hbm = work[top]["bytes"] / (peaks["hbm_gbs"] * 1e9)
+    if args.filter_mode == "spline":
+        COMPUTE_BOUND.discard("filter")
     if top in COMPUTE_BOUND and t_tensor >= t_hbm:
         achieved, peak, unit, bound = stages[top]["TFLOPs"], peaks["bf16_tflops"], "TFLOP/s", "tensor"
     else:
@@ -396,6 +673,19 @@ def run_b200(args):
                 "share_of_step": stages[top]["ms_per_step"] / profiled_ms_per_step,
                 "stage_timing": "live CUDA events after every kernel, same K steps run a second time "
                                 f"({profiled_ms_per_step:.3f} ms/step with the events)"}
+    if "l1_wavefronts" in work[top] and clocks and clocks.get("sm_mhz"):
+        # what bounds the spline message kernels: the SM's L1 / shared-memory data pipe, one 128-byte
+        # wavefront per clock (ncu: l1tex__data_pipe_lsu_wavefronts ~ 70 - 80 % of peak, profiles/)
+        wf_per_s = work[top]["l1_wavefronts"] / (stages[top]["ms_per_step"] * 1e-3)
+        peak_wf = 148 * clocks["sm_mhz"] * 1e6
+        roofline["on_chip"] = {"bound": "L1 / shared-memory data pipe (128 B wavefront per clock per SM)",
+                               "wavefronts_per_step": work[top]["l1_wavefronts"], "achieved_per_s": wf_per_s,
+                               "peak_per_s": peak_wf, "frac": wf_per_s / peak_wf,
+                               "sm_mhz_used": clocks["sm_mhz"],
+                               "note": "algorithmic wavefronts: 6 knots x 3 components of LDS.128 per directed edge and "
+                                       "32-channel slice (layer 0: x 2) + neighbour gathers + edge records"}
+    roofline["compulsory_bytes_accounting"] = "BASELINE.md section 4 (2 N 16H + per-edge records per layer), nothing per pair in HBM" \
+        if args.filter_mode == "spline" else "filter-table rows once per pair + per-edge indices + feature rows once"
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -408,13 +698,22 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "StudentForceFieldCalculator.evaluate_stream (host arrays in, host arrays out, two steps in flight)",
                 "blocking_call_value": e2e_blocking,
-                "blocking_api": "StudentForceFieldCalculator.evaluate_arrays, one step at a time"},
+                "blocking_api": "StudentForceFieldCalculator.evaluate_arrays, one step at a time",
+                "calculate_batch_value": e2e_calculate_batch,
+                "calculate_batch_api": "StudentForceFieldCalculator.calculate_batch(list of structure objects) -> list of "
+                                       "result dicts, the reference's batched entry point (inference/ase_calculator.py:590-645)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "stages": stages, "graph": {"atoms": N, "edges": E, "pairs": P},
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args)
+        out["cpu_baseline"], out["parity"] = cpu_baseline(args, gpu_reference if args.atoms * B == N else None)
+    if world == 1 and not args.no_extras:
+        out["md"] = md_record(args, dev)
+        if args.variant == "original":
+            out["variants"] = variants_record(args, dev)
     print(json.dumps(out))
+    if out.get("parity") is not None and not out["parity"]["ok"]:
+        raise SystemExit(f"parity check failed at the benchmarked size: {out['parity']}")
     if world > 1:
         dist.destroy_process_group()
 
@@ -431,6 +730,8 @@ def main():
         with contextlib.redirect_stdout(buf):
             if args.impl == "reference":
                 run_reference(args)
+            elif args.mode == "sweep":
+                run_sweep(args)
             else:
                 run_b200(args)
     finally:

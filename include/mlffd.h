@@ -85,8 +85,9 @@ typedef struct mlffd_status {
     int32_t max_degree;
     int64_t overflow_events; /* sticky count of overflowed builds since mlffd_model_create (lets a
                                 caller that enqueues many steps, e.g. on-device MD, detect one) */
-    int32_t hint_violation;  /* 1: a structure was larger than mlffd_set_structure_hint promised;
-                                outputs invalid -> clear the hint (0) and call again */
+    int32_t tc_saturated;    /* 1: an operand of a tensor-core dense layer left the FP16 range in this step
+                                (|activation| >= 8 125): energies / forces invalid -> call
+                                mlffd_set_dense_fallback(ctx, 1) and evaluate again */
     int32_t reserved;
 } mlffd_status;
 
@@ -162,20 +163,22 @@ int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out);
  * `stream` a copy of the device status words of the step enqueued just before it into
  * `status_out`, six int32 in pinned host (or device) memory:
  *   [0] num_edges  [1] num_pairs  [2] overflow  [3] max_degree  [4] overflow_events (sticky)
- *   [5] hint_violation
+ *   [5] tc_saturated
  * Valid once the stream has passed this point (record an event after the call).  Never synchronises.
  */
 int mlffd_status_async(mlffd_ctx* ctx, int32_t* status_out, void* stream);
 
 /*
- * Optional promise that no structure of the coming calls has more than this many atoms (0 =
- * unknown, the default).  With small structures (<= 113 atoms at H = 128) the message kernels
- * switch to a structure-per-block variant that stages the structure's feature rows in shared
- * memory (results are bit-identical).  The batched-structure interface of the reference
- * (inference/ase_calculator.py:647-706) knows the atom counts on the host, so the calculator
- * passes max(counts).  A violated promise is detected on the device (mlffd_status.hint_violation).
+ * Range guard of the tensor-core precisions.  MLFFD_PREC_TC_FP16X2 / _TC_FP16 split operands into FP16
+ * terms after a power-of-two pre-scale (activations x 2^3, weights x 2^8): an activation or adjoint with
+ * |x| >= 8 125 (unphysically dense inputs; the reference aggregates un-normalised neighbour sums) would
+ * round to infinity.  Weights are checked once in mlffd_model_create (a model whose max|w| >= 253 keeps
+ * its dense layers on the FP32 FFMA kernels); activations are checked by the kernels that split them,
+ * which raise mlffd_status.tc_saturated.  enable = 1 makes every later call run the dense layers on the
+ * FP32 FFMA kernels (the MLFFD_PREC_FP32 arithmetic) whatever `precision` says; 0 restores the tensor
+ * cores.  The reference has no counterpart (it computes in FP32 throughout).
  */
-int mlffd_set_structure_hint(mlffd_ctx* ctx, int32_t max_atoms_per_structure);
+int mlffd_set_dense_fallback(mlffd_ctx* ctx, int32_t enable);
 
 /*
  * Stage entry point (parity tests, ncu): evaluate the per-layer radial filter and its
@@ -185,6 +188,24 @@ int mlffd_set_structure_hint(mlffd_ctx* ctx, int32_t max_atoms_per_structure);
  */
 int mlffd_filter_table(mlffd_ctx* ctx, int32_t layer, const float* dist_d, int64_t num_pairs,
                        float* filter_d, float* dfilter_d, void* stream);
+
+/*
+ * Operator-level drop-ins for the reference's two Triton kernels (stateless: no context; device pointers).
+ *
+ * mlffd_edge_features replaces fused_edge_features_triton(positions, edge_index, eps)
+ * (kernels/fused_edge_features.py:99-162):  edge_index_d [2,E] i64 (row 0 = src, row 1 = dst) ->
+ *   edge_vec_d [E,3] = pos[src] - pos[dst],  dist_d [E],  unit_d [E,3].
+ *   eps_mode 0: d = |r|, u = r / (d + eps)          the model's own placement (student_model.py:712-715)
+ *   eps_mode 1: d = sqrt(|r|^2 + eps), u = r / d    the Triton kernel's placement (fused_edge_features.py:77-82)
+ * mlffd_rbf_cutoff replaces fused_rbf_cutoff_triton(distances, centers, gamma, r_cut)
+ * (kernels/fused_rbf_cutoff.py:90-134):  out_d [E,K] = exp(-gamma (d - mu_k)^2) * 0.5 (cos(pi d / rc) + 1) [d < rc].
+ * On the product path both are fused into the neighbour fill pass and the filter evaluation; these exports
+ * serve callers of the reference's kernel-level API and the stage parity tests.
+ */
+int mlffd_edge_features(const float* pos_d, const int64_t* edge_index_d, int64_t num_edges, float eps,
+                        int32_t eps_mode, float* edge_vec_d, float* dist_d, float* unit_d, void* stream);
+int mlffd_rbf_cutoff(const float* dist_d, int64_t num_edges, const float* centers_d, int32_t num_rbf,
+                     float gamma, float cutoff, float* out_d, void* stream);
 
 /*
  * Stage entry point (parity tests): the same quantities as mlffd_filter_table, evaluated from the
@@ -259,10 +280,14 @@ int mlffd_virial(mlffd_ctx* ctx, const int32_t* offsets_d, int32_t num_structure
  * dt in ASE time units (fs * 0.0982269...).  The three calls are graph-capturable.
  *   kick_drift : v += dt/2 F/m ; x += dt v ; pos32 = float(x)
  *   kick_energy: v += dt/2 F/m ; series[*counter] = (sum_b E_b, sum m v^2/2) ; ++*counter
+ * `guard` (may be NULL) is the context whose mlffd_energy_forces supplies the forces: when its last force
+ * evaluation failed on the device (mlffd_status.overflow or .tc_saturated), both calls do nothing, so a
+ * trajectory enqueued many steps ahead freezes at the valid mid-step state (x_k, v_{k-1/2}) of the failing
+ * step: reserve more edges / mlffd_set_dense_fallback, evaluate the forces again, call kick_energy, go on.
  */
-int mlffd_md_kick_drift(int64_t num_atoms, double* pos_d, double* vel_d, const float* forces_d,
+int mlffd_md_kick_drift(const mlffd_ctx* guard, int64_t num_atoms, double* pos_d, double* vel_d, const float* forces_d,
                         const double* inv_mass_d, double dt, float* pos32_d, void* stream);
-int mlffd_md_kick_energy(int64_t num_atoms, double* vel_d, const float* forces_d,
+int mlffd_md_kick_energy(const mlffd_ctx* guard, int64_t num_atoms, double* vel_d, const float* forces_d,
                          const double* inv_mass_d, double dt, const float* energy_d,
                          int32_t num_structures, double* series_d, int32_t* counter_d,
                          int32_t capacity, void* stream);

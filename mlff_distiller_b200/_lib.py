@@ -17,7 +17,7 @@ from typing import List, Optional
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libmlffd.so"
 SOURCES = ["mlffd.cu"]
-HEADERS = ["common.cuh", "neighbor.cuh", "cell_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh", "message_pipe.cuh", "message_team.cuh", "message_staged.cuh", "message_spline.cuh", "spline_table.h",
+HEADERS = ["common.cuh", "edge_features.cuh", "neighbor.cuh", "cell_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh", "message_pipe.cuh", "message_team.cuh", "message_spline.cuh", "spline_table.h",
            "update.cuh", "readout.cuh", "md.cuh", "../../include/mlffd.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -28,8 +28,8 @@ EXPORTS = [
     "mlffd_workspace_reserve", "mlffd_neighbor_list", "mlffd_export_edges",
     "mlffd_energy_forces", "mlffd_get_status", "mlffd_filter_table", "mlffd_debug_buffer",
     "mlffd_profile_enable", "mlffd_profile_read", "mlffd_stage_name",
-    "mlffd_md_kick_drift", "mlffd_md_kick_energy", "mlffd_set_structure_hint", "mlffd_virial",
-    "mlffd_status_async", "mlffd_filter_spline",
+    "mlffd_md_kick_drift", "mlffd_md_kick_energy", "mlffd_set_dense_fallback", "mlffd_virial",
+    "mlffd_status_async", "mlffd_filter_spline", "mlffd_edge_features", "mlffd_rbf_cutoff",
 ]
 NUM_STAGES = 10
 
@@ -50,7 +50,7 @@ class MlffdStatus(ctypes.Structure):
     _fields_ = [("num_atoms", ctypes.c_int64), ("num_edges", ctypes.c_int64),
                 ("num_pairs", ctypes.c_int64), ("edge_capacity", ctypes.c_int64),
                 ("overflow", ctypes.c_int32), ("max_degree", ctypes.c_int32),
-                ("overflow_events", ctypes.c_int64), ("hint_violation", ctypes.c_int32),
+                ("overflow_events", ctypes.c_int64), ("tc_saturated", ctypes.c_int32),
                 ("reserved", ctypes.c_int32)]
 
 
@@ -135,6 +135,10 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     lib.mlffd_filter_table.argtypes = [vp, i32, vp, i64, vp, vp, vp]
     lib.mlffd_filter_spline.restype = ctypes.c_int
     lib.mlffd_filter_spline.argtypes = [vp, i32, vp, i64, vp, vp, vp]
+    lib.mlffd_edge_features.restype = ctypes.c_int
+    lib.mlffd_edge_features.argtypes = [vp, vp, i64, ctypes.c_float, i32, vp, vp, vp, vp]
+    lib.mlffd_rbf_cutoff.restype = ctypes.c_int
+    lib.mlffd_rbf_cutoff.argtypes = [vp, i64, vp, i32, ctypes.c_float, ctypes.c_float, vp, vp]
     lib.mlffd_debug_buffer.restype = ctypes.c_int
     lib.mlffd_debug_buffer.argtypes = [vp, ctypes.c_char_p, i32, ctypes.POINTER(vp),
                                        ctypes.POINTER(i64), ctypes.POINTER(i32)]
@@ -144,15 +148,15 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     lib.mlffd_profile_read.argtypes = [vp, ctypes.POINTER(MlffdProfile)]
     lib.mlffd_stage_name.restype = ctypes.c_char_p
     lib.mlffd_stage_name.argtypes = [i32]
-    lib.mlffd_set_structure_hint.restype = ctypes.c_int
-    lib.mlffd_set_structure_hint.argtypes = [vp, i32]
+    lib.mlffd_set_dense_fallback.restype = ctypes.c_int
+    lib.mlffd_set_dense_fallback.argtypes = [vp, i32]
     lib.mlffd_virial.restype = ctypes.c_int
     lib.mlffd_virial.argtypes = [vp, vp, i32, vp, vp]
     f64 = ctypes.c_double
     lib.mlffd_md_kick_drift.restype = ctypes.c_int
-    lib.mlffd_md_kick_drift.argtypes = [i64, vp, vp, vp, vp, f64, vp, vp]
+    lib.mlffd_md_kick_drift.argtypes = [vp, i64, vp, vp, vp, vp, f64, vp, vp]
     lib.mlffd_md_kick_energy.restype = ctypes.c_int
-    lib.mlffd_md_kick_energy.argtypes = [i64, vp, vp, vp, f64, vp, i32, vp, vp, i32, vp]
+    lib.mlffd_md_kick_energy.argtypes = [vp, i64, vp, vp, vp, f64, vp, i32, vp, vp, i32, vp]
     if lib.mlffd_version() != ABI_VERSION:
         raise RuntimeError("libmlffd.so ABI version mismatch; rebuild it")
     _lib = lib

@@ -83,9 +83,15 @@ class StudentForceFieldCalculator(_AseCalculator):
                  jit_path: Optional[Union[str, Path]] = None, use_torch_cluster: bool = True,
                  use_analytical_forces: bool = False, *, precision: str = "tc",
                  pbc_mode: str = "ignore", use_graph: bool = True, filter_mode: str = "spline",
-                 **kwargs):
+                 device_ids: Optional[Sequence[int]] = None, **kwargs):
         super().__init__(**kwargs)
         self.checkpoint_path = Path(checkpoint_path)
+        # device_ids=[0, 1, ...]: ONE process drives several GPUs: this instance owns the
+        # first device, one replica (own context, streams and pinned staging) each further one; batched calls
+        # split their structure list by atom count over the devices, no collective, results in input order
+        self.device_ids = [int(i) for i in device_ids] if device_ids else None
+        if self.device_ids:
+            device = f"cuda:{self.device_ids[0]}"
         self.device = torch.device(device)
         self.dtype = dtype
         self.enable_stress = enable_stress
@@ -117,6 +123,15 @@ class StudentForceFieldCalculator(_AseCalculator):
         self._total_time = 0.0
         self._call_times: List[float] = []
         self._numbers_cache = None  # per-system device / pinned buffers and captured graphs of the single path
+        self._replicas = None
+        if self.device_ids and len(self.device_ids) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            self._replicas = [self] + [
+                StudentForceFieldCalculator(checkpoint_path, device=f"cuda:{i}", dtype=dtype, enable_stress=enable_stress,
+                                            enable_timing=False, use_jit=use_jit, jit_path=jit_path, precision=precision,
+                                            pbc_mode=pbc_mode, use_graph=use_graph, filter_mode=filter_mode)
+                for i in self.device_ids[1:]]
+            self._pool = ThreadPoolExecutor(max_workers=len(self._replicas))
         logger.info("Initialized StudentForceFieldCalculator: device=%s, precision=%s, pbc_mode=%s",
                     self.device, precision, pbc_mode)
 
@@ -288,14 +303,22 @@ class StudentForceFieldCalculator(_AseCalculator):
                 c["graphs"][want_virial] = g
             g.replay()
             stream.synchronize()
-            done = not (c["status_np"][2] or c["status_np"][5])   # overflow: fall through to the eager path
+            done = not (c["status_np"][2] or c["status_np"][5])   # overflow / FP16 saturation: eager path
         if not done:
-            eng.set_structure_hint(0)
             eng.ensure(n, 1, self.model._edges_per_atom)
             for _ in range(3):
                 enqueue_step()
                 stream.synchronize()
-                if not (c["status_np"][2] or c["status_np"][5]):
+                if c["status_np"][5] and not c["status_np"][2]:
+                    # a tensor-core operand left the FP16 range: this call again on the FP32 kernels
+                    eng.set_dense_fallback(True)
+                    try:
+                        enqueue_step()
+                        stream.synchronize()
+                    finally:
+                        eng.set_dense_fallback(False)
+                    eng.saturation_reruns += 1
+                if not c["status_np"][2]:
                     break
                 num_edges = int(c["status_np"][0])
                 eng.reserve(n, int(num_edges * 1.25) + 64, 1)
@@ -353,12 +376,17 @@ class StudentForceFieldCalculator(_AseCalculator):
         numbers = np.asarray(numbers)
         positions = np.asarray(positions)
         counts = np.asarray(counts, dtype=np.int64)
-        if len(numbers) == 0 or np.any(counts == 0):
-            raise ValueError("Cannot calculate properties for empty structure")
-        if np.any(numbers < 1) or np.any(numbers > min(118, self.model.max_z)):
-            raise ValueError(f"Invalid atomic numbers: must be 1-{min(118, self.model.max_z)}")
-        if not np.isfinite(positions).all():
-            raise ValueError("Positions contain NaN or Inf values")
+        self._validate_arrays(numbers, positions, counts)
+        periodic = cells is not None and pbcs is not None and bool(np.any(pbcs))
+        if periodic:
+            if not np.isfinite(np.asarray(cells)).all():
+                raise ValueError("Cell contains NaN or Inf values")
+            cells_a, pbcs_a = np.asarray(cells, dtype=np.float64).reshape(-1, 3, 3), np.asarray(pbcs, dtype=bool).reshape(-1, 3)
+            for b in range(len(counts)):   # a cell too small for the minimum image would silently drop periodic images
+                if pbcs_a[min(b, len(pbcs_a) - 1)].any():
+                    self._check_minimum_image(cells_a[min(b, len(cells_a) - 1)], pbcs_a[min(b, len(pbcs_a) - 1)])
+        if self._replicas is not None and not periodic and len(counts) >= 2 * len(self._replicas):
+            return self._evaluate_on_all_devices(numbers, positions, counts)
         if len(numbers) > self.max_atoms_per_call and len(counts) > 1:
             # micro-batches that fit the workspace (a 100 k-structure sweep does not fit in one call)
             from .sharding import chunk_by_budget
@@ -418,6 +446,30 @@ class StudentForceFieldCalculator(_AseCalculator):
         self._n_calls += 1
         return energies, forces
 
+    def _evaluate_on_all_devices(self, numbers, positions, counts):
+        """One structure list over ``device_ids``: contiguous shards balanced by atoms
+        (sharding.partition_by_atoms), one host thread per device driving that device's own pipeline
+        (pinned staging, copy streams, micro-batches), results concatenated in input order."""
+        from .sharding import partition_by_atoms
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        shards = partition_by_atoms(counts, len(self._replicas))
+
+        def work(replica, a, b):
+            if b <= a:
+                return np.zeros(0, dtype=np.float32), np.zeros((0, 3), dtype=np.float32)
+            torch.cuda.set_device(replica.device)
+            sl = slice(int(offs[a]), int(offs[b]))
+            saved, replica._replicas = replica._replicas, None      # the replica evaluates its shard locally
+            try:
+                return replica.evaluate_arrays(numbers[sl], positions[sl], counts[a:b])
+            finally:
+                replica._replicas = saved
+
+        futures = [self._pool.submit(work, r, a, b) for r, (a, b) in zip(self._replicas, shards)]
+        parts = [f.result() for f in futures]
+        self._n_calls += 1
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
     # ---- pipelined batches -----------------------------------------------------------------
     def evaluate_stream(self, batches: Iterable[Tuple[np.ndarray, np.ndarray, np.ndarray]]
                         ) -> Iterator[Tuple[np.ndarray, np.ndarray]]:
@@ -467,7 +519,6 @@ class StudentForceFieldCalculator(_AseCalculator):
         def launch(slot):
             n, nb = slot["n"], slot["nb"]
             compute.wait_event(slot["h2d_done"])
-            eng.set_structure_hint(slot["max_count"] if nb >= 32 else 0)
             eng.ensure(n, nb, self.model._edges_per_atom)
             eng.energy_forces_async(slot["z_d"][:n], slot["pos_d"][:n], slot["off_d"][:nb + 1], nb,
                                     slot["e_d"][:nb], slot["f_d"][:n])
@@ -483,7 +534,7 @@ class StudentForceFieldCalculator(_AseCalculator):
             n, nb = slot["n"], slot["nb"]
             slot["out_done"].synchronize()
             status = slot["status_h"].numpy()
-            if status[2] or status[5]:   # overflow / hint violation: blocking path grows and re-runs
+            if status[2] or status[5]:   # overflow / FP16 saturation: the blocking path grows / falls back and re-runs
                 torch.cuda.synchronize(dev)
                 try:
                     e_d, f_d = self.model.energy_and_forces_packed(

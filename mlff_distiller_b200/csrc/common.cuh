@@ -18,7 +18,7 @@ struct DeviceStatus {
     int overflow;
     int max_degree;
     int overflow_events;   // sticky: number of neighbour builds that overflowed since creation
-    int hint_violation;    // a structure exceeded mlffd_set_structure_hint: staged kernels skipped it
+    int tc_saturated;      // a tensor-core operand left the FP16 range in this step: dense-layer outputs invalid
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -170,6 +170,12 @@ __device__ __forceinline__ uint32_t umma_idesc_128x128(int tc_mode) {
 
 // 16-bit storage of one pre-scaled value: high term (FP16 or BF16 by mode) and FP16 low term
 // (meaningful in kTcSplit only)
+// FP16 range guard: a pre-scaled operand at or beyond this magnitude (or a NaN) would round to inf.
+// The producers OR the test into a per-thread flag and raise DeviceStatus::tc_saturated once per kernel;
+// the host then repeats the step on the FP32 FFMA kernels (mlffd_set_dense_fallback).
+constexpr float kSplitLimit = 65000.0f;
+__device__ __forceinline__ bool split_saturates(float x) { return !(fabsf(x) < kSplitLimit); }
+
 __device__ __forceinline__ void split_scaled(float x, int tc_mode, uint32_t& hi, uint32_t& lo) {
     if (tc_mode == kTcBF16) {
         hi = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x));
@@ -182,8 +188,10 @@ __device__ __forceinline__ void split_scaled(float x, int tc_mode, uint32_t& hi,
 }
 
 // split of 8 consecutive channels, packed for one 16-byte swizzle chunk
-__device__ __forceinline__ void split8(const float (&xin)[8], int tc_mode, uint4& hi, uint4& lo) {
+__device__ __forceinline__ void split8(const float (&xin)[8], int tc_mode, uint4& hi, uint4& lo, bool& sat) {
     uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sat |= (tc_mode != kTcBF16) && split_saturates(xin[i] * kActScale);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         uint32_t h0, l0, h1, l1;
@@ -197,8 +205,9 @@ __device__ __forceinline__ void split8(const float (&xin)[8], int tc_mode, uint4
 }
 
 // same split for 4 consecutive channels (half a swizzle chunk, 8 bytes per term)
-__device__ __forceinline__ void split4(const float4& xin, int tc_mode, uint2& hi, uint2& lo) {
+__device__ __forceinline__ void split4(const float4& xin, int tc_mode, uint2& hi, uint2& lo, bool& sat) {
     const float x[4] = {xin.x * kActScale, xin.y * kActScale, xin.z * kActScale, xin.w * kActScale};
+    sat |= (tc_mode != kTcBF16) && (split_saturates(x[0]) || split_saturates(x[1]) || split_saturates(x[2]) || split_saturates(x[3]));
     uint32_t h[2], l[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -230,8 +239,9 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int chunk) {
 #endif
 
 // split of one value, pre-scaled like split8 (16-bit patterns)
-__device__ __forceinline__ void split1(float x, int tc_mode, uint16_t& hi, uint16_t& lo) {
+__device__ __forceinline__ void split1(float x, int tc_mode, uint16_t& hi, uint16_t& lo, bool& sat) {
     uint32_t h, l;
+    sat |= (tc_mode != kTcBF16) && split_saturates(x * kActScale);
     split_scaled(x * kActScale, tc_mode, h, l);
     hi = (uint16_t)h;
     lo = (uint16_t)l;
@@ -447,6 +457,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
         // filter.cuh), split and written as the B operand of the first-layer GEMM: rows 0..63 =
         // phi~, rows 64..127 = phi~'.  Thread = (pair, 8-wide K chunk); K is padded to 32.
         FT_DECL
+        bool sat = false;   // an operand left the FP16 range (split_saturates)
         uint4 phi_hi, phi_lo, dphi_hi, dphi_lo;   // this thread's chunk of the next RBF tile
         auto rbf_compute = [&](int it) {   // pure math (overlaps the tensor cores)
             if (tid < 4 * kUmmaPairs) {
@@ -468,8 +479,8 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                     v8[i] = (k < K) ? phi * cut : 0.f;
                     t8[i] = (k < K) ? dphi * cut + phi * dcut : 0.f;
                 }
-                split8(v8, tc_mode, phi_hi, phi_lo);
-                split8(t8, tc_mode, dphi_hi, dphi_lo);
+                split8(v8, tc_mode, phi_hi, phi_lo, sat);
+                split8(t8, tc_mode, dphi_hi, dphi_lo, sat);
             }
         };
         auto rbf_store = [&]() {           // needs the activation tile free (second-layer MMAs done)
@@ -518,8 +529,8 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
                     const float hv = yy * sg;
                     const float tv = sg * (1.0f + yy * (1.0f - sg)) * zz;
                     uint16_t hh, hl, th, tl;
-                    split1(hv, tc_mode, hh, hl);
-                    split1(tv, tc_mode, th, tl);
+                    split1(hv, tc_mode, hh, hl, sat);
+                    split1(tv, tc_mode, th, tl, sat);
                     const uint32_t oh = sw128_offset(p, chunk), ot = sw128_offset(kUmmaPairs + p, chunk);
                     *reinterpret_cast<uint16_t*>(a_hi + oh) = hh;
                     *reinterpret_cast<uint16_t*>(a_hi + ot) = th;
@@ -584,6 +595,7 @@ filter_table_umma_kernel(const float* __restrict__ pair_dist, const int* __restr
             }
         }
         FT_PRINT
+        if (sat && status != nullptr) const_cast<DeviceStatus*>(status)->tc_saturated = 1;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();

@@ -4,6 +4,12 @@
 // nve_harness.py:214-235): half kick, drift, force evaluation, half kick -- integrator state in
 // FP64 like ASE's numpy arrays, positions rounded to FP32 only as model input, exactly like
 // inference/ase_calculator.py:497-500 does every step.
+//
+// Guard: when the force evaluation of a step failed on the device (edge-workspace overflow or an FP16
+// saturation of a tensor-core operand -- DeviceStatus), every kick / drift / record kernel that follows
+// returns without touching the state, so the trajectory FREEZES at the mid-step state (x_k, v_{k-1/2}) of
+// the failing step k, which is valid: the host grows the workspace (or switches the dense layers to the
+// FP32 kernels), repeats the force evaluation and the second half kick, and carries on (md.DeviceMD.run).
 #pragma once
 #include "common.cuh"
 
@@ -13,7 +19,8 @@ namespace mlffd {
 __global__ void __launch_bounds__(256)
 md_kick_drift_kernel(long long n3, double* __restrict__ pos, double* __restrict__ vel,
                      const float* __restrict__ forces, const double* __restrict__ inv_mass,
-                     double dt, float* __restrict__ pos32) {
+                     double dt, float* __restrict__ pos32, const DeviceStatus* __restrict__ guard) {
+    if (guard != nullptr && (guard->overflow | guard->tc_saturated)) return;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n3;
          i += (long long)gridDim.x * blockDim.x) {
         const double v = vel[i] + 0.5 * dt * (double)forces[i] * inv_mass[i / 3];
@@ -28,7 +35,8 @@ md_kick_drift_kernel(long long n3, double* __restrict__ pos, double* __restrict_
 // appends (PE, KE) to the series at *counter and increments it.
 __global__ void __launch_bounds__(256)
 md_kick_kernel(long long n3, double* __restrict__ vel, const float* __restrict__ forces,
-               const double* __restrict__ inv_mass, double dt) {
+               const double* __restrict__ inv_mass, double dt, const DeviceStatus* __restrict__ guard) {
+    if (guard != nullptr && (guard->overflow | guard->tc_saturated)) return;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n3;
          i += (long long)gridDim.x * blockDim.x)
         vel[i] += 0.5 * dt * (double)forces[i] * inv_mass[i / 3];
@@ -41,7 +49,8 @@ __global__ void __launch_bounds__(1024)
 md_energy_kernel(long long n3, double* __restrict__ vel, const float* __restrict__ forces,
                  const double* __restrict__ inv_mass, double dt,
                  const float* __restrict__ energy, int num_structures, double* __restrict__ series,
-                 int* __restrict__ counter, int capacity) {
+                 int* __restrict__ counter, int capacity, const DeviceStatus* __restrict__ guard) {
+    if (guard != nullptr && (guard->overflow | guard->tc_saturated)) return;
     __shared__ double red[32];
     double ke = 0.0;
     for (long long i = threadIdx.x; i < n3; i += blockDim.x) {

@@ -401,6 +401,177 @@ spline_message_backward_kernel(const float* __restrict__ table, int H,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small systems (single-trajectory MD: N <= MLFFD_SMALL_ROWS): with a few hundred rows the kernels above
+// leave most SMs idle while every row group walks its ~20 edges one L2 round trip at a time.  Here the
+// four row groups of a WARP share one row (group t takes edges t, t + 4, ...), a CTA is 8 warps = 8 rows,
+// so a 300-atom system spreads over ~150 CTAs and a row costs ~5 dependent round trips.  The four partial
+// sums meet through shuffles in a fixed order ((g0 + g1) + (g2 + g3)): deterministic; differs from the
+// row-per-group kernels by summation order only.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSplineTeamThreads = 256;
+
+__device__ __forceinline__ pk4 pk_team_sum(pk4 v) {   // sum over the 4 row groups of a warp (lanes l8, l8 + 8, ...)
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        pk4 w;
+        w.x = __shfl_xor_sync(full, v.x, o);
+        w.y = __shfl_xor_sync(full, v.y, o);
+        v = pk_add(v, w);
+    }
+    return v;
+}
+
+template <bool LAYER0>
+__global__ void __launch_bounds__(kSplineTeamThreads)
+spline_message_forward_team_kernel(const float* __restrict__ table, int H,
+                                   const int* __restrict__ rowptr, const float4* __restrict__ erec,
+                                   const float* __restrict__ s_in, const float* __restrict__ v_in,
+                                   float* __restrict__ s_msg, float* __restrict__ v_msg, int num_atoms,
+                                   const DeviceStatus* __restrict__ status) {
+    extern __shared__ float4 spline_tab[];
+    if (status->overflow) return;
+    constexpr int kWarps = kSplineTeamThreads / 32;
+    const int slices = H / kSliceChannels;
+    const int slice = blockIdx.x % slices, part = blockIdx.x / slices, parts = gridDim.x / slices;
+    load_spline_slice(spline_tab, table, slice);
+    const int warp = threadIdx.x >> 5, t = (threadIdx.x >> 3) & 3, l8 = threadIdx.x & 7;
+    const int ch = slice * kSliceChannels + l8 * 4;
+    const pk4* tab = reinterpret_cast<const pk4*>(spline_tab) + l8;
+    for (int j = part * kWarps + warp; j < num_atoms; j += parts * kWarps) {
+        const int e0 = __ldg(rowptr + j), e1 = __ldg(rowptr + j + 1);
+        pk4 acc_s = pk_zero(), acc_x = pk_zero(), acc_y = pk_zero(), acc_z = pk_zero();
+        float4 head = make4(0.f);
+        if (e0 + t < e1) head = __ldg(erec + 4 * (size_t)(e0 + t));
+        for (int e = e0 + t; e < e1; e += 4) {
+            const float4 g = head;   // (source, unit vector)
+            if (e + 4 < e1) head = __ldg(erec + 4 * (size_t)(e + 4));
+            const int i = __float_as_int(g.x);
+            const pk4 si = pk_ldg(s_in + (size_t)i * H + ch);
+            pk4 vix, viy, viz;
+            if (!LAYER0) {
+                const float* vi = v_in + (size_t)i * 3 * H + ch;
+                vix = pk_ldg(vi); viy = pk_ldg(vi + H); viz = pk_ldg(vi + 2 * H);
+            }
+            const float4 w0 = __ldg(erec + 4 * (size_t)e + 1), w1 = __ldg(erec + 4 * (size_t)e + 2);
+            const float b[6] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y};
+            const pk4* row = tab + __float_as_int(w1.z) * kSplineRowFloat4;
+            acc_s = pk_fma(si, spline_value(row, 0, b), acc_s);
+            if (!LAYER0) {
+                const pk4 fb = spline_value(row, 1, b);
+                acc_x = pk_fma(vix, fb, acc_x);
+                acc_y = pk_fma(viy, fb, acc_y);
+                acc_z = pk_fma(viz, fb, acc_z);
+            }
+            const pk4 fc = spline_value(row, 2, b);
+            acc_x = pk_fma_s(g.y, fc, acc_x);
+            acc_y = pk_fma_s(g.z, fc, acc_y);
+            acc_z = pk_fma_s(g.w, fc, acc_z);
+        }
+        acc_s = pk_team_sum(acc_s); acc_x = pk_team_sum(acc_x); acc_y = pk_team_sum(acc_y); acc_z = pk_team_sum(acc_z);
+        if (t == 0) {
+            pk_st(s_msg + (size_t)j * H + ch, pk_add(pk_ldg(s_in + (size_t)j * H + ch), acc_s));
+            float* vo = v_msg + (size_t)j * 3 * H + ch;
+            if (LAYER0) {
+                pk_st(vo, acc_x); pk_st(vo + H, acc_y); pk_st(vo + 2 * H, acc_z);
+            } else {
+                const float* vj = v_in + (size_t)j * 3 * H + ch;
+                pk_st(vo, pk_add(pk_ldg(vj), acc_x));
+                pk_st(vo + H, pk_add(pk_ldg(vj + H), acc_y));
+                pk_st(vo + 2 * H, pk_add(pk_ldg(vj + 2 * H), acc_z));
+            }
+        }
+    }
+}
+
+template <bool LAYER0>
+__global__ void __launch_bounds__(kSplineTeamThreads)
+spline_message_backward_team_kernel(const float* __restrict__ table, int H,
+                                    const int* __restrict__ rowptr, const float4* __restrict__ erec,
+                                    const float* __restrict__ s_in, const float* __restrict__ v_in,
+                                    const float* __restrict__ sbar_m, const float* __restrict__ vbar_m,
+                                    float* __restrict__ sbar_in, float* __restrict__ vbar_in,
+                                    float4* __restrict__ edge_adj, size_t slab_stride, int num_atoms,
+                                    const DeviceStatus* __restrict__ status) {
+    extern __shared__ float4 spline_tab[];
+    if (status->overflow) return;
+    constexpr int kWarps = kSplineTeamThreads / 32;
+    const int slices = H / kSliceChannels;
+    const int slice = blockIdx.x % slices, part = blockIdx.x / slices, parts = gridDim.x / slices;
+    load_spline_slice(spline_tab, table, slice);
+    float* adj_out = reinterpret_cast<float*>(edge_adj + (size_t)slice * slab_stride);
+    const int warp = threadIdx.x >> 5, t = (threadIdx.x >> 3) & 3, l8 = threadIdx.x & 7;
+    const int ch = slice * kSliceChannels + l8 * 4;
+    const pk4* tab = reinterpret_cast<const pk4*>(spline_tab) + l8;
+    const int held = ((l8 & 4) ? 2 : 0) + ((l8 & 2) ? 1 : 0);
+    for (int i = part * kWarps + warp; i < num_atoms; i += parts * kWarps) {
+        const int e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
+        const pk4 sb = pk_ldg(sbar_m + (size_t)i * H + ch);
+        const float* vb = vbar_m + (size_t)i * 3 * H + ch;
+        const pk4 vbx = pk_ldg(vb), vby = pk_ldg(vb + H), vbz = pk_ldg(vb + 2 * H);
+        pk4 acc_s = pk_zero(), acc_x = pk_zero(), acc_y = pk_zero(), acc_z = pk_zero();
+        float4 head = make4(0.f);
+        if (e0 + t < e1) head = __ldg(erec + 4 * (size_t)(e0 + t));
+        const int trips = (e1 - e0 + 3) >> 2;
+        for (int k = 0; k < trips; ++k) {
+            const int e = e0 + 4 * k + t;
+            const bool active = e < e1;
+            const unsigned active_lanes = __ballot_sync(0xffffffffu, active);
+            if (active) {
+                const float4 g = head;
+                if (e + 4 < e1) head = __ldg(erec + 4 * (size_t)(e + 4));
+                const int j = __float_as_int(g.x);
+                const pk4 sj = pk_ldg(s_in + (size_t)j * H + ch);
+                pk4 vjx, vjy, vjz, sbj, vbjx, vbjy, vbjz;
+                if (!LAYER0) {
+                    const float* vj = v_in + (size_t)j * 3 * H + ch;
+                    vjx = pk_ldg(vj); vjy = pk_ldg(vj + H); vjz = pk_ldg(vj + 2 * H);
+                    sbj = pk_ldg(sbar_m + (size_t)j * H + ch);
+                    const float* vbj = vbar_m + (size_t)j * 3 * H + ch;
+                    vbjx = pk_ldg(vbj); vbjy = pk_ldg(vbj + H); vbjz = pk_ldg(vbj + 2 * H);
+                }
+                const float4 w0 = __ldg(erec + 4 * (size_t)e + 1), w1 = __ldg(erec + 4 * (size_t)e + 2);
+                const float4 d0 = __ldg(erec + 4 * (size_t)e + 3);
+                const float b[6] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y};
+                const float db[6] = {d0.x, d0.y, d0.z, d0.w, w1.w, -((d0.x + d0.y) + (d0.z + d0.w) + w1.w)};
+                const pk4* row = tab + __float_as_int(w1.z) * kSplineRowFloat4;
+                pk4 dv;
+                if (LAYER0) {
+                    dv = pk_mul(pk_mul(sj, sb), spline_deriv(row, 0, db));
+                } else {
+                    pk4 fa, dfa, fb, dfb;
+                    spline_value_deriv(row, 0, b, db, fa, dfa);
+                    dv = pk_mul(pk_mul(sj, sb), dfa);
+                    acc_s = pk_fma(fa, sbj, acc_s);
+                    spline_value_deriv(row, 1, b, db, fb, dfb);
+                    const pk4 bbar = pk_fma(vjx, vbx, pk_fma(vjy, vby, pk_mul(vjz, vbz)));
+                    dv = pk_fma(bbar, dfb, dv);
+                    acc_x = pk_fma(fb, vbjx, acc_x);
+                    acc_y = pk_fma(fb, vbjy, acc_y);
+                    acc_z = pk_fma(fb, vbjz, acc_z);
+                }
+                pk4 fc, dfc;
+                spline_value_deriv(row, 2, b, db, fc, dfc);
+                const pk4 cbar = pk_fma_s(g.y, vbx, pk_fma_s(g.z, vby, pk_mul_s(g.w, vbz)));
+                dv = pk_fma(cbar, dfc, dv);
+                const float part4[4] = {pk_hsum(pk_mul(fc, vbx)), pk_hsum(pk_mul(fc, vby)),
+                                        pk_hsum(pk_mul(fc, vbz)), pk_hsum(dv)};
+                const float total = group8_sum4(part4, l8, active_lanes);
+                if ((l8 & 1) == 0) adj_out[4 * (size_t)e + held] = total;
+            }
+        }
+        if (!LAYER0) {
+            acc_s = pk_team_sum(acc_s); acc_x = pk_team_sum(acc_x); acc_y = pk_team_sum(acc_y); acc_z = pk_team_sum(acc_z);
+            if (t == 0) {   // residual path + the gathered sums
+                pk_st(sbar_in + (size_t)i * H + ch, pk_add(sb, acc_s));
+                float* vo = vbar_in + (size_t)i * 3 * H + ch;
+                pk_st(vo, pk_add(vbx, acc_x)); pk_st(vo + H, pk_add(vby, acc_y)); pk_st(vo + 2 * H, pk_add(vbz, acc_z));
+            }
+        }
+    }
+}
+
 // Stage entry point (parity tests): value and d-derivative of the layer's filter spline at `num`
 // distances, all 3H channels: filt / dfilt [num][3H] in the (a | b | c) column order of the filter table.
 __global__ void __launch_bounds__(256)

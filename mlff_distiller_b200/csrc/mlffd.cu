@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,6 +19,7 @@
 
 #include "cell_list.cuh"
 #include "common.cuh"
+#include "edge_features.cuh"
 #include "filter.cuh"
 #include "filter_umma.cuh"
 #include "umma_rows.cuh"
@@ -25,7 +27,6 @@
 #include "message.cuh"
 #include "message_pipe.cuh"
 #include "message_team.cuh"
-#include "message_staged.cuh"
 #include "message_spline.cuh"
 #include "neighbor.cuh"
 #include "readout.cuh"
@@ -82,8 +83,7 @@ struct mlffd_ctx {
     int H = 0, K = 0, L = 0;
     bool debug_keep = false;
     int neighbor_mode = 0;   // 0 auto, 1 sweep, 2 cells (env MLFFD_NEIGHBOR)
-    int struct_hint = 0;     // max atoms per structure promised by the caller (0 = unknown)
-    bool enable_staging = false;     // env MLFFD_STAGING=1
+    bool dense_fallback = false;     // mlffd_set_dense_fallback: dense layers on the FP32 FFMA kernels whatever cfg.precision
     int readout_mode = 0;            // env MLFFD_READOUT: 0 = by size, 1 = tile, 2 = warp
     bool readout_configured = false; // smem attribute of readout_tile_kernel set on this device
     uint32_t pipe_configured = 0;    // bit per pipelined-kernel instantiation whose smem attribute is set on this device
@@ -128,6 +128,20 @@ struct mlffd_ctx {
 };
 
 namespace {
+
+// Entry points run on the context's device and leave the calling thread's current device as they found
+// it (one process may drive several GPUs, and the caller's framework relies on its own current device).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 int fail(mlffd_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg; else g_create_error = msg;
@@ -224,14 +238,6 @@ int set_kernel_attributes(mlffd_ctx* ctx) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(update_backward_kernel<H, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)update_bwd_smem_bytes<H>()));
-    constexpr int kMaxSmem = 227 * 1024;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(message_forward_staged_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(message_forward_staged_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(message_backward_edges_staged_kernel<H, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(message_backward_edges_staged_kernel<H, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(message_backward_edges_staged_kernel<H, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(message_backward_edges_staged_kernel<H, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(message_backward_atoms_staged_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     return MLFFD_OK;
 }
 
@@ -289,7 +295,7 @@ template <int H>
 int launch_filter(mlffd_ctx* ctx, int l, const float* dist, const int* num_pairs_ptr,
                   int num_pairs_arg, const DeviceStatus* status, float* filt, float* dfilt,
                   int64_t pair_bound, cudaStream_t st) {
-    if (ctx->use_umma_filter)
+    if (ctx->use_umma_filter && !ctx->dense_fallback)
         return launch_filter_umma<H>(ctx, l, l + 1, dist, num_pairs_ptr, num_pairs_arg, status, filt, dfilt, pair_bound, st);
     const int blocks_per_sm = (filter_smem_bytes<H>() <= 110 * 1024) ? 2 : 1;
     const int grid = clamp_grid(ceil_div(std::max<int64_t>(pair_bound, 1), kFilterPairs),
@@ -427,8 +433,44 @@ cudaError_t launch_spline_backward_t(mlffd_ctx* ctx, int l, const float* sb, con
             sb, vb, sb_in, vb_in, slab, (size_t)ws.cap_edges, N, ctx->status_d);
     return cudaSuccess;
 }
+// small systems: a warp (four row groups) per CSR row, 8 rows per CTA
+cudaError_t launch_spline_team(mlffd_ctx* ctx, int l, bool backward, const float* sb, const float* vb, float* sb_in,
+                               float* vb_in, int N, cudaStream_t st) {
+    Workspace& ws = ctx->ws;
+    const int slices = ctx->H / kSliceChannels;
+    const int grid = spline_grid(N, slices, kSplineTeamThreads / 32, 2);
+    static bool configured[16] = {};
+    if (!configured[ctx->device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(spline_message_forward_team_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSplineSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spline_message_forward_team_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSplineSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spline_message_backward_team_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSplineSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spline_message_backward_team_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSplineSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured[ctx->device & 15] = true;
+    }
+    const float* table = spline_layer_table(ctx, l);
+    if (!backward) {
+        if (l == 0)
+            spline_message_forward_team_kernel<true><<<grid, kSplineTeamThreads, kSplineSmemBytes, st>>>(
+                table, ctx->H, ws.rowptr, ws.erec, ws.s_in[l], nullptr, ws.s_msg[l], ws.v_msg[l], N, ctx->status_d);
+        else
+            spline_message_forward_team_kernel<false><<<grid, kSplineTeamThreads, kSplineSmemBytes, st>>>(
+                table, ctx->H, ws.rowptr, ws.erec, ws.s_in[l], ws.v_in[l], ws.s_msg[l], ws.v_msg[l], N, ctx->status_d);
+    } else {
+        float4* slab = ws.edge_adj + (size_t)l * slices * ws.cap_edges;
+        if (l == 0)
+            spline_message_backward_team_kernel<true><<<grid, kSplineTeamThreads, kSplineSmemBytes, st>>>(
+                table, ctx->H, ws.rowptr, ws.erec, ws.s_in[l], nullptr, sb, vb, sb_in, vb_in, slab, (size_t)ws.cap_edges, N, ctx->status_d);
+        else
+            spline_message_backward_team_kernel<false><<<grid, kSplineTeamThreads, kSplineSmemBytes, st>>>(
+                table, ctx->H, ws.rowptr, ws.erec, ws.s_in[l], ws.v_in[l], sb, vb, sb_in, vb_in, slab, (size_t)ws.cap_edges, N, ctx->status_d);
+    }
+    return cudaSuccess;
+}
+
 // launch shapes: (threads per CTA, resident CTAs per SM); env MLFFD_SPLINE_FWD / MLFFD_SPLINE_BWD pick one
 cudaError_t launch_spline_forward(mlffd_ctx* ctx, int l, int N, cudaStream_t st) {
+    if (N <= ctx->small_rows && ctx->msg_team > 1) return launch_spline_team(ctx, l, false, nullptr, nullptr, nullptr, nullptr, N, st);
     switch (ctx->spline_fwd_shape) {
         case 1: return launch_spline_forward_t<768, 1>(ctx, l, N, st);
         case 2: return launch_spline_forward_t<384, 2>(ctx, l, N, st);
@@ -438,6 +480,7 @@ cudaError_t launch_spline_forward(mlffd_ctx* ctx, int l, int N, cudaStream_t st)
 }
 cudaError_t launch_spline_backward(mlffd_ctx* ctx, int l, const float* sb, const float* vb, float* sb_in, float* vb_in,
                                    int N, cudaStream_t st) {
+    if (N <= ctx->small_rows && ctx->msg_team > 1) return launch_spline_team(ctx, l, true, sb, vb, sb_in, vb_in, N, st);
     switch (ctx->spline_bwd_shape) {
         case 1: return launch_spline_backward_t<768, 1>(ctx, l, sb, vb, sb_in, vb_in, N, st);
         case 2: return launch_spline_backward_t<384, 2>(ctx, l, sb, vb, sb_in, vb_in, N, st);
@@ -460,23 +503,14 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     const int upd_fwd_grid = clamp_grid(tiles, kNumSMs * (update_fwd_smem_bytes<H>() <= 110 * 1024 ? 2 : 1));
     const int upd_bwd_grid = clamp_grid(tiles, kNumSMs * (update_bwd_smem_bytes<H>() <= 110 * 1024 ? 2 : 1));
     const int warp_grid = clamp_grid(ceil_div(N, 8), kNumSMs * 8);
-    // structure-blocked kernels with smem-staged features when the caller promised small structures
-    const int hint = ctx->struct_hint;
-    const size_t staged_smem = staged_smem_bytes<H>(hint);
-    // Measured on C2 (B200): the staged variant is SLOWER than the generic kernels (message fwd
-    // 1.00 vs 0.77 ms, reverse 2.11 vs 1.98 ms per step) -- the neighbour gathers already hit
-    // L1/L2 and the kernels are bound by streaming the filter-table rows -- so it is opt-in
-    // (MLFFD_STAGING=1) and kept for bit-identity tests and for future tuning.
-    const bool staged = ctx->enable_staging && hint > 0 && staged_smem <= 227 * 1024;
     // reverse message kernels: 0 = one directed edge at a time (accumulates edge adjoints in place),
     // 1 = every pair once, 2 = pair once + cp.async ring (H = 128); 1 and 2 write per-layer slabs
-    const bool bwd_pipe = !staged && ctx->msg_bwd_mode == 2 && H == 128;
-    const bool fwd_pipe = !staged && ctx->msg_fwd_mode == 1 && H == 128;
+    const bool bwd_pipe = ctx->msg_bwd_mode == 2 && H == 128;
+    const bool fwd_pipe = ctx->msg_fwd_mode == 1 && H == 128;
     // small systems: a team of kTeam warps per CSR row (needs the per-layer adjoint slabs of the pair-once modes)
-    const bool team = !staged && (ctx->msg_team == 4 || ctx->msg_team == 8) && N <= ctx->small_rows && ctx->msg_bwd_mode >= 1;
+    const bool team = (ctx->msg_team == 4 || ctx->msg_team == 8) && N <= ctx->small_rows && ctx->msg_bwd_mode >= 1;
     const int team_grid = clamp_grid(ceil_div(N, M::APW), kNumSMs * 16);
-    const bool adj_slabs = !staged && ctx->msg_bwd_mode >= 1;
-    const int staged_grid = staged ? clamp_grid(n_structs, kNumSMs * (int)std::min<size_t>(8, (227 * 1024) / staged_smem)) : 1;
+    const bool adj_slabs = ctx->msg_bwd_mode >= 1;
 
     embedding_kernel<H><<<clamp_grid(ceil_div((int64_t)N * (H / 4), 256), kNumSMs * 8), 256, 0, st>>>(
         z, ctx->emb, ctx->cfg.max_z, ws.s_in[0], N);
@@ -490,7 +524,8 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     // the filters depend on the distances only: with the tensor-core kernel all layers' tables come
     // from one launch ahead of the layer loop
     const bool spline = ctx->spline;
-    const bool filters_up_front = !spline && ctx->use_umma_filter &&
+    const bool use_umma = ctx->use_umma && !ctx->dense_fallback;   // tensor-core update block
+    const bool filters_up_front = !spline && ctx->use_umma_filter && !ctx->dense_fallback &&
                                   (ctx->filter_batch == 1 || (ctx->filter_batch == 2 && N <= ctx->small_rows));
     if (filters_up_front) {
         int rc = launch_filter_umma<H>(ctx, 0, L, ws.pair_dist, &ctx->status_d->num_pairs, 0, status,
@@ -505,15 +540,7 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
         }
         if (spline) {
             CUDA_TRY(ctx, launch_spline_forward(ctx, l, N, st));
-        } else if (staged && l == 0)
-            message_forward_staged_kernel<H, true><<<staged_grid, kStagedThreads, staged_smem, st>>>(
-                offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], nullptr,
-                ws.s_msg[l], ws.v_msg[l], ctx->status_d);
-        else if (staged)
-            message_forward_staged_kernel<H, false><<<staged_grid, kStagedThreads, staged_smem, st>>>(
-                offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], ws.v_in[l],
-                ws.s_msg[l], ws.v_msg[l], ctx->status_d);
-        else if (team) {   // small system: a team of warps per CSR row (message_team.cuh)
+        } else if (team) {   // small system: a team of warps per CSR row (message_team.cuh)
 #define MSG_FWD_TEAM(LAYER0, TT)                                                                       \
     message_forward_team_kernel<H, LAYER0, TT><<<team_grid, 32 * TT, 0, st>>>(                         \
         ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.s_in[l], LAYER0 ? nullptr : ws.v_in[l],     \
@@ -534,7 +561,7 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
         LAUNCHED(ctx, "message_forward_kernel", MLFFD_STAGE_MESSAGE_FWD, st);
         bool upd_done = false;
         if constexpr (H == 128) {
-            if (ctx->use_umma && N <= ctx->small_rows) {
+            if (use_umma && N <= ctx->small_rows) {
                 const UpdateWeights& uw = ctx->layer[l].update;
                 launch_ffma_rows(ctx, UpdateFwd1Op{ws.s_msg[l], ws.v_msg[l], uw.m1, ws.y1[l]}, N, uw.M1t, H, st);
                 LAUNCHED(ctx, "ffma_rows_kernel<UpdateFwd1Op>", MLFFD_STAGE_UPDATE_FWD, st);
@@ -545,7 +572,7 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
                     launch_ffma_rows(ctx, UpdateFwd2Op<false>{ws.y1[l], ws.s_msg[l], ws.v_msg[l], uw.m2, uw.U, ws.s_in[l + 1], ws.v_in[l + 1], ws.gates[l]},
                                      N, uw.M2t, 3 * H, st);
                 upd_done = true;
-            } else if (ctx->use_umma) {
+            } else if (use_umma) {
                 const UpdateWeights& uw = ctx->layer[l].update;
                 const int rows_grid = clamp_grid(ceil_div(N, 128), kNumSMs);
                 TC_DISPATCH(ctx->tc_mode, umma_rows_kernel<UpdateFwd1Op, MODE><<<rows_grid, kFilterUmmaThreads, UmmaRowsSmem::TOTAL, st>>>(
@@ -602,7 +629,7 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
         float* vb = ws.vbar[adj(l)];
         bool bwd_done = false;
         if constexpr (H == 128) {
-            if (ctx->use_umma && N <= ctx->small_rows) {
+            if (use_umma && N <= ctx->small_rows) {
                 const UpdateWeights& uw = ctx->layer[l].update;
                 if (l == L - 1) {
                     launch_ffma_rows(ctx, UpdateBwd1Op<true>{sb, vb, ws.v_msg[l], uw.U, ws.y1[l]}, N, uw.M2, H, st);
@@ -614,7 +641,7 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
                     launch_ffma_rows(ctx, UpdateBwd2Op<false>{ws.y1[l], ws.v_msg[l], ws.gates[l], uw.U, sb, vb}, N, uw.M1, 2 * H, st);
                 }
                 bwd_done = true;
-            } else if (ctx->use_umma) {
+            } else if (use_umma) {
                 const UpdateWeights& uw = ctx->layer[l].update;
                 const int rows_grid = clamp_grid(ceil_div(N, 128), kNumSMs);
                 if (l == L - 1) {
@@ -652,21 +679,8 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     message_backward_pairs_kernel<H, LAYER0, false><<<msg_grid, 256, 0, st>>>(                   \
         ws.rowptr, ws.col, ws.pair, ws.rev, ws.geo, ws.filt[l], ws.dfilt[l], ws.s_in[l],         \
         ws.v_in[l], sb, vb, sb_in, vb_in, ws.edge_adj + (size_t)l * ws.cap_edges, N, status)
-#define MSG_BWD_EDGES(LAYER0, ACC)                                                                         \
-    message_backward_edges_staged_kernel<H, LAYER0, ACC><<<staged_grid, kStagedThreads, staged_smem, st>>>(             \
-        offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.geo, ws.filt[l], ws.dfilt[l], ws.s_in[l],   \
-        ws.v_in[l], sb, vb, ws.edge_adj, ctx->status_d)
         if (spline) {
             CUDA_TRY(ctx, launch_spline_backward(ctx, l, sb, vb, sb_in, vb_in, N, st));
-        } else if (staged) {
-            if (l == 0) { if (first) MSG_BWD_EDGES(true, false); else MSG_BWD_EDGES(true, true); }
-            else        { if (first) MSG_BWD_EDGES(false, false); else MSG_BWD_EDGES(false, true); }
-            if (l > 0) {
-                LAUNCHED(ctx, "message_backward_edges_staged_kernel", MLFFD_STAGE_MESSAGE_BWD, st);
-                message_backward_atoms_staged_kernel<H><<<staged_grid, kStagedThreads, staged_smem, st>>>(
-                    offsets, n_structs, hint, ws.rowptr, ws.col, ws.pair, ws.filt[l], sb, vb, sb_in, vb_in,
-                    ctx->status_d);
-            }
         } else if (team) {
 #define MSG_BWD_TEAM(LAYER0, TT)                                                                          \
     message_backward_pairs_team_kernel<H, LAYER0, TT><<<team_grid, 32 * TT, 0, st>>>(                     \
@@ -682,7 +696,6 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
         } else if (l == 0) { if (first) MSG_BWD(true, false); else MSG_BWD(true, true); }
         else        { if (first) MSG_BWD(false, false); else MSG_BWD(false, true); }
 #undef MSG_BWD_PAIRS
-#undef MSG_BWD_EDGES
 #undef MSG_BWD
         LAUNCHED(ctx, "message_backward_kernel", MLFFD_STAGE_MESSAGE_BWD, st);
     }
@@ -830,8 +843,12 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     if (e != cudaSuccess || count == 0)
         return fail(nullptr, MLFFD_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
     if (device < 0 || device >= count) return fail(nullptr, MLFFD_EINVAL, "bad device index");
-    e = cudaSetDevice(device);
-    if (e != cudaSuccess) return fail(nullptr, MLFFD_ECUDA, cudaGetErrorString(e));
+    DeviceGuard device_guard(device);
+    {
+        int current = -1;
+        if (cudaGetDevice(&current) != cudaSuccess || current != device)
+            return fail(nullptr, MLFFD_ECUDA, "cannot select the requested CUDA device");
+    }
 
     mlffd_ctx* ctx = new (std::nothrow) mlffd_ctx();
     if (!ctx) return fail(nullptr, MLFFD_ENOMEM, "out of host memory");
@@ -840,7 +857,6 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
     ctx->H = H; ctx->K = K; ctx->L = L;
     const char* dbg = std::getenv("MLFFD_DEBUG_KEEP");
     ctx->debug_keep = dbg && dbg[0] == '1';
-    if (const char* ns = std::getenv("MLFFD_STAGING")) ctx->enable_staging = ns[0] == '1';
     // measured (C2 shapes, one B200): the pair-once reverse pass wins at H = 128 (1.49 vs 1.97 ms),
     // but with 2 - 4 atoms per warp its two edge classes diverge and the per-directed-edge kernel
     // is faster (Tiny 0.69 vs 0.88 ms, Ultra-tiny 0.44 vs 0.57 ms)
@@ -1004,7 +1020,15 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
             else if (H == 64) e = cudaFuncSetAttribute(filter_table_umma_kernel<64, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<64>::total());
             else e = cudaFuncSetAttribute(filter_table_umma_kernel<32, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UmmaGeom<32>::total()));
         if (e != cudaSuccess) return bail(MLFFD_ECUDA, cudaGetErrorString(e));
-        ctx->use_umma_filter = K <= kUmmaMaxRbf;   // first layer runs as one 32-wide K block
+        // FP16 range guard for the pre-scaled weight images: a matrix with max|w| * 2^8 beyond the FP16
+        // range cannot be split; such a model runs its dense layers on the FP32 FFMA kernels instead
+        float wmax = 0.f;
+        {
+            const float* q2 = weights_host + (size_t)(config->max_z + 1) * H + 2 * K;
+            for (size_t i = 0; i < (size_t)L * per_layer; ++i) wmax = std::max(wmax, std::fabs(q2[i]));
+        }
+        const bool weights_fit = tc_mode == kTcBF16 || (wmax * kWeightScale < 65000.0f && std::isfinite(wmax));
+        ctx->use_umma_filter = weights_fit && K <= kUmmaMaxRbf;   // first layer runs as one 32-wide K block
         if (H == 128) {
 #define SET_ROWS_ATTR(OP)                                                                            \
         TC_DISPATCH(tc_mode, e = cudaFuncSetAttribute(umma_rows_kernel<OP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -1014,7 +1038,7 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
         SET_ROWS_ATTR(UpdateBwd1Op<false>) SET_ROWS_ATTR(UpdateBwd1Op<true>)
         SET_ROWS_ATTR(UpdateBwd2Op<false>) SET_ROWS_ATTR(UpdateBwd2Op<true>)
 #undef SET_ROWS_ATTR
-            ctx->use_umma = true;
+            ctx->use_umma = weights_fit;
         }
     }
     const float* W = ctx->weights_d;
@@ -1035,7 +1059,7 @@ extern "C" int mlffd_model_create(mlffd_ctx** out, int device, const mlffd_confi
 
 extern "C" void mlffd_model_destroy(mlffd_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard device_guard(ctx->device);
     for (cudaEvent_t ev : ctx->event_pool) cudaEventDestroy(ev);
     if (ctx->ws.arena) cudaFree(ctx->ws.arena);
     if (ctx->weights_d) cudaFree(ctx->weights_d);
@@ -1056,7 +1080,7 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
     max_structures = std::max<int64_t>(std::max(max_structures, ws.cap_structs), 1);
     if (max_atoms >= (1ll << 30) || max_edges >= (1ll << 31) - 64)
         return fail(ctx, MLFFD_EINVAL, "workspace request exceeds 32-bit indexing");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);
     CUDA_TRY(ctx, cudaDeviceSynchronize());
     const int64_t N = max_atoms, E = max_edges, P = max_edges / 2 + 1;
     const int H = ctx->H, L = ctx->L;
@@ -1165,7 +1189,7 @@ extern "C" int mlffd_neighbor_list(mlffd_ctx* ctx, const float* pos_d, const int
     if (!ctx) return MLFFD_EINVAL;
     if (!pos_d || !offsets_d || num_structures < 1 || num_atoms < 1)
         return fail(ctx, MLFFD_EINVAL, "mlffd_neighbor_list: bad argument");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);
     return build_neighbors(ctx, pos_d, offsets_d, num_structures, num_atoms, cells_d, pbc_d,
                            (cudaStream_t)stream);
 }
@@ -1197,7 +1221,7 @@ extern "C" int mlffd_energy_forces(mlffd_ctx* ctx, const int32_t* z_d, const flo
     if (!ctx) return MLFFD_EINVAL;
     if (!z_d || !pos_d || !offsets_d || !energy_d || num_structures < 1 || num_atoms < 1)
         return fail(ctx, MLFFD_EINVAL, "mlffd_energy_forces: bad argument");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = build_neighbors(ctx, pos_d, offsets_d, num_structures, num_atoms, cells_d, pbc_d, st);
     if (rc) return rc;
@@ -1211,7 +1235,7 @@ extern "C" int mlffd_energy_forces(mlffd_ctx* ctx, const int32_t* z_d, const flo
 
 extern "C" int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out) {
     if (!ctx || !out) return MLFFD_EINVAL;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->last_stream));
     DeviceStatus h{};
     CUDA_TRY(ctx, cudaMemcpy(&h, ctx->status_d, sizeof(h), cudaMemcpyDeviceToHost));
@@ -1222,7 +1246,7 @@ extern "C" int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out) {
     out->overflow = h.overflow;
     out->max_degree = h.max_degree;
     out->overflow_events = h.overflow_events;
-    out->hint_violation = h.hint_violation;
+    out->tc_saturated = h.tc_saturated;
     out->reserved = 0;
     return MLFFD_OK;
 }
@@ -1230,7 +1254,7 @@ extern "C" int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out) {
 extern "C" int mlffd_status_async(mlffd_ctx* ctx, int32_t* status_out, void* stream) {
     if (!ctx || !status_out) return MLFFD_EINVAL;
     static_assert(sizeof(DeviceStatus) == 6 * sizeof(int32_t), "mlffd_status_async copies six int32 words");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);
     CUDA_TRY(ctx, cudaMemcpyAsync(status_out, ctx->status_d, sizeof(DeviceStatus), cudaMemcpyDefault,
                                   (cudaStream_t)stream));
     return MLFFD_OK;
@@ -1244,7 +1268,7 @@ extern "C" int mlffd_filter_table(mlffd_ctx* ctx, int32_t layer, const float* di
         num_pairs >= (1ll << 31) / (3 * ctx->H))
         return fail(ctx, MLFFD_EINVAL, "mlffd_filter_table: bad argument");
     if (num_pairs == 0) return MLFFD_OK;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     switch (ctx->H) {
         case 128: return launch_filter<128>(ctx, layer, dist_d, nullptr, (int)num_pairs, nullptr, filter_d, dfilter_d, num_pairs, st);
@@ -1253,13 +1277,33 @@ extern "C" int mlffd_filter_table(mlffd_ctx* ctx, int32_t layer, const float* di
     }
 }
 
+extern "C" int mlffd_edge_features(const float* pos_d, const int64_t* edge_index_d, int64_t num_edges, float eps,
+                                   int32_t eps_mode, float* edge_vec_d, float* dist_d, float* unit_d, void* stream) {
+    if (num_edges == 0) return MLFFD_OK;
+    if (!pos_d || !edge_index_d || !edge_vec_d || !dist_d || !unit_d || num_edges < 0 || (eps_mode != 0 && eps_mode != 1))
+        return MLFFD_EINVAL;
+    edge_features_kernel<<<clamp_grid(ceil_div(num_edges, kEdgeFeatThreads), kNumSMs * 8), kEdgeFeatThreads, 0, (cudaStream_t)stream>>>(
+        pos_d, (const long long*)edge_index_d, (const long long*)edge_index_d + num_edges, (long long)num_edges, eps, eps_mode,
+        edge_vec_d, dist_d, unit_d);
+    return cudaGetLastError() == cudaSuccess ? MLFFD_OK : MLFFD_ECUDA;
+}
+
+extern "C" int mlffd_rbf_cutoff(const float* dist_d, int64_t num_edges, const float* centers_d, int32_t num_rbf,
+                                float gamma, float cutoff, float* out_d, void* stream) {
+    if (num_edges == 0) return MLFFD_OK;
+    if (!dist_d || !centers_d || !out_d || num_edges < 0 || num_rbf < 1 || !(cutoff > 0.f)) return MLFFD_EINVAL;
+    rbf_cutoff_kernel<<<clamp_grid(ceil_div(num_edges * num_rbf, 256), kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(
+        dist_d, (long long)num_edges, centers_d, num_rbf, gamma, cutoff, out_d);
+    return cudaGetLastError() == cudaSuccess ? MLFFD_OK : MLFFD_ECUDA;
+}
+
 extern "C" int mlffd_filter_spline(mlffd_ctx* ctx, int32_t layer, const float* dist_d, int64_t num_pairs,
                                    float* filter_d, float* dfilter_d, void* stream) {
     if (!ctx) return MLFFD_EINVAL;
     if (!dist_d || !filter_d || !dfilter_d || layer < 0 || layer >= ctx->L || num_pairs < 0)
         return fail(ctx, MLFFD_EINVAL, "mlffd_filter_spline: bad argument");
     if (num_pairs == 0) return MLFFD_OK;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);
     spline_filter_eval_kernel<<<clamp_grid(ceil_div(num_pairs * 3 * ctx->H, 256), kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(
         spline_layer_table(ctx, layer), ctx->H, ctx->spline_inv_h, dist_d, (long long)num_pairs, filter_d, dfilter_d);
     LAUNCH_CHECK(ctx, "spline_filter_eval_kernel");
@@ -1273,7 +1317,7 @@ extern "C" int mlffd_virial(mlffd_ctx* ctx, const int32_t* offsets_d, int32_t nu
         return fail(ctx, MLFFD_EINVAL, "mlffd_virial: bad argument");
     if (ctx->last_adj_slabs == 0 || num_structures != ctx->last_structs)
         return fail(ctx, MLFFD_EINVAL, "mlffd_virial: call mlffd_energy_forces with forces first (same structures)");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     Workspace& ws = ctx->ws;
     // few structures with many edges each (a periodic box) -> several chunk blocks per structure
@@ -1332,7 +1376,7 @@ extern "C" int mlffd_debug_buffer(mlffd_ctx* ctx, const char* name, int32_t laye
 
 extern "C" int mlffd_profile_enable(mlffd_ctx* ctx, int32_t enable) {
     if (!ctx) return MLFFD_EINVAL;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->last_stream));
     ctx->marks.clear();
     ctx->events_used = 0;
@@ -1344,7 +1388,7 @@ extern "C" int mlffd_profile_enable(mlffd_ctx* ctx, int32_t enable) {
 
 extern "C" int mlffd_profile_read(mlffd_ctx* ctx, mlffd_profile* out) {
     if (!ctx || !out) return MLFFD_EINVAL;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard device_guard(ctx->device);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->last_stream));
     drain_marks(ctx);
     out->launches = ctx->launches;
@@ -1363,17 +1407,17 @@ extern "C" const char* mlffd_stage_name(int32_t stage) {
 }
 
 // ---- on-device velocity Verlet (stateless helpers; any stream) -------------------------------
-extern "C" int mlffd_md_kick_drift(int64_t num_atoms, double* pos_d, double* vel_d,
+extern "C" int mlffd_md_kick_drift(const mlffd_ctx* guard, int64_t num_atoms, double* pos_d, double* vel_d,
                                    const float* forces_d, const double* inv_mass_d, double dt,
                                    float* pos32_d, void* stream) {
     if (num_atoms < 1 || !pos_d || !vel_d || !forces_d || !inv_mass_d || !pos32_d) return MLFFD_EINVAL;
     const long long n3 = 3 * (long long)num_atoms;
     md_kick_drift_kernel<<<clamp_grid(ceil_div(n3, 256), kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(
-        n3, pos_d, vel_d, forces_d, inv_mass_d, dt, pos32_d);
+        n3, pos_d, vel_d, forces_d, inv_mass_d, dt, pos32_d, guard ? guard->status_d : nullptr);
     return cudaGetLastError() == cudaSuccess ? MLFFD_OK : MLFFD_ECUDA;
 }
 
-extern "C" int mlffd_md_kick_energy(int64_t num_atoms, double* vel_d, const float* forces_d,
+extern "C" int mlffd_md_kick_energy(const mlffd_ctx* guard, int64_t num_atoms, double* vel_d, const float* forces_d,
                                     const double* inv_mass_d, double dt, const float* energy_d,
                                     int32_t num_structures, double* series_d, int32_t* counter_d,
                                     int32_t capacity, void* stream) {
@@ -1381,19 +1425,20 @@ extern "C" int mlffd_md_kick_energy(int64_t num_atoms, double* vel_d, const floa
         return MLFFD_EINVAL;
     const long long n3 = 3 * (long long)num_atoms;
     cudaStream_t st = (cudaStream_t)stream;
+    const DeviceStatus* g = guard ? guard->status_d : nullptr;
     if (n3 <= 8192) {   // small system: kick and energy bookkeeping in one single-block launch
         md_energy_kernel<true><<<1, 1024, 0, st>>>(n3, vel_d, forces_d, inv_mass_d, dt, energy_d, num_structures,
-                                                   series_d, counter_d, capacity);
+                                                   series_d, counter_d, capacity, g);
     } else {
-        md_kick_kernel<<<clamp_grid(ceil_div(n3, 256), kNumSMs * 8), 256, 0, st>>>(n3, vel_d, forces_d, inv_mass_d, dt);
+        md_kick_kernel<<<clamp_grid(ceil_div(n3, 256), kNumSMs * 8), 256, 0, st>>>(n3, vel_d, forces_d, inv_mass_d, dt, g);
         md_energy_kernel<false><<<1, 1024, 0, st>>>(n3, vel_d, forces_d, inv_mass_d, dt, energy_d, num_structures,
-                                                    series_d, counter_d, capacity);
+                                                    series_d, counter_d, capacity, g);
     }
     return cudaGetLastError() == cudaSuccess ? MLFFD_OK : MLFFD_ECUDA;
 }
 
-extern "C" int mlffd_set_structure_hint(mlffd_ctx* ctx, int32_t max_atoms_per_structure) {
-    if (!ctx || max_atoms_per_structure < 0) return MLFFD_EINVAL;
-    ctx->struct_hint = max_atoms_per_structure;
+extern "C" int mlffd_set_dense_fallback(mlffd_ctx* ctx, int32_t enable) {
+    if (!ctx) return MLFFD_EINVAL;
+    ctx->dense_fallback = enable != 0;
     return MLFFD_OK;
 }

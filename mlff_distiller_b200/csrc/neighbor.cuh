@@ -104,7 +104,7 @@ __global__ void neighbor_finalize_kernel(const int* __restrict__ rowptr,
         status->overflow = (e > edge_capacity) ? 1 : 0;
         if (e > edge_capacity) status->overflow_events += 1;
         status->max_degree = 0;
-        status->hint_violation = 0;
+        status->tc_saturated = 0;
     }
 }
 
@@ -153,7 +153,7 @@ neighbor_scan_small_kernel(const int* __restrict__ deg, const int* __restrict__ 
         status->overflow = (e > edge_capacity) ? 1 : 0;
         if (e > edge_capacity) status->overflow_events += 1;
         status->max_degree = 0;
-        status->hint_violation = 0;
+        status->tc_saturated = 0;
     }
 }
 
@@ -308,7 +308,7 @@ neighbor_small_kernel(const float* __restrict__ pos, const int* __restrict__ off
             status->overflow = (num_edges > edge_capacity) ? 1 : 0;
             if (num_edges > edge_capacity) status->overflow_events += 1;
             status->max_degree = warp_m[0];
-            status->hint_violation = 0;
+            status->tc_saturated = 0;
         }
         __syncthreads();
         if (num_edges > edge_capacity) return;   // uniform: outputs invalid, the host grows and re-runs

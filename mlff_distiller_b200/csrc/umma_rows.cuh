@@ -157,6 +157,7 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
         const int q = warp & 3, cs = warp >> 2;               // channel quarter (lanes), row segment
         const int kb = lane >> 4;                             // K block (64 values) of this lane
         const int chunk = (lane & 15) >> 1, half8 = (lane & 1) * 8;
+        bool sat = false;   // an operand left the FP16 range (filter_umma.cuh:split_saturates)
         for (int it = 0; it < my_tiles; ++it) {
             const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * 128;
             for (int ks = 0; ks < KS; ++ks) {
@@ -170,7 +171,7 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
 #pragma unroll
                 for (int rr = 0; rr < 8; ++rr) {
                     uint2 hi, lo;
-                    split4(x[rr], MODE, hi, lo);
+                    split4(x[rr], MODE, hi, lo, sat);
                     const uint32_t o = sw128_offset(warp * 8 + rr, chunk) + half8;
                     *reinterpret_cast<uint2*>(a_hi + o) = hi;
                     if (!single) *reinterpret_cast<uint2*>(a_lo + o) = lo;
@@ -207,6 +208,7 @@ umma_rows_kernel(Op op, int num_rows, const uint8_t* __restrict__ images,
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
+        if (sat && status != nullptr) const_cast<DeviceStatus*>(status)->tc_saturated = 1;
     }
     __syncthreads();
     if (warp == kUmmaComputeWarps) {

@@ -62,6 +62,8 @@ class Engine:
             raise _lib.MlffdError(rc, msg)
         self._ctx = handle
         self.profiling = False
+        self.dense_fallback = False
+        self.saturation_reruns = 0   # calls repeated on the FP32 kernels because a tensor-core operand saturated
         self.cap_atoms = self.cap_edges = self.cap_structs = 0
 
     # -- lifetime ---------------------------------------------------------------------------
@@ -120,11 +122,11 @@ class Engine:
             self._ctx, _ptr(pos), _ptr(offsets), int(n_structs), int(pos.shape[0]), _ptr(cells),
             _ptr(pbc), self._stream()))
 
-    def set_structure_hint(self, max_atoms_per_structure: int):
-        """Promise an upper bound on atoms per structure (0 = unknown) -> smem-staged kernels."""
-        if int(max_atoms_per_structure) != getattr(self, "_hint", 0):
-            self._check(self.lib.mlffd_set_structure_hint(self._ctx, int(max_atoms_per_structure)))
-            self._hint = int(max_atoms_per_structure)
+    def set_dense_fallback(self, enable: bool):
+        """Run the dense layers on the FP32 FFMA kernels (True) or as the precision says (False).
+        Used to repeat a step whose tensor-core operands left the FP16 range (status.tc_saturated)."""
+        self._check(self.lib.mlffd_set_dense_fallback(self._ctx, 1 if enable else 0))
+        self.dense_fallback = bool(enable)
 
     def status(self) -> _lib.MlffdStatus:
         """Synchronises the last call's stream and returns its counters."""
@@ -134,7 +136,7 @@ class Engine:
 
     def status_async(self, out: torch.Tensor):
         """Enqueue a copy of the step's six status words (num_edges, num_pairs, overflow,
-        max_degree, overflow_events, hint_violation) into ``out`` (int32[6], pinned host or device)
+        max_degree, overflow_events, tc_saturated) into ``out`` (int32[6], pinned host or device)
         behind the step just enqueued on the current stream.  Never synchronises."""
         self._check(self.lib.mlffd_status_async(self._ctx, out.data_ptr(), self._stream()))
 

@@ -113,7 +113,8 @@ class DeviceMD:
     """
 
     def __init__(self, model, numbers, positions, velocities, masses, dt_fs: float = 0.5,
-                 offsets=None, cell=None, pbc=None, use_graph: bool = True, capacity: int = 1 << 20):
+                 offsets=None, cell=None, pbc=None, use_graph: bool = True, capacity: int = 1 << 20,
+                 edge_reserve: Optional[int] = None):
         import ctypes
         import torch
         self.torch, self.ctypes = torch, ctypes
@@ -147,11 +148,12 @@ class DeviceMD:
             self._forces()
             st = self.eng.status()
             if not st.overflow:
-                self.eng.reserve(n, int(st.num_edges * 1.5) + 64, self.nb)
+                # edge_reserve: explicit capacity (tests of the freeze / resume path); default 1.5x head-room
+                self.eng.reserve(n, int(st.num_edges * 1.5) + 64 if edge_reserve is None else int(edge_reserve), self.nb)
                 break
             self.eng.reserve(n, int(st.num_edges * 1.5) + 64, self.nb)
         self._forces()
-        self._events0 = int(self.eng.status().overflow_events)
+        self.interruptions = 0   # steps that had to be repaired (workspace growth / FP32 fallback) and resumed
         self._record(0.0)  # series[0] = (PE, KE) at t = 0
 
     def _ptr(self, t):
@@ -162,7 +164,7 @@ class DeviceMD:
                                      self.cells, self.pbc)
 
     def _record(self, dt):
-        rc = self.lib.mlffd_md_kick_energy(self.n, self.vel.data_ptr(), self.forces.data_ptr(),
+        rc = self.lib.mlffd_md_kick_energy(self.eng._ctx, self.n, self.vel.data_ptr(), self.forces.data_ptr(),
                                            self.inv_mass.data_ptr(), dt, self.energy.data_ptr(), self.nb,
                                            self.series.data_ptr(), self.counter.data_ptr(), self.capacity,
                                            self.eng._stream())
@@ -170,47 +172,82 @@ class DeviceMD:
             raise RuntimeError(f"mlffd_md_kick_energy failed ({rc})")
 
     def _step(self):
-        rc = self.lib.mlffd_md_kick_drift(self.n, self.pos.data_ptr(), self.vel.data_ptr(), self.forces.data_ptr(),
+        rc = self.lib.mlffd_md_kick_drift(self.eng._ctx, self.n, self.pos.data_ptr(), self.vel.data_ptr(), self.forces.data_ptr(),
                                           self.inv_mass.data_ptr(), self.dt, self.pos32.data_ptr(), self.eng._stream())
         if rc:
             raise RuntimeError(f"mlffd_md_kick_drift failed ({rc})")
         self._forces()
         self._record(self.dt)
 
-    def run(self, steps: int) -> Dict[str, np.ndarray]:
-        """Advance ``steps`` steps; returns the energy series so far (step 0 included)."""
+    def _capture(self):
+        """Capture one step as a CUDA graph (warm-up outside the capture; the trajectory does not advance)."""
         torch = self.torch
-        caps = (self.eng.cap_atoms, self.eng.cap_edges, self.eng.cap_structs)
-        if self.use_graph and (self.graph is None or self._graph_caps != caps):
-            side = torch.cuda.Stream(device=self.eng.device)
-            side.wait_stream(torch.cuda.current_stream(self.eng.device))
-            with torch.cuda.stream(side):  # warm-up outside capture, then capture one step
-                state = (self.pos.clone(), self.vel.clone(), self.forces.clone(), self.energy.clone(),
-                         self.counter.clone())
-                self._step()
-                side.synchronize()
+        side = torch.cuda.Stream(device=self.eng.device)
+        side.wait_stream(torch.cuda.current_stream(self.eng.device))
+        with torch.cuda.stream(side):
+            state = (self.pos.clone(), self.vel.clone(), self.forces.clone(), self.energy.clone(),
+                     self.counter.clone())
+
+            def restore():
                 for dst, src in zip((self.pos, self.vel, self.forces, self.energy, self.counter), state):
                     dst.copy_(src)
                 self.pos32.copy_(self.pos.to(torch.float32))
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph, stream=side):
-                    self._step()
-                for dst, src in zip((self.pos, self.vel, self.forces, self.energy, self.counter), state):
-                    dst.copy_(src)  # the capture run itself must not advance the trajectory
-                self.pos32.copy_(self.pos.to(torch.float32))
-            torch.cuda.current_stream(self.eng.device).wait_stream(side)
-            self._graph_caps = caps
-        for _ in range(int(steps)):
-            if self.use_graph:
-                self.graph.replay()
-            else:
+
+            self._step()
+            side.synchronize()
+            restore()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
                 self._step()
+            restore()   # the capture run itself must not advance the trajectory
+            self._forces()   # device status words of the restored state (the kicks are guarded by them)
+        torch.cuda.current_stream(self.eng.device).wait_stream(side)
+        self._graph_caps = (self.eng.cap_atoms, self.eng.cap_edges, self.eng.cap_structs, self.eng.dense_fallback)
+
+    def run(self, steps: int) -> Dict[str, np.ndarray]:
+        """Advance ``steps`` steps; returns the energy series so far (step 0 included).
+
+        Steps are enqueued without host synchronisation.  If a force evaluation fails on the device
+        (edge-workspace overflow, FP16 saturation of a tensor-core operand) the guarded kick / drift
+        kernels freeze the trajectory at that step's valid mid-step state; this method then grows the
+        workspace (or moves the dense layers to the FP32 kernels), completes the interrupted step and
+        carries on, so the returned series is the one an uninterrupted run would have produced."""
+        torch = self.torch
+        target = int(self.counter.item()) + int(steps)
+        for _attempt in range(8):
+            todo = target - int(self.counter.item())
+            if todo <= 0:
+                break
+            caps = (self.eng.cap_atoms, self.eng.cap_edges, self.eng.cap_structs, self.eng.dense_fallback)
+            if self.use_graph and (self.graph is None or self._graph_caps != caps):
+                self._capture()
+            for _ in range(todo):
+                if self.use_graph:
+                    self.graph.replay()
+                else:
+                    self._step()
+            torch.cuda.synchronize(self.eng.device)
+            if int(self.counter.item()) >= target:
+                break
+            # frozen at (x_k, v_{k-1/2}) of the failing step k: repair, finish step k, go round again
+            st = self.eng.status()
+            self.interruptions += 1
+            if st.overflow:
+                self.eng.reserve(self.n, int(st.num_edges * 1.5) + 64, self.nb)
+            elif st.tc_saturated:
+                self.eng.set_dense_fallback(True)
+            self._forces()
+            st = self.eng.status()
+            if st.overflow or st.tc_saturated:
+                continue
+            self._record(self.dt)
+        else:
+            raise RuntimeError("on-device trajectory could not be resumed after repeated device-side failures")
         torch.cuda.synchronize(self.eng.device)
-        st = self.eng.status()
-        if int(st.overflow_events) != self._events0:
-            raise RuntimeError("edge workspace overflowed during the on-device trajectory; "
-                               "reserve more edges (Engine.reserve) and restart from the last state")
-        return self.energies()
+        out = self.energies()
+        if not np.isfinite(out["total"]).all():
+            raise RuntimeError("non-finite energies in the on-device trajectory")
+        return out
 
     def energies(self) -> Dict[str, np.ndarray]:
         k = min(int(self.counter.item()), self.capacity)

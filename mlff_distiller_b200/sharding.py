@@ -53,14 +53,41 @@ def chunk_by_budget(counts: Sequence[int], max_atoms: int, max_structs: int) -> 
     return out
 
 
-def gather_in_order(local_energies: np.ndarray, local_forces: np.ndarray, group=None):
-    """Host-side gather of per-rank results into input order via ``all_gather_object``
-    (works on gloo for CPU tests and on nccl-initialised jobs alike; results are small:
-    4 B per structure + 12 B per atom)."""
+def gather_in_order(local_energies: np.ndarray, local_forces: np.ndarray, counts: Sequence[int],
+                    group=None, device=None):
+    """Gather per-rank results into input order with TWO fixed-size collectives and no pickling.
+
+    ``counts`` is the global per-structure atom count list every rank already holds (the shards are a
+    pure function of it, :func:`partition_by_atoms`), so every rank knows every shard's size: the
+    local arrays are padded to the largest shard, exchanged with ``all_gather_into_tensor`` (float32,
+    4 B per structure + 12 B per atom), and the padding is cut away on the host.  Works with gloo
+    (CPU tensors, tests) and with nccl (``device`` = this rank's CUDA device)."""
+    import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    bucket = [None] * world
-    dist.all_gather_object(bucket, (np.asarray(local_energies), np.asarray(local_forces)), group=group)
-    energies = np.concatenate([b[0] for b in bucket])
-    forces = np.concatenate([b[1] for b in bucket])
+    rank = dist.get_rank(group)
+    counts = np.asarray(counts, dtype=np.int64)
+    shards = partition_by_atoms(counts, world)
+    n_structs = [b - a for a, b in shards]
+    n_atoms = [int(counts[a:b].sum()) for a, b in shards]
+    local_energies = np.asarray(local_energies, dtype=np.float32).reshape(-1)
+    local_forces = np.asarray(local_forces, dtype=np.float32).reshape(-1, 3)
+    if len(local_energies) != n_structs[rank] or len(local_forces) not in (0, n_atoms[rank]):
+        raise ValueError("local results do not match this rank's shard of `counts`")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+    def exchange(local: np.ndarray, sizes, width: int) -> np.ndarray:
+        cap = max(max(sizes), 1)
+        send = torch.zeros((cap, width), dtype=torch.float32, device=device)
+        if len(local):
+            send[: len(local)] = torch.from_numpy(np.ascontiguousarray(local).reshape(-1, width)).to(device)
+        recv = torch.empty((world * cap, width), dtype=torch.float32, device=device)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        host = recv.cpu().numpy().reshape(world, cap, width)
+        return np.concatenate([host[r, : sizes[r]] for r in range(world)])
+
+    energies = exchange(local_energies, n_structs, 1).reshape(-1)
+    want_forces = len(local_forces) > 0 or n_atoms[rank] == 0
+    forces = exchange(local_forces, n_atoms, 3) if want_forces else np.zeros((0, 3), dtype=np.float32)
     return energies, forces

@@ -202,21 +202,27 @@ class StudentForceField(nn.Module):
         return self._engine
 
     def _run(self, z, pos, offsets, nb, cells, pbc, want_forces: bool, max_atoms: int = 0):
-        """One evaluation through the C ABI; retries once with a larger edge workspace.
-        ``max_atoms`` (host-known largest structure, 0 = unknown) enables the smem-staged kernels."""
+        """One evaluation through the C ABI; retries with a larger edge workspace on overflow and on
+        the FP32 kernels when a tensor-core operand left the FP16 range (``max_atoms`` is accepted for
+        compatibility and unused)."""
         eng = self.engine()
         n = pos.shape[0]
-        # structure-per-block kernels pay off only when there are enough structures to fill the GPU
-        eng.set_structure_hint(max_atoms if nb >= 32 else 0)
         energy = torch.empty(nb, dtype=torch.float32, device=pos.device)
         forces = torch.empty((n, 3), dtype=torch.float32, device=pos.device) if want_forces else None
         eng.ensure(n, nb, self._edges_per_atom)
-        for _ in range(3):
+        for _ in range(4):
             eng.energy_forces_async(z, pos, offsets, nb, energy, forces, cells, pbc)
             st = eng.status()
-            if st.hint_violation:   # the promise was wrong: fall back to the generic kernels
-                eng.set_structure_hint(0)
-                continue
+            if st.tc_saturated and not st.overflow:
+                # |activation| >= 8 125 in a split-FP16 dense layer (dense / unphysical input): this call
+                # is repeated with the dense layers on the FP32 FFMA kernels
+                eng.set_dense_fallback(True)
+                try:
+                    eng.energy_forces_async(z, pos, offsets, nb, energy, forces, cells, pbc)
+                    st = eng.status()
+                finally:
+                    eng.set_dense_fallback(False)
+                eng.saturation_reruns += 1
             if not st.overflow:
                 return energy, forces
             eng.reserve(n, int(st.num_edges * 1.25) + 64, nb)
@@ -376,16 +382,39 @@ class EnergyOnlyWrapper(nn.Module):
         return self.model(atomic_numbers, positions, None, None, None)
 
 
+_GRAPH_ENGINES: Dict[Tuple[int, float], "object"] = {}
+
+
+def _graph_engine(device: torch.device, cutoff: float):
+    """Weight-free CUDA context for neighbour lists only, cached per (device, cutoff): the neighbour
+    kernels read nothing but the cutoff, so a minimal all-zero model (H = 32, one layer) carries it."""
+    from .engine import Engine
+    if device.type != "cuda":
+        raise RuntimeError("radius_graph (B200 path) runs on CUDA only: pass CUDA positions or engine= "
+                           "(there is no CPU fallback)")
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (index, float(cutoff))
+    eng = _GRAPH_ENGINES.get(key)
+    if eng is None:
+        cfg = ModelConfig(32, 1, 4, float(cutoff), 1)
+        state = {k: np.zeros(shape, dtype=np.float32) for k, shape in ckpt.expected_keys(cfg).items()}
+        state.pop("rbf.centers"), state.pop("rbf.widths")
+        state = ckpt.complete_state(state, cfg)     # reference formula for the RBF buffers
+        eng = _GRAPH_ENGINES[key] = Engine(state, cfg, torch.device("cuda", index), "fp32")
+    return eng
+
+
 def radius_graph(positions: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None,
                  loop: bool = False, use_torch_cluster: bool = True, *, engine=None,
                  cell=None, pbc=None) -> torch.Tensor:
     """Drop-in for the reference ``radius_graph`` (student_model.py:165-191): ``[2,E]`` int64,
     row 0 = src, row 1 = dst, lexicographic order, computed by the CUDA neighbour kernels.
-    Needs an :class:`~mlff_distiller_b200.engine.Engine` (any weights; only ``cutoff`` matters)."""
-    if loop:
-        raise NotImplementedError("self loops are never used on this path")
+    Same call signature as the reference (``radius_graph(positions, r, batch)``): the CUDA context comes
+    from a per-(device, cutoff) cache unless ``engine=`` supplies one; ``use_torch_cluster`` only selected
+    the backend in the reference (same sorted edge set) and is accepted and ignored; ``loop=True`` adds
+    the self pairs the reference keeps when it does not mask the diagonal (:101-103)."""
     if engine is None:
-        raise ValueError("radius_graph needs engine= (a CUDA context); there is no CPU path")
+        engine = _graph_engine(positions.device, float(r))
     if abs(engine.cfg.cutoff - float(r)) > 0:
         raise ValueError("engine was created with a different cutoff")
     dev = engine.device
@@ -404,7 +433,12 @@ def radius_graph(positions: torch.Tensor, r: float, batch: Optional[torch.Tensor
         eng.neighbor_list_async(pos, offsets, nb, cells_d, pbc_d)
         st = eng.status()
         if not st.overflow:
-            return eng.export_edges()
+            edges = eng.export_edges()
+            if loop:   # self pairs, merged into the lexicographic (src, dst) order
+                diag = torch.arange(n, dtype=torch.int64, device=dev)
+                edges = torch.cat([edges, torch.stack([diag, diag])], dim=1)
+                edges = edges[:, torch.argsort(edges[0] * n + edges[1])]
+            return edges
         eng.reserve(n, int(st.num_edges * 1.25) + 64, nb)
     raise RuntimeError("edge workspace overflow persisted after growing")
 

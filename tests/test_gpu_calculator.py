@@ -183,6 +183,177 @@ def test_device_md_matches_host_verlet(calc):
     assert abs(out["drift_percent"]) < 0.14
 
 
+def _nve_fixture():
+    path = GOLDEN / "nve_reference.npz"
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _device_run(calc, numbers, ref, key, steps):
+    dev = md.DeviceMD(calc.model, numbers, ref[key + "_x0"], ref[key + "_v0"], ref[key + "_masses"], dt_fs=0.5)
+    return dev.run(steps)
+
+
+def test_nve_10ps_benzene_on_device_within_reference_bar(calc):
+    """BASELINE north_star: NVE drift over a 10 ps velocity-Verlet run (20 000 x 0.5 fs, 300 K, COM
+    translation + rotation removed: nve_harness.py:158-165, 329-331) within the reference's 0.14 %.
+    Same initial state as the CPU reference trajectory of tests/golden/make_nve_reference.py: the
+    end-point drifts are compared and the first 1 ps of the total-energy series must track it."""
+    ref = _nve_fixture()
+    key = "benzene_seed42"
+    out = _device_run(calc, synthetic.benzene().numbers, ref, key, int(ref["steps"]))
+    tot = out["total"]
+    assert len(tot) == int(ref["steps"]) + 1
+    assert abs(out["drift_percent"]) <= 0.14, out["drift_percent"]
+    assert abs(float(ref[key + "_drift_percent"])) <= 0.14          # the CPU reference meets its own bar too
+    assert np.abs(tot[:2001] - ref[key + "_total_first2001"]).max() < 2e-4
+    band = 100.0 * float(np.max(np.abs(tot - tot[0]))) / abs(tot[0])
+    assert band <= max(0.05, 2.0 * float(ref[key + "_band_percent"]))
+    _write_nve_report("benzene", {"gpu_drift_percent": out["drift_percent"], "cpu_drift_percent": float(ref[key + "_drift_percent"]),
+                                  "gpu_band_percent": band, "cpu_band_percent": float(ref[key + "_band_percent"])})
+
+
+def _write_nve_report(name, payload):
+    import json
+    from conftest import ROOT
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / f"nve_10ps_{name}.json").write_text(json.dumps(payload, indent=1))
+
+
+def test_nve_10ps_h2o_ensemble_inside_the_cpu_reference_band(calc):
+    """H2O over 10 ps, 32 seeds, each started from the SAME (x0, v0) as a CPU run of the reference path
+    (tests/golden/make_nve_reference.py).
+
+    Finding (numbers in gpurun_out/nve_10ps_h2o.json): the reference model itself misses its 0.14 % bar on
+    H2O -- most of the CPU reference's own end-point drifts are outside it -- because the total energy of
+    this three-atom trajectory oscillates by 0.2 - 0.6 % of |E| under velocity Verlet at 0.5 fs and the
+    metric samples that oscillation at one instant; two copies of one trajectory decorrelate within a
+    fraction of a picosecond.  The on-device trajectories are therefore held to the reference's own
+    DISTRIBUTION over the same 32 initial states: the start of every series tracks the CPU series, and
+    the RMS and the 90th percentile of |drift| and the median oscillation band are no larger than the
+    CPU ensemble's (+30 %, the sampling noise of a 32-member ensemble)."""
+    ref = _nve_fixture()
+    steps = int(ref["steps"])
+    numbers = synthetic.water().numbers
+    rows = []
+    for seed in [int(s) for s in ref["h2o_seeds"]]:
+        key = f"h2o_seed{seed}"
+        out = _device_run(calc, numbers, ref, key, steps)
+        tot = out["total"]
+        band = 100.0 * float(np.max(np.abs(tot - tot[0]))) / abs(tot[0])
+        diff = np.abs(tot[:2001] - ref[key + "_total_first2001"])
+        rows.append({"seed": seed, "gpu_drift_percent": out["drift_percent"], "cpu_drift_percent": float(ref[key + "_drift_percent"]),
+                     "gpu_band_percent": band, "cpu_band_percent": float(ref[key + "_band_percent"]),
+                     "early_max_dE_eV": {"20_steps": float(diff[:21].max()), "100_steps": float(diff[:101].max()),
+                                         "500_steps": float(diff[:501].max()), "2000_steps": float(diff.max())}})
+    gpu = np.array([r["gpu_drift_percent"] for r in rows])
+    cpu = np.array([r["cpu_drift_percent"] for r in rows])
+    gband = np.array([r["gpu_band_percent"] for r in rows])
+    cband = np.array([r["cpu_band_percent"] for r in rows])
+    summary = {"seeds": len(rows),
+               "rms_drift_percent": {"gpu": float(np.sqrt(np.mean(gpu ** 2))), "cpu": float(np.sqrt(np.mean(cpu ** 2)))},
+               "p90_abs_drift_percent": {"gpu": float(np.percentile(np.abs(gpu), 90)), "cpu": float(np.percentile(np.abs(cpu), 90))},
+               "mean_drift_percent": {"gpu": float(gpu.mean()), "cpu": float(cpu.mean())},
+               "median_band_percent": {"gpu": float(np.median(gband)), "cpu": float(np.median(cband))},
+               "within_0.14_percent": {"gpu": int(np.sum(np.abs(gpu) <= 0.14)), "cpu": int(np.sum(np.abs(cpu) <= 0.14))}}
+    _write_nve_report("h2o", {"summary": summary, "rows": rows})
+    for r in rows:
+        assert r["early_max_dE_eV"]["20_steps"] < 1e-4, r       # same forces, same integrator: the start coincides
+    assert summary["within_0.14_percent"]["cpu"] < len(rows) // 2    # the finding: the reference misses its own bar here
+    assert summary["rms_drift_percent"]["gpu"] <= 1.3 * summary["rms_drift_percent"]["cpu"], summary
+    assert summary["p90_abs_drift_percent"]["gpu"] <= 1.3 * summary["p90_abs_drift_percent"]["cpu"], summary
+    assert summary["median_band_percent"]["gpu"] <= 1.3 * summary["median_band_percent"]["cpu"], summary
+
+
+def test_device_md_freezes_and_resumes_on_edge_overflow(calc):
+    """A force evaluation that overflows the edge workspace mid-trajectory must not corrupt the state:
+    the guarded kick / drift kernels freeze at that step, DeviceMD.run grows the workspace, completes
+    the step and carries on -- same series as a run with ample capacity, bit for bit.  Two benzene
+    molecules start beyond each other's cutoff and fly together, so the edge count must grow."""
+    from mlff_distiller_b200.student_model import StudentForceField
+    a, b = synthetic.benzene(), synthetic.benzene()
+    numbers = np.concatenate([a.numbers, b.numbers])
+    pos = np.concatenate([a.get_positions(), b.get_positions() + np.array([10.5, 0.0, 0.0])])
+    m = md.ATOMIC_MASSES[numbers]
+    v0 = np.zeros_like(pos)
+    v0[:12, 0], v0[12:, 0] = 0.25, -0.25           # Angstrom per ASE time unit: ~0.025 A closer per step
+    steps = 120
+    ample = md.DeviceMD(calc.model, numbers, pos, v0, m, dt_fs=0.5, edge_reserve=2000)
+    e_start = int(ample.eng.status().num_edges)
+    ref = ample.run(steps)
+    assert ample.interruptions == 0 and int(ample.eng.status().num_edges) > e_start + 2
+    tight_model = StudentForceField.load(GOLDEN / "weights_original.npz", device="cuda")
+    tight_model.engine().reserve(len(numbers), e_start + 2, 1)   # exact: the first new pair overflows it
+    dev = md.DeviceMD(tight_model, numbers, pos, v0, m, dt_fs=0.5, edge_reserve=1)
+    assert dev.eng.cap_edges == e_start + 2
+    out = dev.run(steps)
+    assert dev.interruptions >= 1
+    assert len(out["total"]) == steps + 1
+    assert np.array_equal(out["total"], ref["total"])
+
+
+def test_fp16_range_guard_falls_back_to_the_fp32_kernels():
+    """ADVICE / VERDICT weak #5: the two-term FP16 split has a finite range.  (a) activations: with
+    the embedding scaled x 1e4 the update block's operands leave the FP16 range; the producers raise
+    tc_saturated and the call is repeated on the FP32 FFMA kernels -- the result equals the fp32 model's.
+    (b) weights: a matrix with max|w| >= 253 cannot be pre-scaled; such a model never uses the tensor cores."""
+    from conftest import load_weights
+    from mlff_distiller_b200.checkpoint import infer_config
+    from mlff_distiller_b200.student_model import StudentForceField
+    state, cfg = load_weights("original")
+    structs = synthetic.druglike_batch(48, first=50)   # 2 400 atoms: above MLFFD_SMALL_ROWS, so the tcgen05 update block runs
+    z, pos, off = synthetic.concatenate(structs)
+    z_d = torch.from_numpy(z.astype(np.int32)).cuda()
+    p_d = torch.from_numpy(pos.astype(np.float32)).cuda()
+    o_d = torch.from_numpy(off.astype(np.int32)).cuda()
+
+    def run(st, precision):
+        model = StudentForceField.from_state(st, infer_config(st, cfg), "cuda:0", precision=precision)
+        e, f = model.energy_and_forces_packed(z_d, p_d, o_d, len(structs))
+        return model, e.cpu().numpy(), f.cpu().numpy()
+
+    hot = dict(state)
+    hot["embedding.weight"] = state["embedding.weight"] * 1.0e4
+    m_tc, e_tc, f_tc = run(hot, "tc")
+    m_32, e_32, f_32 = run(hot, "fp32")
+    assert m_tc.engine().saturation_reruns == 1
+    assert np.isfinite(e_tc).all() and np.isfinite(f_tc).all()
+    assert np.array_equal(e_tc, e_32) and np.array_equal(f_tc, f_32)
+    m_ok, e_ok, _ = run(state, "tc")
+    assert m_ok.engine().saturation_reruns == 0            # trained weights stay far inside the range
+    big = dict(state)
+    key = "interactions.2.update.update_mlp.2.weight"
+    big[key] = state[key] * np.float32(300.0 / np.abs(state[key]).max())      # max|w| = 300 >= 253
+    m_w, e_w, f_w = run(big, "tc")
+    m_w32, e_w32, f_w32 = run(big, "fp32")
+    assert m_w.engine().saturation_reruns == 0
+    assert np.isfinite(e_w).all() and np.isfinite(f_w).all()
+    assert np.array_equal(e_w, e_w32) and np.array_equal(f_w, f_w32)
+
+
+def test_device_ids_spread_one_batch_over_the_gpus_of_the_process():
+    """SURVEY section 8e / VERDICT missing #4: one process, several GPUs behind the calculator API --
+    calculate_batch / evaluate_arrays split one structure list over device_ids (no torchrun, no collective)
+    and return the same results, in input order, as a single device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in the process")
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+    ids = list(range(min(torch.cuda.device_count(), 4)))
+    multi = StudentForceFieldCalculator(GOLDEN / "weights_original.npz", device_ids=ids)
+    single = StudentForceFieldCalculator(GOLDEN / "weights_original.npz", device="cuda:0")
+    structs = synthetic.druglike_batch(37, first=4000, ragged=True)
+    z, pos, off = synthetic.concatenate(structs)
+    e_m, f_m = multi.evaluate_arrays(z, pos, np.diff(off))
+    e_s, f_s = single.evaluate_arrays(z, pos, np.diff(off))
+    assert np.array_equal(e_m, e_s) and np.array_equal(f_m, f_s)     # same kernels, same inputs, any GPU
+    res = multi.calculate_batch(structs)
+    assert len(res) == len(structs)
+    assert all(r["forces"].shape == (len(s), 3) for r, s in zip(res, structs))
+    assert np.allclose([r["energy"] for r in res], e_s)
+    assert torch.cuda.current_device() == 0      # the library leaves the caller's current device alone
+
+
 def test_device_md_batch_of_independent_trajectories(calc):
     structs = [synthetic.water(), synthetic.benzene(), synthetic.druglike(5, 30)]
     z, pos, off = synthetic.concatenate(structs)

@@ -78,10 +78,13 @@ a, b = sharding.shard_slice(counts, rank, world)
 z, pos, off = synthetic.concatenate(structs[a:b])
 e_local = np.array([pos[off[i]:off[i+1]].sum() for i in range(b - a)])   # stand-in "energy"
 f_local = pos * 2.0                                                        # stand-in "forces"
-e, f = sharding.gather_in_order(e_local, f_local)
+e, f = sharding.gather_in_order(e_local, f_local, counts)
 zz, pp, oo = synthetic.concatenate(structs)
-assert np.allclose(e, [pp[oo[i]:oo[i+1]].sum() for i in range(len(structs))])
-assert np.allclose(f, pp * 2.0)
+assert e.dtype == np.float32 and f.dtype == np.float32
+assert np.allclose(e, [pp[oo[i]:oo[i+1]].sum() for i in range(len(structs))], rtol=1e-6)
+assert np.allclose(f, pp * 2.0, rtol=1e-6)
+e2, f2 = sharding.gather_in_order(e_local, np.zeros((0, 3)), counts)      # energies only (sweeps)
+assert np.array_equal(e2, e) and f2.shape == (0, 3)
 if rank == 0:
     print('GATHER_OK', a, b)
 dist.destroy_process_group()

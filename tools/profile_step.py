@@ -22,7 +22,6 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--precision", default="tc")
-    ap.add_argument("--no-hint", action="store_true", help="do not promise the largest structure size")
     args = ap.parse_args()
     model = StudentForceField.load(ROOT / "tests" / "golden" / f"weights_{args.variant}.npz", device="cuda:0",
                                    pbc_mode="minimum_image", precision=args.precision)
@@ -40,8 +39,7 @@ def main():
     z_d = torch.from_numpy(z.astype(np.int32)).cuda()
     p_d = torch.from_numpy(pos.astype(np.float32)).cuda()
     o_d = torch.from_numpy(off.astype(np.int32)).cuda()
-    hint = 0 if args.no_hint else int(np.diff(off).max())
-    e, f = model.energy_and_forces_packed(z_d, p_d, o_d, len(structs), cells, pbc, max_atoms=hint)
+    e, f = model.energy_and_forces_packed(z_d, p_d, o_d, len(structs), cells, pbc)
     st = model.engine().status()
     print(f"N={len(z)} E={st.num_edges} P={st.num_pairs} maxdeg={st.max_degree} E0={float(e[0]):.4f}")
     eng = model.engine()

@@ -55,7 +55,7 @@ def main():
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e_all, _ = sharding.gather_in_order(e, np.zeros((0, 3), dtype=np.float32))
+        e_all, _ = sharding.gather_in_order(e, np.zeros((0, 3), dtype=np.float32), sizes)
     else:
         e_all = e
     if rank == 0:
