@@ -58,6 +58,9 @@ def parse_args():
                          "sweep = BASELINE config 5: ONE host-side list of ragged structures (n ~ U{20..80}) partitioned "
                          "over the ranks, staged, evaluated and gathered back in input order (strong scaling)")
     ap.add_argument("--sweep-structures", type=int, default=100000)
+    ap.add_argument("--sweep-cache", default="",
+                    help="npz written by tools/make_sweep_cache.py (numbers, positions, counts of the whole list): "
+                         "ranks slice their shard from it instead of generating it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the records measured outside the C2 timed region (md: C1/C3/C4 single-trajectory latency, "
@@ -423,7 +426,16 @@ def run_sweep(args):
     # every rank derives the global size list (the shards are a pure function of it) and generates its own shard
     sizes = np.array([int(np.random.default_rng(500000 + s).integers(20, 81)) for s in range(total)], dtype=np.int64)
     a, b = sharding.shard_slice(sizes, rank, world)
-    numbers, pos, counts = sweep_shard(a, b - a, max(1, (os.cpu_count() or 2) // world))
+    if args.sweep_cache and Path(args.sweep_cache).exists():
+        with np.load(args.sweep_cache) as z:
+            all_counts = z["counts"].astype(np.int64)
+            assert len(all_counts) >= total and np.array_equal(all_counts[:total], sizes)
+            o = np.concatenate([[0], np.cumsum(all_counts)])
+            numbers = z["numbers"][o[a]:o[b]].astype(np.int64)
+            pos = z["positions"][o[a]:o[b]].astype(np.float64)
+            counts = all_counts[a:b]
+    else:
+        numbers, pos, counts = sweep_shard(a, b - a, max(1, (os.cpu_count() or 2) // world))
     assert np.array_equal(counts, sizes[a:b])
     calc = StudentForceFieldCalculator(ROOT / "tests" / "golden" / VARIANT_FILES[args.variant], device=str(dev),
                                       precision=args.precision, filter_mode=args.filter_mode)
@@ -432,7 +444,7 @@ def run_sweep(args):
     for _ in range(2):   # sizes the workspace, the pinned staging and (N > 1) the gather buffers
         calc.evaluate_arrays(numbers[: offs[warm]], pos[: offs[warm]], counts[:warm])
     if world > 1:
-        sharding.gather_in_order(np.zeros(b - a, np.float32), np.zeros((int(counts.sum()), 3), np.float32), sizes, device=dev)
+        sharding.gather_in_order(np.zeros(b - a, np.float32), np.zeros((int(counts.sum()), 3), np.float32), sizes, device=dev, root=0)
         dist.barrier()
     torch.cuda.synchronize(dev)
     sampler = ClockSampler(local)
@@ -450,7 +462,7 @@ def run_sweep(args):
         e, f = calc.evaluate_arrays(numbers, pos, counts)           # H2D, steps and D2H of every micro-batch
         t1 = time.perf_counter()
         if world > 1:
-            e_all, f_all = sharding.gather_in_order(e, f, sizes, device=dev)   # ordered gather of energies and forces
+            e_all, f_all = sharding.gather_in_order(e, f, sizes, device=dev, root=0)   # ordered gather of energies and forces on rank 0
         else:
             e_all, f_all = e, f
         torch.cuda.synchronize(dev)
@@ -461,8 +473,8 @@ def run_sweep(args):
         t_eval.append(float(dt[1].item()))
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.profile_read()["launches"]
-    assert len(e_all) == total and len(f_all) == int(sizes.sum())
     if rank == 0:
+        assert len(e_all) == total and len(f_all) == int(sizes.sum())
         best = int(np.argmin(times))
         value = total / times[best]
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": reps, "warmup": 2,
@@ -472,8 +484,8 @@ def run_sweep(args):
                                       f"{int(sizes.sum())} atoms), energy+forces, PaiNN student '{args.variant}', ONE host-side "
                                       "list partitioned over the ranks by atom count, results gathered in input order",
                           "variant": args.variant, "precision": args.precision, "filter_mode": args.filter_mode,
-                          "parallelism": f"structure-sharded x{world}; data path without collective, one ordered "
-                                         "all_gather of energies + forces at the end",
+                          "parallelism": f"structure-sharded x{world}; data path without collective; at the end every rank sends its "
+                                         "energies + forces point-to-point into its slice of rank 0's output",
                           "l2_policy": "every micro-batch is new data (>100 MB of inputs and results per pass)"},
                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(16 * sizes.sum() + 4 * total),
                        "d2h_bytes_per_step": int(12 * sizes.sum() + 4 * total),

@@ -8,7 +8,7 @@ system or a single MD trajectory does not shard ("replicas only").
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -54,14 +54,18 @@ def chunk_by_budget(counts: Sequence[int], max_atoms: int, max_structs: int) -> 
 
 
 def gather_in_order(local_energies: np.ndarray, local_forces: np.ndarray, counts: Sequence[int],
-                    group=None, device=None):
-    """Gather per-rank results into input order with TWO fixed-size collectives and no pickling.
+                    group=None, device=None, root: Optional[int] = None):
+    """Gather per-rank results into input order with fixed-size transfers and no pickling.
 
     ``counts`` is the global per-structure atom count list every rank already holds (the shards are a
-    pure function of it, :func:`partition_by_atoms`), so every rank knows every shard's size: the
-    local arrays are padded to the largest shard, exchanged with ``all_gather_into_tensor`` (float32,
-    4 B per structure + 12 B per atom), and the padding is cut away on the host.  Works with gloo
-    (CPU tensors, tests) and with nccl (``device`` = this rank's CUDA device)."""
+    pure function of it, :func:`partition_by_atoms`), so every rank knows every shard's size and its
+    place in the output.  Works with gloo (CPU tensors, tests) and with nccl (``device`` = this rank's
+    CUDA device).
+
+    ``root=None``: every rank receives everything (two padded ``all_gather_into_tensor`` calls).
+    ``root=r``: shards are contiguous in input order, so every other rank sends its slab point-to-point
+    straight into its slice of ONE output tensor on rank r (no padding, no concatenation; one
+    device-to-pinned-host copy); rank r returns ``(energies, forces)``, the others ``(None, None)``."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -72,10 +76,37 @@ def gather_in_order(local_energies: np.ndarray, local_forces: np.ndarray, counts
     n_atoms = [int(counts[a:b].sum()) for a, b in shards]
     local_energies = np.asarray(local_energies, dtype=np.float32).reshape(-1)
     local_forces = np.asarray(local_forces, dtype=np.float32).reshape(-1, 3)
-    if len(local_energies) != n_structs[rank] or len(local_forces) not in (0, n_atoms[rank]):
+    want_forces = len(local_forces) > 0 or n_atoms[rank] == 0
+    if len(local_energies) != n_structs[rank] or (want_forces and len(local_forces) != n_atoms[rank]):
         raise ValueError("local results do not match this rank's shard of `counts`")
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    device = torch.device(device)
+
+    if root is not None:
+        def to_root(local: np.ndarray, sizes, width: int):
+            starts = np.concatenate([[0], np.cumsum(sizes)])
+            mine = torch.from_numpy(np.ascontiguousarray(local).reshape(-1, width)).to(device)
+            if rank != root:
+                if sizes[rank]:
+                    dist.send(mine, dst=root, group=group)
+                return None
+            out = torch.empty((int(starts[-1]), width), dtype=torch.float32, device=device)
+            out[int(starts[root]):int(starts[root + 1])] = mine
+            for r in range(world):
+                if r != root and sizes[r]:
+                    dist.recv(out[int(starts[r]):int(starts[r + 1])], src=r, group=group)
+            if device.type == "cuda":
+                host = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+                host.copy_(out, non_blocking=False)
+                return host.numpy()
+            return out.numpy()
+
+        energies = to_root(local_energies, n_structs, 1)
+        forces = to_root(local_forces, n_atoms, 3) if want_forces else None
+        if rank != root:
+            return None, None
+        return energies.reshape(-1), (forces if want_forces else np.zeros((0, 3), dtype=np.float32))
 
     def exchange(local: np.ndarray, sizes, width: int) -> np.ndarray:
         cap = max(max(sizes), 1)
@@ -88,6 +119,5 @@ def gather_in_order(local_energies: np.ndarray, local_forces: np.ndarray, counts
         return np.concatenate([host[r, : sizes[r]] for r in range(world)])
 
     energies = exchange(local_energies, n_structs, 1).reshape(-1)
-    want_forces = len(local_forces) > 0 or n_atoms[rank] == 0
     forces = exchange(local_forces, n_atoms, 3) if want_forces else np.zeros((0, 3), dtype=np.float32)
     return energies, forces

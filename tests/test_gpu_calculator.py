@@ -346,7 +346,9 @@ def test_device_ids_spread_one_batch_over_the_gpus_of_the_process():
     z, pos, off = synthetic.concatenate(structs)
     e_m, f_m = multi.evaluate_arrays(z, pos, np.diff(off))
     e_s, f_s = single.evaluate_arrays(z, pos, np.diff(off))
-    assert np.array_equal(e_m, e_s) and np.array_equal(f_m, f_s)     # same kernels, same inputs, any GPU
+    # the kernels a call takes depend on its size (small-system path, tile shapes), so a shard and the whole
+    # list agree to rounding, not bit for bit
+    assert np.abs(e_m - e_s).max() / 80 <= 1e-6 and np.abs(f_m - f_s).max() <= 2e-5
     res = multi.calculate_batch(structs)
     assert len(res) == len(structs)
     assert all(r["forces"].shape == (len(s), 3) for r, s in zip(res, structs))

@@ -85,6 +85,11 @@ assert np.allclose(e, [pp[oo[i]:oo[i+1]].sum() for i in range(len(structs))], rt
 assert np.allclose(f, pp * 2.0, rtol=1e-6)
 e2, f2 = sharding.gather_in_order(e_local, np.zeros((0, 3)), counts)      # energies only (sweeps)
 assert np.array_equal(e2, e) and f2.shape == (0, 3)
+e3, f3 = sharding.gather_in_order(e_local, f_local, counts, root=0)        # point-to-point into rank 0's output
+if rank == 0:
+    assert np.array_equal(e3, e) and np.array_equal(f3, f)
+else:
+    assert e3 is None and f3 is None
 if rank == 0:
     print('GATHER_OK', a, b)
 dist.destroy_process_group()
