@@ -88,7 +88,7 @@ typedef struct mlffd_status {
     int32_t tc_saturated;    /* 1: an operand of a tensor-core dense layer left the FP16 range in this step
                                 (|activation| >= 8 125): energies / forces invalid -> call
                                 mlffd_set_dense_fallback(ctx, 1) and evaluate again */
-    int32_t reserved;
+    int32_t skin_rebuilds;   /* candidate-list builds since the skin list was (re)started (0 without a skin) */
 } mlffd_status;
 
 typedef struct mlffd_ctx mlffd_ctx;
@@ -167,6 +167,20 @@ int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out);
  * Valid once the stream has passed this point (record an event after the call).  Never synchronises.
  */
 int mlffd_status_async(mlffd_ctx* ctx, int32_t* status_out, void* stream);
+
+/*
+ * Verlet-skin neighbour list, an option; default 0 = the exact list is rebuilt
+ * from scratch on every call, like the reference does (student_model.py:694-703).  skin > 0 (Angstrom):
+ * a candidate list of all pairs within cutoff + skin is kept and rebuilt only when some atom has moved
+ * further than skin / 2 since it was built (decided on the device, no host synchronisation); every call
+ * still derives the EXACT d <= cutoff list from the candidates with the same pair test, so edges, their
+ * order and the geometry are bit-identical to the full build.  Meant for a trajectory of one system: the
+ * list is tied to (num_atoms, num_structures) and restarts when they change; call mlffd_set_skin again
+ * (or change the skin) after replacing the atoms or the cell of a same-sized system.  Periodic cells need
+ * heights >= 2 (cutoff + skin).  Frees the workspace: reserve again afterwards.  Systems of up to 64 atoms
+ * keep the one-launch exact kernel.
+ */
+int mlffd_set_skin(mlffd_ctx* ctx, float skin);
 
 /*
  * Range guard of the tensor-core precisions.  MLFFD_PREC_TC_FP16X2 / _TC_FP16 split operands into FP16

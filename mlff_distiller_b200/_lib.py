@@ -17,7 +17,7 @@ from typing import List, Optional
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libmlffd.so"
 SOURCES = ["mlffd.cu"]
-HEADERS = ["common.cuh", "edge_features.cuh", "neighbor.cuh", "cell_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh", "message_pipe.cuh", "message_team.cuh", "message_spline.cuh", "spline_table.h",
+HEADERS = ["common.cuh", "edge_features.cuh", "neighbor.cuh", "cell_list.cuh", "skin_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh", "message_pipe.cuh", "message_team.cuh", "message_spline.cuh", "spline_table.h",
            "update.cuh", "readout.cuh", "md.cuh", "../../include/mlffd.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -29,7 +29,7 @@ EXPORTS = [
     "mlffd_energy_forces", "mlffd_get_status", "mlffd_filter_table", "mlffd_debug_buffer",
     "mlffd_profile_enable", "mlffd_profile_read", "mlffd_stage_name",
     "mlffd_md_kick_drift", "mlffd_md_kick_energy", "mlffd_set_dense_fallback", "mlffd_virial",
-    "mlffd_status_async", "mlffd_filter_spline", "mlffd_edge_features", "mlffd_rbf_cutoff",
+    "mlffd_status_async", "mlffd_filter_spline", "mlffd_edge_features", "mlffd_rbf_cutoff", "mlffd_set_skin",
 ]
 NUM_STAGES = 10
 
@@ -51,7 +51,7 @@ class MlffdStatus(ctypes.Structure):
                 ("num_pairs", ctypes.c_int64), ("edge_capacity", ctypes.c_int64),
                 ("overflow", ctypes.c_int32), ("max_degree", ctypes.c_int32),
                 ("overflow_events", ctypes.c_int64), ("tc_saturated", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("skin_rebuilds", ctypes.c_int32)]
 
 
 class MlffdProfile(ctypes.Structure):
@@ -148,6 +148,8 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     lib.mlffd_profile_read.argtypes = [vp, ctypes.POINTER(MlffdProfile)]
     lib.mlffd_stage_name.restype = ctypes.c_char_p
     lib.mlffd_stage_name.argtypes = [i32]
+    lib.mlffd_set_skin.restype = ctypes.c_int
+    lib.mlffd_set_skin.argtypes = [vp, ctypes.c_float]
     lib.mlffd_set_dense_fallback.restype = ctypes.c_int
     lib.mlffd_set_dense_fallback.argtypes = [vp, i32]
     lib.mlffd_virial.restype = ctypes.c_int

@@ -83,7 +83,7 @@ class StudentForceFieldCalculator(_AseCalculator):
                  jit_path: Optional[Union[str, Path]] = None, use_torch_cluster: bool = True,
                  use_analytical_forces: bool = False, *, precision: str = "tc",
                  pbc_mode: str = "ignore", use_graph: bool = True, filter_mode: str = "spline",
-                 device_ids: Optional[Sequence[int]] = None, **kwargs):
+                 device_ids: Optional[Sequence[int]] = None, skin: float = 0.0, **kwargs):
         super().__init__(**kwargs)
         self.checkpoint_path = Path(checkpoint_path)
         # device_ids=[0, 1, ...]: ONE process drives several GPUs: this instance owns the
@@ -105,6 +105,7 @@ class StudentForceFieldCalculator(_AseCalculator):
         self.use_analytical_forces = use_analytical_forces
         self.precision = precision
         self.filter_mode = filter_mode
+        self.skin = float(skin)   # Verlet-skin neighbour list for trajectories of one system (0 = off, the reference's behaviour)
         self.pbc_mode = pbc_mode
         self.use_graph = use_graph   # replay single-structure steps as one CUDA graph once a system keeps coming back
         self.graph_after_calls = 3   # eager calls for a system before its step is captured
@@ -157,7 +158,7 @@ class StudentForceFieldCalculator(_AseCalculator):
         try:
             model = StudentForceField.load(source, device=str(self.device),
                                            precision=self.precision, pbc_mode=self.pbc_mode,
-                                           filter_mode=self.filter_mode)
+                                           filter_mode=self.filter_mode, skin=self.skin)
             model.eval()
             model.engine()  # fail loudly now if the CUDA library / device is missing
             return model
@@ -235,6 +236,10 @@ class StudentForceFieldCalculator(_AseCalculator):
                     raise ValueError(
                         f"pbc_mode='minimum_image' needs cell heights >= 2*cutoff "
                         f"({2 * self.model.cutoff:.2f} Å); axis {k} has {height:.3f} Å")
+                if height < 2.0 * (self.model.cutoff + self.skin):
+                    raise ValueError(
+                        f"skin={self.skin} needs periodic cell heights >= 2*(cutoff + skin) "
+                        f"({2 * (self.model.cutoff + self.skin):.2f} Å); axis {k} has {height:.3f} Å")
 
     def _evaluate_single(self, positions, numbers, cell, pbc, want_virial: bool = False):
         """One structure.  The first calls for a system run eagerly (size the workspace, grow it

@@ -42,7 +42,9 @@ __device__ __forceinline__ int grid_bin(const GridInfo& g, int k, float s) {
 __global__ void __launch_bounds__(256)
 grid_setup_kernel(const float* __restrict__ pos, const int* __restrict__ offsets,
                   const float* __restrict__ cells, const uint8_t* __restrict__ pbc, float cutoff,
-                  int max_cells_per_struct, GridInfo* __restrict__ grids, int* __restrict__ ncells) {
+                  int max_cells_per_struct, GridInfo* __restrict__ grids, int* __restrict__ ncells,
+                  const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;
     const int b = blockIdx.x;
     const int lo = offsets[b], hi = offsets[b + 1];
     __shared__ GridInfo g;
@@ -124,7 +126,9 @@ grid_setup_kernel(const float* __restrict__ pos, const int* __restrict__ offsets
 
 // serial prefix over structures (this path is taken for few, large structures)
 __global__ void grid_offsets_kernel(GridInfo* __restrict__ grids, const int* __restrict__ ncells,
-                                    int num_structures, int* __restrict__ total_cells) {
+                                    int num_structures, int* __restrict__ total_cells,
+                                    const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int acc = 0;
         for (int b = 0; b < num_structures; ++b) { grids[b].cell_offset = acc; acc += ncells[b]; }
@@ -143,7 +147,8 @@ __device__ __forceinline__ int atom_cell_id(const GridInfo& g, float x, float y,
 __global__ void __launch_bounds__(256)
 cell_count_kernel(const float* __restrict__ pos, const int* __restrict__ atom_struct,
                   const GridInfo* __restrict__ grids, int num_atoms, int* __restrict__ atom_cell,
-                  int* __restrict__ cell_count) {
+                  int* __restrict__ cell_count, const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < num_atoms; i += gridDim.x * blockDim.x) {
         const GridInfo g = grids[atom_struct[i]];
         int bin[3];
@@ -155,7 +160,9 @@ cell_count_kernel(const float* __restrict__ pos, const int* __restrict__ atom_st
 
 __global__ void __launch_bounds__(256)
 cell_fill_kernel(const int* __restrict__ atom_cell, const int* __restrict__ cell_start,
-                 int* __restrict__ cell_cursor, int num_atoms, int* __restrict__ cell_atoms) {
+                 int* __restrict__ cell_cursor, int num_atoms, int* __restrict__ cell_atoms,
+                 const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < num_atoms; i += gridDim.x * blockDim.x) {
         const int c = atom_cell[i];
         cell_atoms[cell_start[c] + atomicAdd(cell_cursor + c, 1)] = i;  // order inside a cell is irrelevant:
@@ -174,7 +181,8 @@ neighbor_cells_kernel(const float* __restrict__ pos, const int* __restrict__ ato
                       const int* __restrict__ rowptr, int* __restrict__ tmp_col,
                       float4* __restrict__ tmp_geo, int* __restrict__ col,
                       int* __restrict__ edge_dst, float4* __restrict__ geo,
-                      DeviceStatus* __restrict__ status) {
+                      DeviceStatus* __restrict__ status, const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;   // skin list: the candidate build is not due this step
     if (FILL && status->overflow) return;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;

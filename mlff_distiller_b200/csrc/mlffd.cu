@@ -30,6 +30,7 @@
 #include "message_spline.cuh"
 #include "neighbor.cuh"
 #include "readout.cuh"
+#include "skin_list.cuh"
 #include "update.cuh"
 
 using namespace mlffd;
@@ -45,6 +46,7 @@ struct LayerWeights {
 
 struct Workspace {
     int64_t cap_atoms = 0, cap_edges = 0, cap_structs = 0, cap_pairs = 0;
+    int64_t req_edges = 0;   // edge capacity the caller asked for (cap_edges is larger when a skin list needs room)
     void* arena = nullptr;
     size_t arena_bytes = 0;
     // graph
@@ -52,6 +54,10 @@ struct Workspace {
     int *col = nullptr, *edge_dst = nullptr, *rev = nullptr, *pair = nullptr;
     float4 *geo = nullptr, *edge_adj = nullptr;
     float4* erec = nullptr;   // [E][4] per-edge records of the spline message kernels (message_spline.cuh)
+    // Verlet-skin candidate list (skin_list.cuh), only when mlffd_set_skin > 0
+    SkinState* skin = nullptr;
+    int *cand_deg = nullptr, *cand_rowptr = nullptr, *cand_col = nullptr;
+    float* pos_ref = nullptr;
     double* virial64 = nullptr;      // [cap_structs][9] FP64 accumulators of mlffd_virial
     float* pair_dist = nullptr;
     // cell list (large structures)
@@ -83,6 +89,9 @@ struct mlffd_ctx {
     int H = 0, K = 0, L = 0;
     bool debug_keep = false;
     int neighbor_mode = 0;   // 0 auto, 1 sweep, 2 cells (env MLFFD_NEIGHBOR)
+    float skin = 0.f;                // mlffd_set_skin: Verlet-skin width in Angstrom (0 = exact rebuild every step)
+    int64_t skin_atoms = -1;         // system the candidate list belongs to (atoms, structures); a change invalidates it
+    int skin_structs = -1;
     bool dense_fallback = false;     // mlffd_set_dense_fallback: dense layers on the FP32 FFMA kernels whatever cfg.precision
     int readout_mode = 0;            // env MLFFD_READOUT: 0 = by size, 1 = tile, 2 = warp
     bool readout_configured = false; // smem attribute of readout_tile_kernel set on this device
@@ -735,34 +744,91 @@ int build_neighbors(mlffd_ctx* ctx, const float* pos, const int* offsets, int n_
     const int sweep_grid = clamp_grid(ceil_div(N, 8), kNumSMs * 16);
     const bool use_cells = ctx->neighbor_mode == 2 ||
                            (ctx->neighbor_mode == 0 && n_atoms >= (int64_t)2048 * n_structs);
+    const bool skin = ctx->skin > 0.f && ws.skin != nullptr;
+    // Candidate generator of the heavy count / fill passes: the whole structure (sweep), the 27 surrounding
+    // cells, or -- with a skin -- the candidate list, itself rebuilt by the same sweep / cell kernels with
+    // cutoff + skin whenever the device-side displacement check asks for it (skin_list.cuh).
     size_t bytes;
-    if (use_cells) {
-        const int C = (int)ws.cap_cells;
-        const int cap_per_struct = (int)std::max<int64_t>(8, 2 * (n_atoms / n_structs));
-        grid_setup_kernel<<<n_structs, 256, 0, st>>>(pos, offsets, cells, pbc, ctx->cfg.cutoff,
-                                                     cap_per_struct, ws.grids, ws.ncells);
-        LAUNCHED(ctx, "grid_setup_kernel", MLFFD_STAGE_NEIGHBOR, st);
-        grid_offsets_kernel<<<1, 32, 0, st>>>(ws.grids, ws.ncells, n_structs, ws.total_cells);
-        LAUNCHED(ctx, "grid_offsets_kernel", MLFFD_STAGE_NEIGHBOR, st);
-        CUDA_TRY(ctx, cudaMemsetAsync(ws.cell_count, 0, sizeof(int) * (C + 1), st));
-        CUDA_TRY(ctx, cudaMemsetAsync(ws.cell_cursor, 0, sizeof(int) * (C + 1), st));
-        const int atom_grid = clamp_grid(ceil_div(N, 256), kNumSMs * 8);
-        cell_count_kernel<<<atom_grid, 256, 0, st>>>(pos, ws.atom_struct, ws.grids, N, ws.atom_cell, ws.cell_count);
-        LAUNCHED(ctx, "cell_count_kernel", MLFFD_STAGE_NEIGHBOR, st);
-        bytes = ws.cub_bytes;
-        CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ws.cub_temp, bytes, ws.cell_count, ws.cell_start, C + 1, st));
-        mark(ctx, MLFFD_STAGE_NEIGHBOR, st, 2);
-        cell_fill_kernel<<<atom_grid, 256, 0, st>>>(ws.atom_cell, ws.cell_start, ws.cell_cursor, N, ws.cell_atoms);
-        LAUNCHED(ctx, "cell_fill_kernel", MLFFD_STAGE_NEIGHBOR, st);
-        neighbor_cells_kernel<false><<<sweep_grid, 256, 0, st>>>(
-            pos, ws.atom_struct, cells, ws.grids, ws.cell_start, ws.cell_atoms, N, ctx->cfg.cutoff,
-            ws.deg, ws.deg_low, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->status_d);
-        LAUNCHED(ctx, "neighbor_cells_kernel<count>", MLFFD_STAGE_NEIGHBOR, st);
+    auto candidate_pass = [&](bool fill, float cutoff, int* deg, int* deg_low, const int* rowptr, int* col,
+                              const int* gate) -> int {
+        if (use_cells) {
+            if (!fill) {
+                const int C = (int)ws.cap_cells;
+                const int cap_per_struct = (int)std::max<int64_t>(8, 2 * (n_atoms / n_structs));
+                grid_setup_kernel<<<n_structs, 256, 0, st>>>(pos, offsets, cells, pbc, cutoff, cap_per_struct, ws.grids,
+                                                             ws.ncells, gate);
+                LAUNCHED(ctx, "grid_setup_kernel", MLFFD_STAGE_NEIGHBOR, st);
+                grid_offsets_kernel<<<1, 32, 0, st>>>(ws.grids, ws.ncells, n_structs, ws.total_cells, gate);
+                LAUNCHED(ctx, "grid_offsets_kernel", MLFFD_STAGE_NEIGHBOR, st);
+                CUDA_TRY(ctx, cudaMemsetAsync(ws.cell_count, 0, sizeof(int) * (C + 1), st));
+                CUDA_TRY(ctx, cudaMemsetAsync(ws.cell_cursor, 0, sizeof(int) * (C + 1), st));
+                const int atom_grid = clamp_grid(ceil_div(N, 256), kNumSMs * 8);
+                cell_count_kernel<<<atom_grid, 256, 0, st>>>(pos, ws.atom_struct, ws.grids, N, ws.atom_cell, ws.cell_count, gate);
+                LAUNCHED(ctx, "cell_count_kernel", MLFFD_STAGE_NEIGHBOR, st);
+                size_t b2 = ws.cub_bytes;
+                CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ws.cub_temp, b2, ws.cell_count, ws.cell_start, C + 1, st));
+                mark(ctx, MLFFD_STAGE_NEIGHBOR, st, 2);
+                cell_fill_kernel<<<atom_grid, 256, 0, st>>>(ws.atom_cell, ws.cell_start, ws.cell_cursor, N, ws.cell_atoms, gate);
+                LAUNCHED(ctx, "cell_fill_kernel", MLFFD_STAGE_NEIGHBOR, st);
+                neighbor_cells_kernel<false><<<sweep_grid, 256, 0, st>>>(
+                    pos, ws.atom_struct, cells, ws.grids, ws.cell_start, ws.cell_atoms, N, cutoff,
+                    deg, deg_low, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->status_d, gate);
+                LAUNCHED(ctx, "neighbor_cells_kernel<count>", MLFFD_STAGE_NEIGHBOR, st);
+            } else {
+                // scratch for the unsorted rows: `rev` and `edge_adj` are only written by later kernels
+                neighbor_cells_kernel<true><<<sweep_grid, 256, 0, st>>>(
+                    pos, ws.atom_struct, cells, ws.grids, ws.cell_start, ws.cell_atoms, N, cutoff,
+                    nullptr, nullptr, rowptr, ws.rev, ws.edge_adj, col, ws.edge_dst, ws.geo, ctx->status_d, gate);
+                LAUNCHED(ctx, "neighbor_cells_kernel<fill>", MLFFD_STAGE_NEIGHBOR, st);
+            }
+        } else if (!fill) {
+            neighbor_sweep_kernel<false><<<sweep_grid, 256, 0, st>>>(
+                pos, offsets, ws.atom_struct, cells, pbc, N, cutoff, deg, deg_low, nullptr,
+                nullptr, nullptr, nullptr, ctx->status_d, gate);
+            LAUNCHED(ctx, "neighbor_sweep_kernel<count>", MLFFD_STAGE_NEIGHBOR, st);
+        } else {
+            neighbor_sweep_kernel<true><<<sweep_grid, 256, 0, st>>>(
+                pos, offsets, ws.atom_struct, cells, pbc, N, cutoff, nullptr, nullptr, rowptr,
+                col, ws.edge_dst, ws.geo, ctx->status_d, gate);
+            LAUNCHED(ctx, "neighbor_sweep_kernel<fill>", MLFFD_STAGE_NEIGHBOR, st);
+        }
+        return MLFFD_OK;
+    };
+    if (skin) {
+        if (ctx->skin_atoms != n_atoms || ctx->skin_structs != n_structs) {   // another system: no valid candidates
+            CUDA_TRY(ctx, cudaMemsetAsync(ws.skin, 0, sizeof(SkinState), st));
+            ctx->skin_atoms = n_atoms; ctx->skin_structs = n_structs;
+        }
+        const int* gate = &ws.skin->rebuild;
+        skin_check_kernel<<<clamp_grid(ceil_div(N, 256), kNumSMs * 4), 256, 0, st>>>(pos, ws.pos_ref, N, ws.skin);
+        LAUNCHED(ctx, "skin_check_kernel", MLFFD_STAGE_NEIGHBOR, st);
+        skin_decide_kernel<<<1, 32, 0, st>>>(ws.skin, 0.25f * ctx->skin * ctx->skin, ctx->status_d);
+        LAUNCHED(ctx, "skin_decide_kernel", MLFFD_STAGE_NEIGHBOR, st);
+        const float wide = ctx->cfg.cutoff + ctx->skin;
+        int rc = candidate_pass(false, wide, ws.cand_deg, ws.deg_low, nullptr, nullptr, gate);   // deg_low: scratch here
+        if (rc) return rc;
+        if (N <= 32768) {
+            neighbor_scan_small_kernel<<<1, 1024, 0, st>>>(ws.cand_deg, ws.deg_low, ws.cand_rowptr, ws.lowptr, N,
+                                                           (int)ws.cap_edges, nullptr);
+            LAUNCHED(ctx, "neighbor_scan_small_kernel", MLFFD_STAGE_NEIGHBOR, st);
+        } else {
+            bytes = ws.cub_bytes;
+            CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(ws.cub_temp, bytes, ws.cand_deg, ws.cand_rowptr, N + 1, st));
+            mark(ctx, MLFFD_STAGE_NEIGHBOR, st, 2);
+        }
+        skin_cand_finalize_kernel<<<1, 32, 0, st>>>(ws.cand_rowptr, N, (int)ws.cap_edges, ws.skin, ctx->status_d);
+        LAUNCHED(ctx, "skin_cand_finalize_kernel", MLFFD_STAGE_NEIGHBOR, st);
+        rc = candidate_pass(true, wide, nullptr, nullptr, ws.cand_rowptr, ws.cand_col, gate);
+        if (rc) return rc;
+        skin_copy_ref_kernel<<<clamp_grid(ceil_div(3 * N, 256), kNumSMs * 4), 256, 0, st>>>(pos, ws.pos_ref, 3 * N, ws.skin);
+        LAUNCHED(ctx, "skin_copy_ref_kernel", MLFFD_STAGE_NEIGHBOR, st);
+        neighbor_cand_kernel<false><<<sweep_grid, 256, 0, st>>>(
+            pos, ws.atom_struct, cells, pbc, N, ctx->cfg.cutoff, ws.cand_rowptr, ws.cand_col, ws.deg, ws.deg_low,
+            nullptr, nullptr, nullptr, nullptr, ws.skin, ctx->status_d);
+        LAUNCHED(ctx, "neighbor_cand_kernel<count>", MLFFD_STAGE_NEIGHBOR, st);
     } else {
-        neighbor_sweep_kernel<false><<<sweep_grid, 256, 0, st>>>(
-            pos, offsets, ws.atom_struct, cells, pbc, N, ctx->cfg.cutoff, ws.deg, ws.deg_low, nullptr,
-            nullptr, nullptr, nullptr, ctx->status_d);
-        LAUNCHED(ctx, "neighbor_sweep_kernel<count>", MLFFD_STAGE_NEIGHBOR, st);
+        int rc = candidate_pass(false, ctx->cfg.cutoff, ws.deg, ws.deg_low, nullptr, nullptr, nullptr);
+        if (rc) return rc;
     }
     if (N <= 32768) {   // latency path: one launch instead of five
         neighbor_scan_small_kernel<<<1, 1024, 0, st>>>(ws.deg, ws.deg_low, ws.rowptr, ws.lowptr, N,
@@ -778,17 +844,16 @@ int build_neighbors(mlffd_ctx* ctx, const float* pos, const int* offsets, int n_
                                                    ctx->status_d);
         LAUNCHED(ctx, "neighbor_finalize_kernel", MLFFD_STAGE_NEIGHBOR, st);
     }
-    if (use_cells) {
-        // scratch for the unsorted rows: `rev` and `edge_adj` are only written by later kernels
-        neighbor_cells_kernel<true><<<sweep_grid, 256, 0, st>>>(
-            pos, ws.atom_struct, cells, ws.grids, ws.cell_start, ws.cell_atoms, N, ctx->cfg.cutoff,
-            nullptr, nullptr, ws.rowptr, ws.rev, ws.edge_adj, ws.col, ws.edge_dst, ws.geo, ctx->status_d);
-        LAUNCHED(ctx, "neighbor_cells_kernel<fill>", MLFFD_STAGE_NEIGHBOR, st);
+    if (skin) {
+        skin_merge_status_kernel<<<1, 32, 0, st>>>(ws.skin, ctx->status_d);
+        LAUNCHED(ctx, "skin_merge_status_kernel", MLFFD_STAGE_NEIGHBOR, st);
+        neighbor_cand_kernel<true><<<sweep_grid, 256, 0, st>>>(
+            pos, ws.atom_struct, cells, pbc, N, ctx->cfg.cutoff, ws.cand_rowptr, ws.cand_col, nullptr, nullptr,
+            ws.rowptr, ws.col, ws.edge_dst, ws.geo, ws.skin, ctx->status_d);
+        LAUNCHED(ctx, "neighbor_cand_kernel<fill>", MLFFD_STAGE_NEIGHBOR, st);
     } else {
-        neighbor_sweep_kernel<true><<<sweep_grid, 256, 0, st>>>(
-            pos, offsets, ws.atom_struct, cells, pbc, N, ctx->cfg.cutoff, nullptr, nullptr, ws.rowptr,
-            ws.col, ws.edge_dst, ws.geo, ctx->status_d);
-        LAUNCHED(ctx, "neighbor_sweep_kernel<fill>", MLFFD_STAGE_NEIGHBOR, st);
+        int rc = candidate_pass(true, ctx->cfg.cutoff, nullptr, nullptr, ws.rowptr, ws.col, nullptr);
+        if (rc) return rc;
     }
     reverse_pair_kernel<<<clamp_grid(ceil_div(std::max<int64_t>(ws.cap_edges, 1), 256), kNumSMs * 8),
                           256, 0, st>>>(ws.rowptr, ws.lowptr, ws.col, ws.edge_dst, ws.geo, ws.rev,
@@ -1073,10 +1138,15 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
                                        int64_t max_structures) {
     if (!ctx) return MLFFD_EINVAL;
     Workspace& ws = ctx->ws;
-    if (max_atoms <= ws.cap_atoms && max_edges <= ws.cap_edges && max_structures <= ws.cap_structs)
+    if (max_atoms <= ws.cap_atoms && max_edges <= ws.req_edges && max_structures <= ws.cap_structs)
         return MLFFD_OK;
     max_atoms = std::max<int64_t>(std::max(max_atoms, ws.cap_atoms), 1);
-    max_edges = std::max<int64_t>(std::max(max_edges, ws.cap_edges), 2);
+    max_edges = std::max<int64_t>(std::max(max_edges, ws.req_edges), 2);
+    const int64_t requested_edges = max_edges;
+    if (ctx->skin > 0.f) {   // room for the candidate list: all pairs within cutoff + skin
+        const double r = (ctx->cfg.cutoff + ctx->skin) / ctx->cfg.cutoff;
+        max_edges = (int64_t)(max_edges * r * r * r * 1.15) + 64;
+    }
     max_structures = std::max<int64_t>(std::max(max_structures, ws.cap_structs), 1);
     if (max_atoms >= (1ll << 30) || max_edges >= (1ll << 31) - 64)
         return fail(ctx, MLFFD_EINVAL, "workspace request exceeds 32-bit indexing");
@@ -1101,6 +1171,12 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
     // per-layer (spline mode: per-layer, per-slice) slabs + debug sum
     const size_t o_adj = plan.take(sizeof(float4) * E * ((size_t)L * ctx->adj_slabs_per_layer + 1));
     const size_t o_erec = plan.take(ctx->spline ? sizeof(float4) * 4 * E : 0);
+    const bool skin_on = ctx->skin > 0.f;
+    const size_t o_skin = plan.take(skin_on ? sizeof(SkinState) : 0);
+    const size_t o_cand_deg = plan.take(skin_on ? sizeof(int) * (N + 1) : 0);
+    const size_t o_cand_rowptr = plan.take(skin_on ? sizeof(int) * (N + 1) : 0);
+    const size_t o_cand_col = plan.take(skin_on ? sizeof(int) * E : 0);
+    const size_t o_pos_ref = plan.take(skin_on ? sizeof(float) * 3 * N : 0);
     const int64_t PT = ctx->spline ? 0 : P;   // the per-step filter tables exist in MLFFD_FILTER_TABLE mode only
     const size_t o_pdist = plan.take(sizeof(float) * P);
     const size_t o_eps = plan.take(sizeof(float) * N);
@@ -1150,6 +1226,7 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
     char* base = (char*)arena;
     ws.arena = arena; ws.arena_bytes = plan.total;
     ws.cap_atoms = N; ws.cap_edges = E; ws.cap_structs = max_structures; ws.cap_pairs = P;
+    ws.req_edges = requested_edges;
     ws.atom_struct = (int*)(base + o_atom_struct);
     ws.deg = (int*)(base + o_deg); ws.deg_low = (int*)(base + o_deg_low);
     ws.rowptr = (int*)(base + o_rowptr); ws.lowptr = (int*)(base + o_lowptr);
@@ -1157,6 +1234,14 @@ extern "C" int mlffd_workspace_reserve(mlffd_ctx* ctx, int64_t max_atoms, int64_
     ws.rev = (int*)(base + o_rev); ws.pair = (int*)(base + o_pair);
     ws.geo = (float4*)(base + o_geo); ws.edge_adj = (float4*)(base + o_adj);
     ws.erec = (float4*)(base + o_erec);
+    if (skin_on) {
+        ws.skin = (SkinState*)(base + o_skin);
+        ws.cand_deg = (int*)(base + o_cand_deg); ws.cand_rowptr = (int*)(base + o_cand_rowptr);
+        ws.cand_col = (int*)(base + o_cand_col); ws.pos_ref = (float*)(base + o_pos_ref);
+        CUDA_TRY(ctx, cudaMemset(ws.skin, 0, sizeof(SkinState)));          // no valid candidate list yet
+        CUDA_TRY(ctx, cudaMemset(ws.cand_deg, 0, sizeof(int) * (N + 1)));
+        ctx->skin_atoms = -1;
+    }
     ws.pair_dist = (float*)(base + o_pdist);
     ws.eps = (float*)(base + o_eps);
     ws.virial64 = (double*)(base + o_virial);
@@ -1247,7 +1332,12 @@ extern "C" int mlffd_get_status(mlffd_ctx* ctx, mlffd_status* out) {
     out->max_degree = h.max_degree;
     out->overflow_events = h.overflow_events;
     out->tc_saturated = h.tc_saturated;
-    out->reserved = 0;
+    out->skin_rebuilds = 0;
+    if (ctx->ws.skin != nullptr) {
+        SkinState sk{};
+        CUDA_TRY(ctx, cudaMemcpy(&sk, ctx->ws.skin, sizeof(sk), cudaMemcpyDeviceToHost));
+        out->skin_rebuilds = sk.rebuilds;
+    }
     return MLFFD_OK;
 }
 
@@ -1435,6 +1525,18 @@ extern "C" int mlffd_md_kick_energy(const mlffd_ctx* guard, int64_t num_atoms, d
                                                     series_d, counter_d, capacity, g);
     }
     return cudaGetLastError() == cudaSuccess ? MLFFD_OK : MLFFD_ECUDA;
+}
+
+extern "C" int mlffd_set_skin(mlffd_ctx* ctx, float skin) {
+    if (!ctx || !(skin >= 0.f) || skin > 4.0f * ctx->cfg.cutoff) return ctx ? fail(ctx, MLFFD_EINVAL, "mlffd_set_skin: bad skin") : MLFFD_EINVAL;
+    if (skin == ctx->skin) return MLFFD_OK;
+    DeviceGuard device_guard(ctx->device);
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    ctx->skin = skin;
+    ctx->skin_atoms = -1;
+    if (ctx->ws.arena) { cudaFree(ctx->ws.arena); ctx->ws = Workspace(); }   // the next mlffd_workspace_reserve sizes the candidate buffers
+    ctx->last_adj_slabs = 0;
+    return MLFFD_OK;
 }
 
 extern "C" int mlffd_set_dense_fallback(mlffd_ctx* ctx, int32_t enable) {

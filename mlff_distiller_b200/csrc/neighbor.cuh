@@ -41,7 +41,8 @@ neighbor_sweep_kernel(const float* __restrict__ pos, const int* __restrict__ off
                       int* __restrict__ deg, int* __restrict__ deg_low,
                       const int* __restrict__ rowptr, int* __restrict__ col,
                       int* __restrict__ edge_dst, float4* __restrict__ geo,
-                      DeviceStatus* __restrict__ status) {
+                      DeviceStatus* __restrict__ status, const int* __restrict__ gate = nullptr) {
+    if (gate != nullptr && *gate == 0) return;   // skin list: the candidate build is not due this step
     if (FILL && status->overflow) return;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
@@ -113,7 +114,7 @@ __global__ void neighbor_finalize_kernel(const int* __restrict__ rowptr,
 __global__ void __launch_bounds__(1024)
 neighbor_scan_small_kernel(const int* __restrict__ deg, const int* __restrict__ deg_low,
                            int* __restrict__ rowptr, int* __restrict__ lowptr, int num_atoms,
-                           int edge_capacity, DeviceStatus* __restrict__ status) {
+                           int edge_capacity, DeviceStatus* __restrict__ status /* may be NULL: scan only */) {
     __shared__ int warp_a[32], warp_b[32];
     const int n = num_atoms + 1;   // deg[num_atoms] == 0 closes the CSR
     const int chunk = (n + 1023) / 1024;
@@ -146,7 +147,7 @@ neighbor_scan_small_kernel(const int* __restrict__ deg, const int* __restrict__ 
         rowptr[i] = pa; lowptr[i] = pb;
         pa += deg[i]; pb += deg_low[i];
     }
-    if (threadIdx.x == 1023) {
+    if (threadIdx.x == 1023 && status != nullptr) {
         const int e = warp_a[31];
         status->num_edges = e;
         status->num_pairs = warp_b[31];

@@ -63,6 +63,7 @@ class Engine:
         self._ctx = handle
         self.profiling = False
         self.dense_fallback = False
+        self.skin = 0.0
         self.saturation_reruns = 0   # calls repeated on the FP32 kernels because a tensor-core operand saturated
         self.cap_atoms = self.cap_edges = self.cap_structs = 0
 
@@ -121,6 +122,12 @@ class Engine:
         self._check(self.lib.mlffd_neighbor_list(
             self._ctx, _ptr(pos), _ptr(offsets), int(n_structs), int(pos.shape[0]), _ptr(cells),
             _ptr(pbc), self._stream()))
+
+    def set_skin(self, skin: float):
+        """Verlet-skin width in Angstrom (0 = exact rebuild every call).  Frees the workspace."""
+        self._check(self.lib.mlffd_set_skin(self._ctx, float(skin)))
+        self.skin = float(skin)
+        self.cap_atoms = self.cap_edges = self.cap_structs = 0
 
     def set_dense_fallback(self, enable: bool):
         """Run the dense layers on the FP32 FFMA kernels (True) or as the precision says (False).

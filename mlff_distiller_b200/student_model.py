@@ -116,7 +116,7 @@ class StudentForceField(nn.Module):
     def __init__(self, hidden_dim: int = 128, num_interactions: int = 3, num_rbf: int = 20,
                  cutoff: float = 5.0, max_z: int = 118, learnable_rbf: bool = False,
                  use_torch_cluster: bool = True, *, precision: str = "tc",
-                 pbc_mode: str = "ignore", filter_mode: str = "spline"):
+                 pbc_mode: str = "ignore", filter_mode: str = "spline", skin: float = 0.0):
         super().__init__()
         if pbc_mode not in ("ignore", "minimum_image"):
             raise ValueError("pbc_mode must be 'ignore' or 'minimum_image'")
@@ -129,6 +129,7 @@ class StudentForceField(nn.Module):
         self.precision = precision
         self.pbc_mode = pbc_mode
         self.filter_mode = filter_mode   # 'spline' (per-model filter splines in shared memory) | 'table'
+        self.skin = float(skin)          # Verlet-skin width in Angstrom (0 = the list is rebuilt exactly every call, as the reference does)
         self.embedding = nn.Embedding(max_z + 1, hidden_dim)
         self.rbf = _RBFBuffers(num_rbf, cutoff, learnable_rbf)
         self.interactions = nn.ModuleList(
@@ -198,6 +199,8 @@ class StudentForceField(nn.Module):
             if self._engine is not None:
                 self._engine.close()
             self._engine = Engine(state, self.config, dev, self.precision, self.filter_mode)
+            if self.skin > 0.0:
+                self._engine.set_skin(self.skin)
             self._engine_key = key
         return self._engine
 

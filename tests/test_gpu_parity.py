@@ -702,3 +702,52 @@ def test_team_message_kernels_match_row_per_warp_kernels(variant_name):
     e_ref, f_ref = po.evaluate(state, cfg["cutoff"], z, pos, off, dtype=torch.float64, dense_graph=False)
     assert np.max(np.abs(e_t - e_ref) / np.diff(off)) <= E_TOL
     assert np.max(np.abs(f_t - f_ref)) <= F_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# Verlet-skin neighbour list: an option, bit-identical to the full rebuild
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("system", ["chain300_sweep", "water_box_3000_cells"])
+def test_skin_list_is_bit_identical_to_the_full_rebuild(system):
+    """A random walk of the positions: the exact list derived from the skin candidates must equal the
+    full rebuild's in every array (row starts, sources, reverse indices, geometry), whether the step
+    reuses the candidate list or rebuilds it; rebuilds must happen, and not on every step."""
+    from mlff_distiller_b200 import synthetic
+    from mlff_distiller_b200.student_model import StudentForceField
+    exact, state, cfg = _model("ultra_tiny", pbc_mode="minimum_image")
+    skinned, _, _ = _model("ultra_tiny", pbc_mode="minimum_image", skin=1.0)
+    if system == "chain300_sweep":
+        s = synthetic.alkane_chain(100)
+        pos, cells, pbc = s.positions.astype(np.float32), None, None
+    else:
+        box = synthetic.water_box(n_mol=1000, seed=3004)
+        pos, cells, pbc = box.positions.astype(np.float32), box.cell[None], box.pbc[None]
+    n = len(pos)
+    off = torch.tensor([0, n], dtype=torch.int32, device="cuda")
+    c_d = b_d = None
+    if cells is not None:
+        c_d, b_d = StudentForceField.pack_cells(torch.from_numpy(cells), torch.from_numpy(pbc), 1, "cuda:0")
+    rng = np.random.default_rng(5)
+    steps = 40
+    for step in range(steps):
+        pos = (pos + rng.normal(0.0, 0.04, pos.shape)).astype(np.float32)
+        p_d = torch.from_numpy(pos).cuda()
+        out = []
+        for model in (exact, skinned):
+            eng = model.engine()
+            eng.ensure(n, 1, 80)
+            eng.neighbor_list_async(p_d, off, 1, c_d, b_d)
+            st = eng.status()
+            assert not st.overflow
+            out.append({k: eng.debug_buffer(k).cpu().numpy() for k in ("rowptr", "col", "rev", "edge_dst", "geo")})
+        assert out[0]["col"].size > 1000
+        for k in out[0]:
+            assert np.array_equal(out[0][k], out[1][k]), (step, k)
+    rebuilds = int(skinned.engine().status().skin_rebuilds)
+    assert 1 <= rebuilds < steps, rebuilds
+    assert int(exact.engine().status().skin_rebuilds) == 0
+    # energies and forces through the same lists
+    z = np.full(n, 6, dtype=np.int64) if system == "chain300_sweep" else box.numbers
+    e0, f0 = _run(exact, z, pos, [0, n], cells, pbc)
+    e1, f1 = _run(skinned, z, pos, [0, n], cells, pbc)
+    assert np.array_equal(e0, e1) and np.array_equal(f0, f1)
