@@ -53,7 +53,7 @@ enum {
  * the message kernels.  It depends on the distance only, never on the structure. */
 enum {
     MLFFD_FILTER_SPLINE = 0, /* default: a quintic B-spline of every component function on [0, cutoff]
-                                (256 intervals) built once per model in FP64; the message kernels keep a
+                                (192 intervals) built once per model in FP64; the message kernels keep a
                                 32-channel slice of it in shared memory and evaluate value and
                                 d-derivative per edge.  Nothing per-pair is written to HBM.  Stated bound:
                                 |f - spline| <= 2e-7, |f' - spline'| <= 1e-5 / Angstrom as functions (FP64

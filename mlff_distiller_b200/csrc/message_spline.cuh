@@ -6,7 +6,7 @@
 // quintic B-spline of spline_table.h instead of the two dense layers of rbf_to_scalar.
 //
 // Decomposition: the H channels are cut into slices of 32.  A CTA owns ONE slice of ONE layer: its
-// (256 + 5) x 3 x 32 coefficient block (100 224 B) sits in shared memory for the whole launch.  Eight
+// (192 + 5) x 3 x 32 coefficient block (75 648 B) sits in shared memory for the whole launch.  Eight
 // lanes own a CSR row (one float4 of channels per lane, 4 rows per warp) and accumulate it in
 // registers in source-ascending order -- the order the reference's CPU index_add_ applies: no atomics,
 // bit-reproducible.  The four row groups of a warp advance through their own row sequences
@@ -28,7 +28,7 @@ namespace mlffd {
 
 constexpr int kSplineRowFloat4 = 3 * kSliceChannels / 4;          // float4 per table row: 24
 constexpr int kSplineSliceFloat4 = kSplineRows * kSplineRowFloat4;
-constexpr size_t kSplineSmemBytes = (size_t)kSplineSliceFloat4 * sizeof(float4);   // 100 224 B
+constexpr size_t kSplineSmemBytes = (size_t)kSplineSliceFloat4 * sizeof(float4);   // 75 648 B
 
 // ---- packed FP32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): four floats = two 64-bit registers ----
 typedef ulonglong2 pk4;

@@ -141,6 +141,7 @@ __global__ void skin_merge_status_kernel(const SkinState* __restrict__ skin, Dev
     if (threadIdx.x == 0 && blockIdx.x == 0 && skin->cand_overflow) {
         status->overflow = 1;
         status->overflow_events += 1;
+        status->num_edges = skin->cand_edges;   // what the caller has to make room for (the exact list is a subset)
     }
 }
 

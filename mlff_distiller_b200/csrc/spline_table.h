@@ -9,10 +9,12 @@
 // (message_spline.cuh) evaluate value and d-derivative from the same six coefficients, so the
 // forces stay the exact gradient of the (interpolated) energy.
 //
-// Stated bound (tests/test_gpu_parity.py:test_filter_spline_matches_oracle, tools/spline_error.py):
-// with 256 intervals the interpolation error of the trained Original / Tiny / Ultra-tiny filters is
-// <= 3e-9 in value and <= 5e-7 per Angstrom in derivative (max |f| ~ 2.5, max |f'| ~ 5), i.e. below
-// the FP32 rounding of the quantities themselves.
+// Stated bound (tests/test_spline_host.py, tests/test_gpu_parity.py:test_filter_spline_matches_oracle):
+// with 192 intervals the interpolation error of the trained Original / Tiny / Ultra-tiny filters is
+// <= 2e-8 in value and <= 2e-6 per Angstrom in derivative in exact arithmetic (max |f| ~ 2.5, max |f'| ~ 5),
+// below the FP32 rounding of the stored coefficients, which dominates the total: <= 1e-7 / 6e-6 measured
+// for any interval count between 160 and 256 (fewer intervals = less amplification of the coefficient
+// rounding in the derivative, 1 / h; more = less truncation).
 //
 // Collocation: n + 5 coefficients are fixed by f at the n + 1 knots plus the midpoints of the first
 // two and last two intervals (Schoenberg-Whitney holds: site s lies inside the support of basis s).
@@ -26,7 +28,10 @@
 
 namespace mlffd {
 
-constexpr int kSplineIntervals = 256;
+#ifndef MLFFD_SPLINE_INTERVALS
+#define MLFFD_SPLINE_INTERVALS 192
+#endif
+constexpr int kSplineIntervals = MLFFD_SPLINE_INTERVALS;
 constexpr int kSplineDegree = 5;
 constexpr int kSplineRows = kSplineIntervals + kSplineDegree;   // coefficients per component function
 constexpr int kSliceChannels = 32;                              // channels of one shared-memory table slice
