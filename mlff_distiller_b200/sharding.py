@@ -53,6 +53,18 @@ def chunk_by_budget(counts: Sequence[int], max_atoms: int, max_structs: int) -> 
     return out
 
 
+_PINNED = {}   # (rows, width) -> pinned host tensor reused by the root of gather_in_order
+
+
+def _pinned(rows: int, width: int):
+    import torch
+    key = (width,)
+    buf = _PINNED.get(key)
+    if buf is None or buf.shape[0] < rows:
+        buf = _PINNED[key] = torch.empty((max(rows, 1), width), dtype=torch.float32).pin_memory()
+    return buf[:rows]
+
+
 def gather_in_order(local_energies: np.ndarray, local_forces: np.ndarray, counts: Sequence[int],
                     group=None, device=None, root: Optional[int] = None):
     """Gather per-rank results into input order with fixed-size transfers and no pickling.
@@ -97,9 +109,9 @@ def gather_in_order(local_energies: np.ndarray, local_forces: np.ndarray, counts
                 if r != root and sizes[r]:
                     dist.recv(out[int(starts[r]):int(starts[r + 1])], src=r, group=group)
             if device.type == "cuda":
-                host = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+                host = _pinned(out.shape[0], width)      # page-locked once, reused by every later gather
                 host.copy_(out, non_blocking=False)
-                return host.numpy()
+                return host.numpy().copy()
             return out.numpy()
 
         energies = to_root(local_energies, n_structs, 1)

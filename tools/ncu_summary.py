@@ -16,6 +16,12 @@ WANT = [
     "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem",
     "launch__occupancy_limit_registers", "lts__t_sector_hit_rate.pct",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__t_sector_hit_rate.pct",
+    "smsp__thread_inst_executed_per_inst_executed.ratio",
 ]
 
 
