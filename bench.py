@@ -681,7 +681,8 @@ def run_b200(args):
     traffic = None   # dram bytes per launch of the same kernel from the committed ncu --set full capture
     tfile = ROOT / "profiles" / "ncu_traffic.json"
     if tfile.exists():
-        traffic = json.loads(tfile.read_text()).get(args.precision, {}).get(top)
+        tkey = "spline" if args.filter_mode == "spline" else args.precision
+        traffic = json.loads(tfile.read_text()).get(tkey, {}).get(top)
     roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
                 "frac": achieved / peak if achieved else None, "traffic": traffic,
                 "peak_source": peaks["source"],
