@@ -15,7 +15,8 @@ from pathlib import Path
 from typing import List, Optional
 
 CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = CSRC / "libmlffd.so"
+# MLFFD_LIB: load another build of the same sources (kernel A/B experiments, tools/); the default is the in-tree library
+LIB_PATH = Path(os.environ["MLFFD_LIB"]) if os.environ.get("MLFFD_LIB") else CSRC / "libmlffd.so"
 SOURCES = ["mlffd.cu"]
 HEADERS = ["common.cuh", "edge_features.cuh", "neighbor.cuh", "cell_list.cuh", "skin_list.cuh", "tile_gemm.cuh", "filter.cuh", "filter_umma.cuh", "umma_rows.cuh", "message.cuh", "message_pipe.cuh", "message_team.cuh", "message_spline.cuh", "spline_table.h",
            "update.cuh", "readout.cuh", "md.cuh", "../../include/mlffd.h"]

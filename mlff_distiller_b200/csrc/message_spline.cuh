@@ -300,11 +300,20 @@ __device__ __forceinline__ float group8_sum4(const float (&v)[4], int l8, unsign
 //        edge_adj (this layer's, this slice's slab): (dE/du_x, dE/du_y, dE/du_z, dE/dd through the
 //        filter) of every directed edge restricted to the slice's channels; the force kernel sums the
 //        L x slices slabs.
-// Row i handles its directed edges e = (j -> i) one by one (uniform work, no pairing):
-//   gate adjoints  a_bar = s_j * s_bar'_i,  b_bar = sum_x v_j[x] * v_bar'_i[x],  c_bar = sum_x u[x] v_bar'_i[x]
-//   d_bar_e = a_bar . a'(d) + b_bar . b'(d) + c_bar . c'(d)      u_bar_e[x] = c(d) . v_bar'_i[x]
-// and, because edge (i -> j) shares the filter (same distance), the scatter to SOURCE atoms becomes a
-// gather over the same row:  s_bar_i += a(d) * s_bar'_j,  v_bar_i[x] += b(d) * v_bar'_j[x].
+// Row i walks its CSR entries e = (j -> i) one by one (uniform work, no pairing).  Edge e and its reverse
+// r = (i -> j) have the same distance, hence the same filter, and u_r = -u_e.
+// LAYER0 (v_in == 0, no input adjoints): the entry's own adjoint, from the gathered s_j and the row's adjoints:
+//   a_bar = s_j * s_bar'_i,  c_bar = sum_x u_e[x] v_bar'_i[x],  d_bar_e = a_bar . a'(d) + c_bar . c'(d),
+//   u_bar_e[x] = c(d) . v_bar'_i[x]                                   -> slab[e] = adjoint of e   ("direct" slab)
+// other layers: everything row i computes comes from the REVERSE edge r, whose source is i itself, so one
+// gather of the neighbour's adjoints (s_bar'_j, v_bar'_j: 4 x 128 B) serves both the scatter-turned-gather
+//   s_bar_i += a(d) * s_bar'_j,  v_bar_i[x] += b(d) * v_bar'_j[x]
+// and the edge adjoint of r, with the row's own FEATURES (registers) in place of gathered ones:
+//   a_bar = s_i * s_bar'_j,  b_bar = sum_x v_i[x] * v_bar'_j[x],  c_bar = -sum_x u_e[x] v_bar'_j[x],
+//   d_bar_r = a_bar . a' + b_bar . b' + c_bar . c',  u_bar_r[x] = c(d) . v_bar'_j[x]
+//                                                                     -> slab[e] = adjoint of rev(e) ("swapped" slab)
+// The force / virial kernels (readout.cuh) read both e and rev(e) anyway and know which slabs are swapped.
+// Half the gathers of a formulation that computes the adjoint of e itself (features AND adjoints of j).
 // The filter MLP is never back-propagated: f' is the exact derivative of the spline the forward used.
 // ---------------------------------------------------------------------------------------------
 template <bool LAYER0, int THREADS, int MIN_CTAS>
@@ -329,9 +338,11 @@ spline_message_backward_kernel(const float* __restrict__ table, int H,
     const int held = ((l8 & 4) ? 2 : 0) + ((l8 & 2) ? 1 : 0);   // which reduced value this lane ends up with
     RowCursor c;
     c.init(part * kGroups + sub, parts * kGroups, rowptr, erec, num_atoms);
+    // LAYER0: the row's adjoints (sb, vb*);  other layers: the row's features (own_s, own_*)
     pk4 sb = pk_zero(), vbx = pk_zero(), vby = pk_zero(), vbz = pk_zero();
+    pk4 own_s = pk_zero(), own_x = pk_zero(), own_y = pk_zero(), own_z = pk_zero();
     pk4 acc_s = pk_zero(), acc_x = pk_zero(), acc_y = pk_zero(), acc_z = pk_zero();
-    bool had_edges = false, loaded = false;   // loaded: the row's own adjoints are in registers
+    bool had_edges = false, loaded = false;   // loaded: the row's own vectors are in registers
     while (__any_sync(0xffffffffu, c.row < num_atoms)) {
         if (c.row < num_atoms && loaded && c.e == c.e_end) {   // row complete: write it out, take the next one
             if (!LAYER0) {
@@ -344,12 +355,19 @@ spline_message_backward_kernel(const float* __restrict__ table, int H,
             had_edges = false;
             loaded = false;
         }
-        if (c.row < num_atoms && !loaded) {   // the row's own adjoints; they also start the residual path
+        if (c.row < num_atoms && !loaded) {
             const int i = c.row;
-            sb = pk_ldg(sbar_m + (size_t)i * H + ch);
             const float* vb = vbar_m + (size_t)i * 3 * H + ch;
-            vbx = pk_ldg(vb); vby = pk_ldg(vb + H); vbz = pk_ldg(vb + 2 * H);
-            acc_s = sb; acc_x = vbx; acc_y = vby; acc_z = vbz;
+            if (LAYER0) {
+                sb = pk_ldg(sbar_m + (size_t)i * H + ch);
+                vbx = pk_ldg(vb); vby = pk_ldg(vb + H); vbz = pk_ldg(vb + 2 * H);
+            } else {   // the row's adjoints start the residual path; its features stay for the edge adjoints
+                acc_s = pk_ldg(sbar_m + (size_t)i * H + ch);
+                acc_x = pk_ldg(vb); acc_y = pk_ldg(vb + H); acc_z = pk_ldg(vb + 2 * H);
+                own_s = pk_ldg(s_in + (size_t)i * H + ch);
+                const float* vi = v_in + (size_t)i * 3 * H + ch;
+                own_x = pk_ldg(vi); own_y = pk_ldg(vi + H); own_z = pk_ldg(vi + 2 * H);
+            }
             loaded = true;
         }
         const bool active = c.row < num_atoms && c.e < c.e_end;
@@ -358,14 +376,13 @@ spline_message_backward_kernel(const float* __restrict__ table, int H,
             const int e = c.e;
             const float4 g = c.take_head(erec);   // (source, unit vector)
             const int j = __float_as_int(g.x);
-            const pk4 sj = pk_ldg(s_in + (size_t)j * H + ch);
-            pk4 vjx, vjy, vjz, sbj, vbjx, vbjy, vbjz;
-            if (!LAYER0) {
-                const float* vj = v_in + (size_t)j * 3 * H + ch;
-                vjx = pk_ldg(vj); vjy = pk_ldg(vj + H); vjz = pk_ldg(vj + 2 * H);
-                sbj = pk_ldg(sbar_m + (size_t)j * H + ch);
+            pk4 gs, gx, gy, gz;   // LAYER0: s_j (features);  other layers: s_bar'_j, v_bar'_j (adjoints)
+            if (LAYER0) {
+                gs = pk_ldg(s_in + (size_t)j * H + ch);
+            } else {
+                gs = pk_ldg(sbar_m + (size_t)j * H + ch);
                 const float* vbj = vbar_m + (size_t)j * 3 * H + ch;
-                vbjx = pk_ldg(vbj); vbjy = pk_ldg(vbj + H); vbjz = pk_ldg(vbj + 2 * H);
+                gx = pk_ldg(vbj); gy = pk_ldg(vbj + H); gz = pk_ldg(vbj + 2 * H);
             }
             const float4 w0 = __ldg(erec + 4 * (size_t)e + 1), w1 = __ldg(erec + 4 * (size_t)e + 2);
             const float4 d0 = __ldg(erec + 4 * (size_t)e + 3);
@@ -373,26 +390,33 @@ spline_message_backward_kernel(const float* __restrict__ table, int H,
             const float db[6] = {d0.x, d0.y, d0.z, d0.w, w1.w, -((d0.x + d0.y) + (d0.z + d0.w) + w1.w)};
             const pk4* row = tab + __float_as_int(w1.z) * kSplineRowFloat4;
             pk4 dv;   // per-channel products of gate adjoints and filter derivatives, summed at the end
+            pk4 fc, dfc;
+            float part4[4];
             if (LAYER0) {
-                dv = pk_mul(pk_mul(sj, sb), spline_deriv(row, 0, db));
+                dv = pk_mul(pk_mul(gs, sb), spline_deriv(row, 0, db));
+                spline_value_deriv(row, 2, b, db, fc, dfc);
+                const pk4 cbar = pk_fma_s(g.y, vbx, pk_fma_s(g.z, vby, pk_mul_s(g.w, vbz)));
+                dv = pk_fma(cbar, dfc, dv);
+                part4[0] = pk_hsum(pk_mul(fc, vbx)); part4[1] = pk_hsum(pk_mul(fc, vby));
+                part4[2] = pk_hsum(pk_mul(fc, vbz));
             } else {
                 pk4 fa, dfa, fb, dfb;
                 spline_value_deriv(row, 0, b, db, fa, dfa);
-                dv = pk_mul(pk_mul(sj, sb), dfa);
-                acc_s = pk_fma(fa, sbj, acc_s);
+                dv = pk_mul(pk_mul(own_s, gs), dfa);
+                acc_s = pk_fma(fa, gs, acc_s);
                 spline_value_deriv(row, 1, b, db, fb, dfb);
-                const pk4 bbar = pk_fma(vjx, vbx, pk_fma(vjy, vby, pk_mul(vjz, vbz)));
+                const pk4 bbar = pk_fma(own_x, gx, pk_fma(own_y, gy, pk_mul(own_z, gz)));
                 dv = pk_fma(bbar, dfb, dv);
-                acc_x = pk_fma(fb, vbjx, acc_x);
-                acc_y = pk_fma(fb, vbjy, acc_y);
-                acc_z = pk_fma(fb, vbjz, acc_z);
+                acc_x = pk_fma(fb, gx, acc_x);
+                acc_y = pk_fma(fb, gy, acc_y);
+                acc_z = pk_fma(fb, gz, acc_z);
+                spline_value_deriv(row, 2, b, db, fc, dfc);
+                const pk4 cbar = pk_fma_s(-g.y, gx, pk_fma_s(-g.z, gy, pk_mul_s(-g.w, gz)));   // u_r = -u_e
+                dv = pk_fma(cbar, dfc, dv);
+                part4[0] = pk_hsum(pk_mul(fc, gx)); part4[1] = pk_hsum(pk_mul(fc, gy));
+                part4[2] = pk_hsum(pk_mul(fc, gz));
             }
-            pk4 fc, dfc;
-            spline_value_deriv(row, 2, b, db, fc, dfc);
-            const pk4 cbar = pk_fma_s(g.y, vbx, pk_fma_s(g.z, vby, pk_mul_s(g.w, vbz)));
-            dv = pk_fma(cbar, dfc, dv);
-            const float part4[4] = {pk_hsum(pk_mul(fc, vbx)), pk_hsum(pk_mul(fc, vby)),
-                                    pk_hsum(pk_mul(fc, vbz)), pk_hsum(dv)};
+            part4[3] = pk_hsum(dv);
             const float total = group8_sum4(part4, l8, active_lanes);
             if ((l8 & 1) == 0) adj_out[4 * (size_t)e + held] = total;
             c.e = e + 1;
@@ -507,9 +531,17 @@ spline_message_backward_team_kernel(const float* __restrict__ table, int H,
     const int held = ((l8 & 4) ? 2 : 0) + ((l8 & 2) ? 1 : 0);
     for (int i = part * kWarps + warp; i < num_atoms; i += parts * kWarps) {
         const int e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
-        const pk4 sb = pk_ldg(sbar_m + (size_t)i * H + ch);
         const float* vb = vbar_m + (size_t)i * 3 * H + ch;
-        const pk4 vbx = pk_ldg(vb), vby = pk_ldg(vb + H), vbz = pk_ldg(vb + 2 * H);
+        pk4 sb = pk_zero(), vbx = pk_zero(), vby = pk_zero(), vbz = pk_zero();             // LAYER0: the row's adjoints
+        pk4 own_s = pk_zero(), own_x = pk_zero(), own_y = pk_zero(), own_z = pk_zero();   // other layers: its features
+        if (LAYER0) {
+            sb = pk_ldg(sbar_m + (size_t)i * H + ch);
+            vbx = pk_ldg(vb); vby = pk_ldg(vb + H); vbz = pk_ldg(vb + 2 * H);
+        } else {
+            own_s = pk_ldg(s_in + (size_t)i * H + ch);
+            const float* vi = v_in + (size_t)i * 3 * H + ch;
+            own_x = pk_ldg(vi); own_y = pk_ldg(vi + H); own_z = pk_ldg(vi + 2 * H);
+        }
         pk4 acc_s = pk_zero(), acc_x = pk_zero(), acc_y = pk_zero(), acc_z = pk_zero();
         float4 head = make4(0.f);
         if (e0 + t < e1) head = __ldg(erec + 4 * (size_t)(e0 + t));
@@ -522,51 +554,57 @@ spline_message_backward_team_kernel(const float* __restrict__ table, int H,
                 const float4 g = head;
                 if (e + 4 < e1) head = __ldg(erec + 4 * (size_t)(e + 4));
                 const int j = __float_as_int(g.x);
-                const pk4 sj = pk_ldg(s_in + (size_t)j * H + ch);
-                pk4 vjx, vjy, vjz, sbj, vbjx, vbjy, vbjz;
-                if (!LAYER0) {
-                    const float* vj = v_in + (size_t)j * 3 * H + ch;
-                    vjx = pk_ldg(vj); vjy = pk_ldg(vj + H); vjz = pk_ldg(vj + 2 * H);
-                    sbj = pk_ldg(sbar_m + (size_t)j * H + ch);
+                pk4 gs, gx, gy, gz;   // LAYER0: s_j;  other layers: s_bar'_j, v_bar'_j (see the row kernel)
+                if (LAYER0) {
+                    gs = pk_ldg(s_in + (size_t)j * H + ch);
+                } else {
+                    gs = pk_ldg(sbar_m + (size_t)j * H + ch);
                     const float* vbj = vbar_m + (size_t)j * 3 * H + ch;
-                    vbjx = pk_ldg(vbj); vbjy = pk_ldg(vbj + H); vbjz = pk_ldg(vbj + 2 * H);
+                    gx = pk_ldg(vbj); gy = pk_ldg(vbj + H); gz = pk_ldg(vbj + 2 * H);
                 }
                 const float4 w0 = __ldg(erec + 4 * (size_t)e + 1), w1 = __ldg(erec + 4 * (size_t)e + 2);
                 const float4 d0 = __ldg(erec + 4 * (size_t)e + 3);
                 const float b[6] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y};
                 const float db[6] = {d0.x, d0.y, d0.z, d0.w, w1.w, -((d0.x + d0.y) + (d0.z + d0.w) + w1.w)};
                 const pk4* row = tab + __float_as_int(w1.z) * kSplineRowFloat4;
-                pk4 dv;
+                pk4 dv, fc, dfc;
+                float part4[4];
                 if (LAYER0) {
-                    dv = pk_mul(pk_mul(sj, sb), spline_deriv(row, 0, db));
+                    dv = pk_mul(pk_mul(gs, sb), spline_deriv(row, 0, db));
+                    spline_value_deriv(row, 2, b, db, fc, dfc);
+                    const pk4 cbar = pk_fma_s(g.y, vbx, pk_fma_s(g.z, vby, pk_mul_s(g.w, vbz)));
+                    dv = pk_fma(cbar, dfc, dv);
+                    part4[0] = pk_hsum(pk_mul(fc, vbx)); part4[1] = pk_hsum(pk_mul(fc, vby));
+                    part4[2] = pk_hsum(pk_mul(fc, vbz));
                 } else {
                     pk4 fa, dfa, fb, dfb;
                     spline_value_deriv(row, 0, b, db, fa, dfa);
-                    dv = pk_mul(pk_mul(sj, sb), dfa);
-                    acc_s = pk_fma(fa, sbj, acc_s);
+                    dv = pk_mul(pk_mul(own_s, gs), dfa);
+                    acc_s = pk_fma(fa, gs, acc_s);
                     spline_value_deriv(row, 1, b, db, fb, dfb);
-                    const pk4 bbar = pk_fma(vjx, vbx, pk_fma(vjy, vby, pk_mul(vjz, vbz)));
+                    const pk4 bbar = pk_fma(own_x, gx, pk_fma(own_y, gy, pk_mul(own_z, gz)));
                     dv = pk_fma(bbar, dfb, dv);
-                    acc_x = pk_fma(fb, vbjx, acc_x);
-                    acc_y = pk_fma(fb, vbjy, acc_y);
-                    acc_z = pk_fma(fb, vbjz, acc_z);
+                    acc_x = pk_fma(fb, gx, acc_x);
+                    acc_y = pk_fma(fb, gy, acc_y);
+                    acc_z = pk_fma(fb, gz, acc_z);
+                    spline_value_deriv(row, 2, b, db, fc, dfc);
+                    const pk4 cbar = pk_fma_s(-g.y, gx, pk_fma_s(-g.z, gy, pk_mul_s(-g.w, gz)));   // u_r = -u_e
+                    dv = pk_fma(cbar, dfc, dv);
+                    part4[0] = pk_hsum(pk_mul(fc, gx)); part4[1] = pk_hsum(pk_mul(fc, gy));
+                    part4[2] = pk_hsum(pk_mul(fc, gz));
                 }
-                pk4 fc, dfc;
-                spline_value_deriv(row, 2, b, db, fc, dfc);
-                const pk4 cbar = pk_fma_s(g.y, vbx, pk_fma_s(g.z, vby, pk_mul_s(g.w, vbz)));
-                dv = pk_fma(cbar, dfc, dv);
-                const float part4[4] = {pk_hsum(pk_mul(fc, vbx)), pk_hsum(pk_mul(fc, vby)),
-                                        pk_hsum(pk_mul(fc, vbz)), pk_hsum(dv)};
+                part4[3] = pk_hsum(dv);
                 const float total = group8_sum4(part4, l8, active_lanes);
                 if ((l8 & 1) == 0) adj_out[4 * (size_t)e + held] = total;
             }
         }
         if (!LAYER0) {
             acc_s = pk_team_sum(acc_s); acc_x = pk_team_sum(acc_x); acc_y = pk_team_sum(acc_y); acc_z = pk_team_sum(acc_z);
-            if (t == 0) {   // residual path + the gathered sums
-                pk_st(sbar_in + (size_t)i * H + ch, pk_add(sb, acc_s));
+            if (t == 0) {   // residual path (the row's own adjoints) + the gathered sums
+                pk_st(sbar_in + (size_t)i * H + ch, pk_add(pk_ldg(sbar_m + (size_t)i * H + ch), acc_s));
                 float* vo = vbar_in + (size_t)i * 3 * H + ch;
-                pk_st(vo, pk_add(vbx, acc_x)); pk_st(vo + H, pk_add(vby, acc_y)); pk_st(vo + 2 * H, pk_add(vbz, acc_z));
+                pk_st(vo, pk_add(pk_ldg(vb), acc_x)); pk_st(vo + H, pk_add(pk_ldg(vb + H), acc_y));
+                pk_st(vo + 2 * H, pk_add(pk_ldg(vb + 2 * H), acc_z));
             }
         }
     }

@@ -97,6 +97,7 @@ struct mlffd_ctx {
     bool readout_configured = false; // smem attribute of readout_tile_kernel set on this device
     uint32_t pipe_configured = 0;    // bit per pipelined-kernel instantiation whose smem attribute is set on this device
     int last_adj_slabs = 0;          // edge-adjoint slabs written by the last force evaluation (0 = none)
+    int last_adj_direct = 0;         // the first `last_adj_direct` of them hold the adjoint of edge e at index e, the rest that of rev(e)
     int msg_bwd_mode = 2;            // env MLFFD_MSG_BWD = edges (0) | pairs (1) | pipe (2)
     int msg_fwd_mode = 1;            // env MLFFD_MSG_FWD = rows (0) | pipe (1)
     int pipe_depth_fwd = 2;          // env MLFFD_PIPE_DEPTH_FWD: ring slots per warp
@@ -709,8 +710,10 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
         LAUNCHED(ctx, "message_backward_kernel", MLFFD_STAGE_MESSAGE_BWD, st);
     }
     ctx->last_adj_slabs = spline ? L * ctx->adj_slabs_per_layer : (adj_slabs ? L : 1);
+    // spline reverse kernels: layer 0 writes the adjoint of e, the other layers that of rev(e) (message_spline.cuh)
+    ctx->last_adj_direct = spline ? ctx->adj_slabs_per_layer : ctx->last_adj_slabs;
     force_kernel<<<warp_grid, 256, 0, st>>>(ws.rowptr, ws.rev, ws.geo, ws.edge_adj, ctx->last_adj_slabs,
-                                            (size_t)ws.cap_edges,
+                                            ctx->last_adj_direct, (size_t)ws.cap_edges,
                                             ctx->debug_keep ? ws.edge_adj + (size_t)L * ctx->adj_slabs_per_layer * ws.cap_edges : nullptr,
                                             forces, N, status);
     LAUNCHED(ctx, "force_kernel", MLFFD_STAGE_FORCE, st);
@@ -1415,7 +1418,7 @@ extern "C" int mlffd_virial(mlffd_ctx* ctx, const int32_t* offsets_d, int32_t nu
     const int chunks = (int)std::min<int64_t>(64, std::max<int64_t>(1, per_struct / kVirialChunk));
     if (chunks > 1) CUDA_TRY(ctx, cudaMemsetAsync(ws.virial64, 0, sizeof(double) * 9 * num_structures, st));
     virial_kernel<<<dim3(num_structures, chunks), 256, 0, st>>>(offsets_d, num_structures, ws.rowptr, ws.geo, ws.edge_adj,
-                                                                ctx->last_adj_slabs, (size_t)ws.cap_edges,
+                                                                ctx->last_adj_slabs, ctx->last_adj_direct, (size_t)ws.cap_edges,
                                                                 ws.virial64, ctx->status_d);
     virial_finalize_kernel<<<ceil_div(9 * num_structures, 256), 256, 0, st>>>(ws.virial64, 9 * num_structures,
                                                                                virial_d, ctx->status_d);

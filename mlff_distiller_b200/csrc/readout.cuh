@@ -406,12 +406,15 @@ __device__ __forceinline__ float3 edge_position_adjoint(const float4 g, const fl
                        fmaf(scale, g.z, adj.z * inv_q));
 }
 
-// Edge adjoint summed over the per-layer slabs, last layer first (the order the single-buffer
-// accumulation of the reverse pass uses).
-__device__ __forceinline__ float4 edge_adjoint_sum(const float4* __restrict__ edge_adj, int e, int slabs,
+// Edge adjoint summed over the slabs [lo, hi), last first (the order the single-buffer accumulation of the
+// reverse pass uses); zero for an empty range.
+// Slabs [0, direct) hold at index e the adjoint (u_bar, d_bar) of edge e; slabs [direct, slabs) -- written by
+// the spline reverse kernels of the layers > 0, message_spline.cuh -- hold at index e the adjoint of rev(e).
+__device__ __forceinline__ float4 edge_adjoint_sum(const float4* __restrict__ edge_adj, int e, int lo, int hi,
                                                    size_t slab_stride) {
-    float4 t = __ldg(edge_adj + (size_t)(slabs - 1) * slab_stride + e);
-    for (int l = slabs - 2; l >= 0; --l) t = add4(__ldg(edge_adj + (size_t)l * slab_stride + e), t);
+    if (hi <= lo) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 t = __ldg(edge_adj + (size_t)(hi - 1) * slab_stride + e);
+    for (int l = hi - 2; l >= lo; --l) t = add4(__ldg(edge_adj + (size_t)l * slab_stride + e), t);
     return t;
 }
 
@@ -420,7 +423,7 @@ __device__ __forceinline__ float4 edge_adjoint_sum(const float4* __restrict__ ed
 // adj_sum_out (debug only) receives the summed adjoint of every edge.
 __global__ void __launch_bounds__(256)
 force_kernel(const int* __restrict__ rowptr, const int* __restrict__ rev,
-             const float4* __restrict__ geo, const float4* __restrict__ edge_adj, int slabs,
+             const float4* __restrict__ geo, const float4* __restrict__ edge_adj, int slabs, int direct,
              size_t slab_stride, float4* __restrict__ adj_sum_out, float* __restrict__ forces,
              int num_atoms, const DeviceStatus* __restrict__ status) {
     if (status->overflow) return;
@@ -432,8 +435,14 @@ force_kernel(const int* __restrict__ rowptr, const int* __restrict__ rev,
         float fx = 0.f, fy = 0.f, fz = 0.f;
         for (int e = e0 + lane; e < e1; e += 32) {
             const int r = __ldg(rev + e);
-            const float4 adj_e = edge_adjoint_sum(edge_adj, e, slabs, slab_stride);
-            const float4 adj_r = edge_adjoint_sum(edge_adj, r, slabs, slab_stride);
+            float4 adj_e = edge_adjoint_sum(edge_adj, e, 0, direct, slab_stride);
+            float4 adj_r = edge_adjoint_sum(edge_adj, r, 0, direct, slab_stride);
+            if (direct < slabs) {   // swapped slabs: what is stored at e belongs to r and vice versa
+                const float4 at_e = edge_adjoint_sum(edge_adj, e, direct, slabs, slab_stride);
+                const float4 at_r = edge_adjoint_sum(edge_adj, r, direct, slabs, slab_stride);
+                adj_e = add4(adj_e, at_r);
+                adj_r = add4(adj_r, at_e);
+            }
             if (adj_sum_out != nullptr) adj_sum_out[e] = adj_e;
             const float3 a = edge_position_adjoint(__ldg(geo + e), adj_e);
             const float3 b = edge_position_adjoint(__ldg(geo + r), adj_r);
@@ -459,7 +468,7 @@ constexpr int kVirialChunk = 8192;
 
 __global__ void __launch_bounds__(256)
 virial_kernel(const int* __restrict__ offsets, int num_structures, const int* __restrict__ rowptr,
-              const float4* __restrict__ geo, const float4* __restrict__ edge_adj, int slabs,
+              const float4* __restrict__ geo, const float4* __restrict__ edge_adj, int slabs, int direct,
               size_t slab_stride, double* __restrict__ virial, const DeviceStatus* __restrict__ status) {
     if (status->overflow) return;
     __shared__ double part[8][9];
@@ -474,7 +483,14 @@ virial_kernel(const int* __restrict__ offsets, int num_structures, const int* __
         const int c1 = min(c0 + kVirialChunk, e_hi);
         for (int e = c0 + (int)threadIdx.x; e < c1; e += (int)blockDim.x) {
             const float4 g = __ldg(geo + e);
-            const float3 rb = edge_position_adjoint(g, edge_adjoint_sum(edge_adj, e, slabs, slab_stride));
+            float3 rb = edge_position_adjoint(g, edge_adjoint_sum(edge_adj, e, 0, direct, slab_stride));
+            if (direct < slabs) {
+                // a swapped slab entry is the adjoint of rev(e): unit vector -u, edge vector -r.  The sum over all
+                // e of r_bar_rev(e) (x) r_rev(e) is the same total, so it is folded in here with both signs flipped.
+                const float3 rs = edge_position_adjoint(make_float4(-g.x, -g.y, -g.z, g.w),
+                                                        edge_adjoint_sum(edge_adj, e, direct, slabs, slab_stride));
+                rb.x -= rs.x; rb.y -= rs.y; rb.z -= rs.z;
+            }
             const float q = g.w + kUnitEps;
             const float r[3] = {g.x * q, g.y * q, g.z * q};
             const float a[3] = {rb.x, rb.y, rb.z};
