@@ -172,25 +172,35 @@ __device__ __forceinline__ pk4 spline_deriv(const pk4* row, int comp, const floa
 // Group g of CTA partition p owns rows p * R + g, (p + parts) * R + g, ... (R = row groups per CTA).
 // The next row's edge range is fetched one row ahead, and the source index of the next edge one edge
 // ahead (across row boundaries), so the only exposed global-memory latency per edge is the gather.
+// With `lowptr` (prefix sums of the number of entries with source < row) a row's walk starts at its first
+// entry with source > row: the upper half of every undirected pair (pair-once kernels).
 struct RowCursor {
     int row, e, e_end, nrow, ne0, ne1, step;
     float4 head;   // first record entry (source, unit vector) of the edge to process next
-    __device__ __forceinline__ void fetch_next_range(const int* __restrict__ rowptr, int num_atoms) {
+    __device__ __forceinline__ static void row_range(const int* __restrict__ rowptr, const int* __restrict__ lowptr,
+                                                     int r, int& first, int& last) {
+        first = __ldg(rowptr + r); last = __ldg(rowptr + r + 1);
+        if (lowptr != nullptr) first += __ldg(lowptr + r + 1) - __ldg(lowptr + r);
+    }
+    __device__ __forceinline__ void fetch_next_range(const int* __restrict__ rowptr, int num_atoms,
+                                                     const int* __restrict__ lowptr) {
         ne0 = ne1 = 0;
-        if (nrow < num_atoms) { ne0 = __ldg(rowptr + nrow); ne1 = __ldg(rowptr + nrow + 1); }
+        if (nrow < num_atoms) row_range(rowptr, lowptr, nrow, ne0, ne1);
     }
     __device__ __forceinline__ void init(int first_row, int row_step, const int* __restrict__ rowptr,
-                                         const float4* __restrict__ erec, int num_atoms) {
+                                         const float4* __restrict__ erec, int num_atoms,
+                                         const int* __restrict__ lowptr = nullptr) {
         row = first_row; step = row_step; e = e_end = 0; head = make4(0.f);
-        if (row < num_atoms) { e = __ldg(rowptr + row); e_end = __ldg(rowptr + row + 1); }
+        if (row < num_atoms) row_range(rowptr, lowptr, row, e, e_end);
         nrow = row + step;
-        fetch_next_range(rowptr, num_atoms);
+        fetch_next_range(rowptr, num_atoms, lowptr);
         if (e < e_end) head = __ldg(erec + 4 * (size_t)e);
     }
     __device__ __forceinline__ void advance_row(const int* __restrict__ rowptr, const float4* __restrict__ erec,
-                                                int num_atoms, bool had_edges) {
+                                                int num_atoms, bool had_edges,
+                                                const int* __restrict__ lowptr = nullptr) {
         row = nrow; e = ne0; e_end = ne1; nrow += step;
-        fetch_next_range(rowptr, num_atoms);
+        fetch_next_range(rowptr, num_atoms, lowptr);
         // the head of the new row's first edge was prefetched by the last edge of the previous row
         if (!had_edges && e < e_end) head = __ldg(erec + 4 * (size_t)e);
     }
@@ -302,9 +312,12 @@ __device__ __forceinline__ float group8_sum4(const float (&v)[4], int l8, unsign
 //        L x slices slabs.
 // Row i walks its CSR entries e = (j -> i) one by one (uniform work, no pairing).  Edge e and its reverse
 // r = (i -> j) have the same distance, hence the same filter, and u_r = -u_e.
-// LAYER0 (v_in == 0, no input adjoints): the entry's own adjoint, from the gathered s_j and the row's adjoints:
-//   a_bar = s_j * s_bar'_i,  c_bar = sum_x u_e[x] v_bar'_i[x],  d_bar_e = a_bar . a'(d) + c_bar . c'(d),
-//   u_bar_e[x] = c(d) . v_bar'_i[x]                                   -> slab[e] = adjoint of e   ("direct" slab)
+// LAYER0 (v_in == 0, no input adjoints, nothing to accumulate per row): every undirected PAIR once.  Row i
+// walks only its entries with j > i (RowCursor with lowptr) and forms the sum over both directions -- only
+// u_bar_e - u_bar_r and d_bar_e + d_bar_r enter the forces (r_bar_e - r_bar_r, readout.cuh):
+//   d_bar = (s_j s_bar'_i + s_i s_bar'_j) . a'(d) + (sum_x u_e[x] (v_bar'_i - v_bar'_j)[x]) . c'(d)
+//   u_bar[x] = c(d) . (v_bar'_i - v_bar'_j)[x]                         -> slab[e], e upper   ("pair" slab)
+// 12 coefficient reads per pair instead of 24.
 // other layers: everything row i computes comes from the REVERSE edge r, whose source is i itself, so one
 // gather of the neighbour's adjoints (s_bar'_j, v_bar'_j: 4 x 128 B) serves both the scatter-turned-gather
 //   s_bar_i += a(d) * s_bar'_j,  v_bar_i[x] += b(d) * v_bar'_j[x]
@@ -324,7 +337,7 @@ spline_message_backward_kernel(const float* __restrict__ table, int H,
                                const float* __restrict__ sbar_m, const float* __restrict__ vbar_m,
                                float* __restrict__ sbar_in, float* __restrict__ vbar_in,
                                float4* __restrict__ edge_adj, size_t slab_stride, int num_atoms,
-                               const DeviceStatus* __restrict__ status) {
+                               const int* __restrict__ lowptr, const DeviceStatus* __restrict__ status) {
     extern __shared__ float4 spline_tab[];
     if (status->overflow) return;
     constexpr int kGroups = THREADS / 8;
@@ -336,9 +349,10 @@ spline_message_backward_kernel(const float* __restrict__ table, int H,
     const int ch = slice * kSliceChannels + l8 * 4;
     const pk4* tab = reinterpret_cast<const pk4*>(spline_tab) + l8;
     const int held = ((l8 & 4) ? 2 : 0) + ((l8 & 2) ? 1 : 0);   // which reduced value this lane ends up with
+    const int* upper = LAYER0 ? lowptr : nullptr;   // LAYER0: pairs once, rows start at their first j > i
     RowCursor c;
-    c.init(part * kGroups + sub, parts * kGroups, rowptr, erec, num_atoms);
-    // LAYER0: the row's adjoints (sb, vb*);  other layers: the row's features (own_s, own_*)
+    c.init(part * kGroups + sub, parts * kGroups, rowptr, erec, num_atoms, upper);
+    // LAYER0: the row's adjoints (sb, vb*) and own_s;  other layers: the row's features (own_s, own_*)
     pk4 sb = pk_zero(), vbx = pk_zero(), vby = pk_zero(), vbz = pk_zero();
     pk4 own_s = pk_zero(), own_x = pk_zero(), own_y = pk_zero(), own_z = pk_zero();
     pk4 acc_s = pk_zero(), acc_x = pk_zero(), acc_y = pk_zero(), acc_z = pk_zero();
@@ -351,7 +365,7 @@ spline_message_backward_kernel(const float* __restrict__ table, int H,
                 float* vo = vbar_in + (size_t)i * 3 * H + ch;
                 pk_st(vo, acc_x); pk_st(vo + H, acc_y); pk_st(vo + 2 * H, acc_z);
             }
-            c.advance_row(rowptr, erec, num_atoms, had_edges);
+            c.advance_row(rowptr, erec, num_atoms, had_edges, upper);
             had_edges = false;
             loaded = false;
         }
@@ -359,8 +373,11 @@ spline_message_backward_kernel(const float* __restrict__ table, int H,
             const int i = c.row;
             const float* vb = vbar_m + (size_t)i * 3 * H + ch;
             if (LAYER0) {
-                sb = pk_ldg(sbar_m + (size_t)i * H + ch);
-                vbx = pk_ldg(vb); vby = pk_ldg(vb + H); vbz = pk_ldg(vb + 2 * H);
+                if (c.e < c.e_end) {   // a row without upper entries has nothing to do
+                    sb = pk_ldg(sbar_m + (size_t)i * H + ch);
+                    vbx = pk_ldg(vb); vby = pk_ldg(vb + H); vbz = pk_ldg(vb + 2 * H);
+                    own_s = pk_ldg(s_in + (size_t)i * H + ch);
+                }
             } else {   // the row's adjoints start the residual path; its features stay for the edge adjoints
                 acc_s = pk_ldg(sbar_m + (size_t)i * H + ch);
                 acc_x = pk_ldg(vb); acc_y = pk_ldg(vb + H); acc_z = pk_ldg(vb + 2 * H);
@@ -376,14 +393,12 @@ spline_message_backward_kernel(const float* __restrict__ table, int H,
             const int e = c.e;
             const float4 g = c.take_head(erec);   // (source, unit vector)
             const int j = __float_as_int(g.x);
-            pk4 gs, gx, gy, gz;   // LAYER0: s_j (features);  other layers: s_bar'_j, v_bar'_j (adjoints)
-            if (LAYER0) {
-                gs = pk_ldg(s_in + (size_t)j * H + ch);
-            } else {
-                gs = pk_ldg(sbar_m + (size_t)j * H + ch);
-                const float* vbj = vbar_m + (size_t)j * 3 * H + ch;
-                gx = pk_ldg(vbj); gy = pk_ldg(vbj + H); gz = pk_ldg(vbj + 2 * H);
-            }
+            // the neighbour's adjoints s_bar'_j, v_bar'_j; LAYER0 also its features s_j
+            const pk4 gs = pk_ldg(sbar_m + (size_t)j * H + ch);
+            const float* vbj = vbar_m + (size_t)j * 3 * H + ch;
+            const pk4 gx = pk_ldg(vbj), gy = pk_ldg(vbj + H), gz = pk_ldg(vbj + 2 * H);
+            pk4 gf = pk_zero();
+            if (LAYER0) gf = pk_ldg(s_in + (size_t)j * H + ch);
             const float4 w0 = __ldg(erec + 4 * (size_t)e + 1), w1 = __ldg(erec + 4 * (size_t)e + 2);
             const float4 d0 = __ldg(erec + 4 * (size_t)e + 3);
             const float b[6] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y};
@@ -393,12 +408,13 @@ spline_message_backward_kernel(const float* __restrict__ table, int H,
             pk4 fc, dfc;
             float part4[4];
             if (LAYER0) {
-                dv = pk_mul(pk_mul(gs, sb), spline_deriv(row, 0, db));
+                dv = pk_mul(pk_fma(gf, sb, pk_mul(own_s, gs)), spline_deriv(row, 0, db));
                 spline_value_deriv(row, 2, b, db, fc, dfc);
-                const pk4 cbar = pk_fma_s(g.y, vbx, pk_fma_s(g.z, vby, pk_mul_s(g.w, vbz)));
+                const pk4 dx = pk_fma_s(-1.0f, gx, vbx), dy = pk_fma_s(-1.0f, gy, vby), dz = pk_fma_s(-1.0f, gz, vbz);
+                const pk4 cbar = pk_fma_s(g.y, dx, pk_fma_s(g.z, dy, pk_mul_s(g.w, dz)));
                 dv = pk_fma(cbar, dfc, dv);
-                part4[0] = pk_hsum(pk_mul(fc, vbx)); part4[1] = pk_hsum(pk_mul(fc, vby));
-                part4[2] = pk_hsum(pk_mul(fc, vbz));
+                part4[0] = pk_hsum(pk_mul(fc, dx)); part4[1] = pk_hsum(pk_mul(fc, dy));
+                part4[2] = pk_hsum(pk_mul(fc, dz));
             } else {
                 pk4 fa, dfa, fb, dfb;
                 spline_value_deriv(row, 0, b, db, fa, dfa);

@@ -97,7 +97,7 @@ struct mlffd_ctx {
     bool readout_configured = false; // smem attribute of readout_tile_kernel set on this device
     uint32_t pipe_configured = 0;    // bit per pipelined-kernel instantiation whose smem attribute is set on this device
     int last_adj_slabs = 0;          // edge-adjoint slabs written by the last force evaluation (0 = none)
-    int last_adj_direct = 0;         // the first `last_adj_direct` of them hold the adjoint of edge e at index e, the rest that of rev(e)
+    int last_adj_pairs = 0, last_adj_direct = 0;   // slab kinds (readout.cuh): [0, pairs) pair sums, [pairs, direct) adjoint of e, the rest that of rev(e)
     int msg_bwd_mode = 2;            // env MLFFD_MSG_BWD = edges (0) | pairs (1) | pipe (2)
     int msg_fwd_mode = 1;            // env MLFFD_MSG_FWD = rows (0) | pipe (1)
     int pipe_depth_fwd = 2;          // env MLFFD_PIPE_DEPTH_FWD: ring slots per warp
@@ -436,11 +436,11 @@ cudaError_t launch_spline_backward_t(mlffd_ctx* ctx, int l, const float* sb, con
     if (l == 0)
         spline_message_backward_kernel<true, THREADS, CTAS><<<grid, THREADS, kSplineSmemBytes, st>>>(
             spline_layer_table(ctx, l), ctx->H, ws.rowptr, ws.erec, ws.s_in[l], nullptr,
-            sb, vb, sb_in, vb_in, slab, (size_t)ws.cap_edges, N, ctx->status_d);
+            sb, vb, sb_in, vb_in, slab, (size_t)ws.cap_edges, N, ws.lowptr, ctx->status_d);
     else
         spline_message_backward_kernel<false, THREADS, CTAS><<<grid, THREADS, kSplineSmemBytes, st>>>(
             spline_layer_table(ctx, l), ctx->H, ws.rowptr, ws.erec, ws.s_in[l], ws.v_in[l],
-            sb, vb, sb_in, vb_in, slab, (size_t)ws.cap_edges, N, ctx->status_d);
+            sb, vb, sb_in, vb_in, slab, (size_t)ws.cap_edges, N, ws.lowptr, ctx->status_d);
     return cudaSuccess;
 }
 // small systems: a warp (four row groups) per CSR row, 8 rows per CTA
@@ -479,8 +479,9 @@ cudaError_t launch_spline_team(mlffd_ctx* ctx, int l, bool backward, const float
 }
 
 // launch shapes: (threads per CTA, resident CTAs per SM); env MLFFD_SPLINE_FWD / MLFFD_SPLINE_BWD pick one
+bool spline_team_path(const mlffd_ctx* ctx, int N) { return N <= ctx->small_rows && ctx->msg_team > 1; }
 cudaError_t launch_spline_forward(mlffd_ctx* ctx, int l, int N, cudaStream_t st) {
-    if (N <= ctx->small_rows && ctx->msg_team > 1) return launch_spline_team(ctx, l, false, nullptr, nullptr, nullptr, nullptr, N, st);
+    if (spline_team_path(ctx, N)) return launch_spline_team(ctx, l, false, nullptr, nullptr, nullptr, nullptr, N, st);
     switch (ctx->spline_fwd_shape) {
         case 1: return launch_spline_forward_t<768, 1>(ctx, l, N, st);
         case 2: return launch_spline_forward_t<384, 2>(ctx, l, N, st);
@@ -490,7 +491,7 @@ cudaError_t launch_spline_forward(mlffd_ctx* ctx, int l, int N, cudaStream_t st)
 }
 cudaError_t launch_spline_backward(mlffd_ctx* ctx, int l, const float* sb, const float* vb, float* sb_in, float* vb_in,
                                    int N, cudaStream_t st) {
-    if (N <= ctx->small_rows && ctx->msg_team > 1) return launch_spline_team(ctx, l, true, sb, vb, sb_in, vb_in, N, st);
+    if (spline_team_path(ctx, N)) return launch_spline_team(ctx, l, true, sb, vb, sb_in, vb_in, N, st);
     switch (ctx->spline_bwd_shape) {
         case 1: return launch_spline_backward_t<768, 1>(ctx, l, sb, vb, sb_in, vb_in, N, st);
         case 2: return launch_spline_backward_t<384, 2>(ctx, l, sb, vb, sb_in, vb_in, N, st);
@@ -712,8 +713,10 @@ int run_model(mlffd_ctx* ctx, const int* z, int64_t n_atoms, const int* offsets,
     ctx->last_adj_slabs = spline ? L * ctx->adj_slabs_per_layer : (adj_slabs ? L : 1);
     // spline reverse kernels: layer 0 writes the adjoint of e, the other layers that of rev(e) (message_spline.cuh)
     ctx->last_adj_direct = spline ? ctx->adj_slabs_per_layer : ctx->last_adj_slabs;
+    // ... and layer 0 of the row kernels (not of the small-system team kernels) writes pair sums
+    ctx->last_adj_pairs = (spline && !spline_team_path(ctx, N)) ? ctx->adj_slabs_per_layer : 0;
     force_kernel<<<warp_grid, 256, 0, st>>>(ws.rowptr, ws.rev, ws.geo, ws.edge_adj, ctx->last_adj_slabs,
-                                            ctx->last_adj_direct, (size_t)ws.cap_edges,
+                                            ctx->last_adj_pairs, ctx->last_adj_direct, (size_t)ws.cap_edges,
                                             ctx->debug_keep ? ws.edge_adj + (size_t)L * ctx->adj_slabs_per_layer * ws.cap_edges : nullptr,
                                             forces, N, status);
     LAUNCHED(ctx, "force_kernel", MLFFD_STAGE_FORCE, st);
@@ -1417,8 +1420,8 @@ extern "C" int mlffd_virial(mlffd_ctx* ctx, const int32_t* offsets_d, int32_t nu
     const int64_t per_struct = std::max<int64_t>(1, ws.cap_edges / std::max<int64_t>(1, ctx->last_structs));
     const int chunks = (int)std::min<int64_t>(64, std::max<int64_t>(1, per_struct / kVirialChunk));
     if (chunks > 1) CUDA_TRY(ctx, cudaMemsetAsync(ws.virial64, 0, sizeof(double) * 9 * num_structures, st));
-    virial_kernel<<<dim3(num_structures, chunks), 256, 0, st>>>(offsets_d, num_structures, ws.rowptr, ws.geo, ws.edge_adj,
-                                                                ctx->last_adj_slabs, ctx->last_adj_direct, (size_t)ws.cap_edges,
+    virial_kernel<<<dim3(num_structures, chunks), 256, 0, st>>>(offsets_d, num_structures, ws.rowptr, ws.rev, ws.geo, ws.edge_adj,
+                                                                ctx->last_adj_slabs, ctx->last_adj_pairs, ctx->last_adj_direct, (size_t)ws.cap_edges,
                                                                 ws.virial64, ctx->status_d);
     virial_finalize_kernel<<<ceil_div(9 * num_structures, 256), 256, 0, st>>>(ws.virial64, 9 * num_structures,
                                                                                virial_d, ctx->status_d);

@@ -408,8 +408,12 @@ __device__ __forceinline__ float3 edge_position_adjoint(const float4 g, const fl
 
 // Edge adjoint summed over the slabs [lo, hi), last first (the order the single-buffer accumulation of the
 // reverse pass uses); zero for an empty range.
-// Slabs [0, direct) hold at index e the adjoint (u_bar, d_bar) of edge e; slabs [direct, slabs) -- written by
-// the spline reverse kernels of the layers > 0, message_spline.cuh -- hold at index e the adjoint of rev(e).
+// Three kinds of slab, in this order (message_spline.cuh says who writes which):
+//   [0, pairs)       at the UPPER entry e of a pair (rev(e) > e) the sum over both directions, (u_bar_e - u_bar_r,
+//                    d_bar_e + d_bar_r); the lower entry is not written.  r_bar_e - r_bar_r is the position
+//                    adjoint of that sum taken with e's geometry.
+//   [pairs, direct)  at index e the adjoint (u_bar, d_bar) of edge e
+//   [direct, slabs)  at index e the adjoint of rev(e)
 __device__ __forceinline__ float4 edge_adjoint_sum(const float4* __restrict__ edge_adj, int e, int lo, int hi,
                                                    size_t slab_stride) {
     if (hi <= lo) return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -423,7 +427,7 @@ __device__ __forceinline__ float4 edge_adjoint_sum(const float4* __restrict__ ed
 // adj_sum_out (debug only) receives the summed adjoint of every edge.
 __global__ void __launch_bounds__(256)
 force_kernel(const int* __restrict__ rowptr, const int* __restrict__ rev,
-             const float4* __restrict__ geo, const float4* __restrict__ edge_adj, int slabs, int direct,
+             const float4* __restrict__ geo, const float4* __restrict__ edge_adj, int slabs, int pairs, int direct,
              size_t slab_stride, float4* __restrict__ adj_sum_out, float* __restrict__ forces,
              int num_atoms, const DeviceStatus* __restrict__ status) {
     if (status->overflow) return;
@@ -435,8 +439,12 @@ force_kernel(const int* __restrict__ rowptr, const int* __restrict__ rev,
         float fx = 0.f, fy = 0.f, fz = 0.f;
         for (int e = e0 + lane; e < e1; e += 32) {
             const int r = __ldg(rev + e);
-            float4 adj_e = edge_adjoint_sum(edge_adj, e, 0, direct, slab_stride);
-            float4 adj_r = edge_adjoint_sum(edge_adj, r, 0, direct, slab_stride);
+            float4 adj_e = edge_adjoint_sum(edge_adj, e, pairs, direct, slab_stride);
+            float4 adj_r = edge_adjoint_sum(edge_adj, r, pairs, direct, slab_stride);
+            if (pairs > 0) {   // the pair's sum lives at its upper entry: r_bar_e - r_bar_r = +- its position adjoint
+                if (r > e) adj_e = add4(adj_e, edge_adjoint_sum(edge_adj, e, 0, pairs, slab_stride));
+                else adj_r = add4(adj_r, edge_adjoint_sum(edge_adj, r, 0, pairs, slab_stride));
+            }
             if (direct < slabs) {   // swapped slabs: what is stored at e belongs to r and vice versa
                 const float4 at_e = edge_adjoint_sum(edge_adj, e, direct, slabs, slab_stride);
                 const float4 at_r = edge_adjoint_sum(edge_adj, r, direct, slabs, slab_stride);
@@ -468,8 +476,8 @@ constexpr int kVirialChunk = 8192;
 
 __global__ void __launch_bounds__(256)
 virial_kernel(const int* __restrict__ offsets, int num_structures, const int* __restrict__ rowptr,
-              const float4* __restrict__ geo, const float4* __restrict__ edge_adj, int slabs, int direct,
-              size_t slab_stride, double* __restrict__ virial, const DeviceStatus* __restrict__ status) {
+              const int* __restrict__ rev, const float4* __restrict__ geo, const float4* __restrict__ edge_adj,
+              int slabs, int pairs, int direct, size_t slab_stride, double* __restrict__ virial, const DeviceStatus* __restrict__ status) {
     if (status->overflow) return;
     __shared__ double part[8][9];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -483,7 +491,10 @@ virial_kernel(const int* __restrict__ offsets, int num_structures, const int* __
         const int c1 = min(c0 + kVirialChunk, e_hi);
         for (int e = c0 + (int)threadIdx.x; e < c1; e += (int)blockDim.x) {
             const float4 g = __ldg(geo + e);
-            float3 rb = edge_position_adjoint(g, edge_adjoint_sum(edge_adj, e, 0, direct, slab_stride));
+            float4 adj = edge_adjoint_sum(edge_adj, e, pairs, direct, slab_stride);
+            // pair slabs: (r_bar_e - r_bar_r) (x) r_e = r_bar_e (x) r_e + r_bar_r (x) r_r, counted at the upper entry
+            if (pairs > 0 && __ldg(rev + e) > e) adj = add4(adj, edge_adjoint_sum(edge_adj, e, 0, pairs, slab_stride));
+            float3 rb = edge_position_adjoint(g, adj);
             if (direct < slabs) {
                 // a swapped slab entry is the adjoint of rev(e): unit vector -u, edge vector -r.  The sum over all
                 // e of r_bar_rev(e) (x) r_rev(e) is the same total, so it is folded in here with both signs flipped.
