@@ -547,13 +547,13 @@ spline_message_backward_team_kernel(const float* __restrict__ table, int H,
     const int held = ((l8 & 4) ? 2 : 0) + ((l8 & 2) ? 1 : 0);
     for (int i = part * kWarps + warp; i < num_atoms; i += parts * kWarps) {
         const int e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
+        // the row's adjoints: LAYER0 operands / residual path of the other layers (requested up front: a load
+        // at the end of the row would add an exposed L2 round trip to a kernel that is one latency chain)
+        const pk4 sb = pk_ldg(sbar_m + (size_t)i * H + ch);
         const float* vb = vbar_m + (size_t)i * 3 * H + ch;
-        pk4 sb = pk_zero(), vbx = pk_zero(), vby = pk_zero(), vbz = pk_zero();             // LAYER0: the row's adjoints
-        pk4 own_s = pk_zero(), own_x = pk_zero(), own_y = pk_zero(), own_z = pk_zero();   // other layers: its features
-        if (LAYER0) {
-            sb = pk_ldg(sbar_m + (size_t)i * H + ch);
-            vbx = pk_ldg(vb); vby = pk_ldg(vb + H); vbz = pk_ldg(vb + 2 * H);
-        } else {
+        const pk4 vbx = pk_ldg(vb), vby = pk_ldg(vb + H), vbz = pk_ldg(vb + 2 * H);
+        pk4 own_s = pk_zero(), own_x = pk_zero(), own_y = pk_zero(), own_z = pk_zero();   // the row's features
+        if (!LAYER0) {
             own_s = pk_ldg(s_in + (size_t)i * H + ch);
             const float* vi = v_in + (size_t)i * 3 * H + ch;
             own_x = pk_ldg(vi); own_y = pk_ldg(vi + H); own_z = pk_ldg(vi + 2 * H);
@@ -616,11 +616,10 @@ spline_message_backward_team_kernel(const float* __restrict__ table, int H,
         }
         if (!LAYER0) {
             acc_s = pk_team_sum(acc_s); acc_x = pk_team_sum(acc_x); acc_y = pk_team_sum(acc_y); acc_z = pk_team_sum(acc_z);
-            if (t == 0) {   // residual path (the row's own adjoints) + the gathered sums
-                pk_st(sbar_in + (size_t)i * H + ch, pk_add(pk_ldg(sbar_m + (size_t)i * H + ch), acc_s));
+            if (t == 0) {   // residual path + the gathered sums
+                pk_st(sbar_in + (size_t)i * H + ch, pk_add(sb, acc_s));
                 float* vo = vbar_in + (size_t)i * 3 * H + ch;
-                pk_st(vo, pk_add(pk_ldg(vb), acc_x)); pk_st(vo + H, pk_add(pk_ldg(vb + H), acc_y));
-                pk_st(vo + 2 * H, pk_add(pk_ldg(vb + 2 * H), acc_z));
+                pk_st(vo, pk_add(vbx, acc_x)); pk_st(vo + H, pk_add(vby, acc_y)); pk_st(vo + 2 * H, pk_add(vbz, acc_z));
             }
         }
     }
