@@ -72,6 +72,9 @@ except Exception:  # ImportError or a broken install
         def get_forces(self, atoms=None):
             return self.get_property("forces", atoms)
 
+        def get_stress(self, atoms=None):
+            return self.get_property("stress", atoms)
+
 
 class StudentForceFieldCalculator(_AseCalculator):
     """ASE-style calculator backed by the hand-written CUDA energy+force path."""
@@ -180,13 +183,18 @@ class StudentForceFieldCalculator(_AseCalculator):
             self._validate_inputs(positions, numbers, cell, pbc)
             want_stress = "stress" in properties and self.enable_stress
             volume = abs(float(np.linalg.det(cell)))
-            energy, forces, virial = self._evaluate_single(positions, numbers, cell, pbc,
-                                                           want_virial=want_stress and volume > 1e-12)
+            # Stress semantics.  The reference returns zeros without a cell or without a periodic axis
+            # (ase_calculator.py:548-550) and, because its model never reads `cell`, zeros for periodic
+            # input as well (the autograd call at :566 fails and :586-588 falls back).  pbc_mode='ignore' is
+            # the mode that reproduces the reference, so it returns those zeros; with
+            # pbc_mode='minimum_image' the model does see the cell and the stress is the real one:
+            # (1/V) dE/d(strain) from the edge adjoints of the force evaluation.
+            real_stress = (want_stress and self.pbc_mode == "minimum_image" and bool(pbc.any())
+                           and volume > 1e-12)
+            energy, forces, virial = self._evaluate_single(positions, numbers, cell, pbc, want_virial=real_stress)
             results: Dict[str, Any] = {"energy": energy, "forces": forces}
             if want_stress:
                 if virial is None:
-                    # no cell: like the reference (ase_calculator.py:521-588), whose stress path
-                    # yields zeros for every input
                     results["stress"] = np.zeros(6)
                 else:
                     # ASE convention: stress = (1/V) dE/d(strain), Voigt order xx yy zz yz xz xy
@@ -346,10 +354,10 @@ class StudentForceFieldCalculator(_AseCalculator):
         if len(atoms_list) == 1:
             atoms = atoms_list[0]
             atoms.calc = self
-            return [{
+            return [{   # same keys and stress handling as the reference's single-structure branch (:626-633)
                 "energy": self.get_potential_energy(atoms) if "energy" in properties else None,
                 "forces": self.get_forces(atoms) if "forces" in properties else None,
-                "stress": None,
+                "stress": self.get_stress(atoms) if "stress" in properties and self.enable_stress else None,
             }]
         counts = np.array([len(a) for a in atoms_list], dtype=np.int64)
         if np.any(counts == 0):

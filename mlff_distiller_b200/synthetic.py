@@ -68,6 +68,9 @@ class Structure:
     def get_forces(self):
         return self.calc.get_forces(self)
 
+    def get_stress(self):
+        return self.calc.get_stress(self)
+
 
 def water() -> Structure:
     """C1: ASE g2 H2O (O at z=0.119262, H at y=+-0.763239, z=-0.477047)."""

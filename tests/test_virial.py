@@ -124,7 +124,17 @@ def test_calculator_stress_voigt():
     sig = 0.5 * (w_ref[0] + w_ref[0].T) / abs(np.linalg.det(cell))
     voigt = np.array([sig[0, 0], sig[1, 1], sig[2, 2], sig[1, 2], sig[0, 2], sig[0, 1]])
     assert np.max(np.abs(s - voigt)) <= 2e-5 * max(1.0, np.abs(voigt).max())
-    # no cell -> zeros, like the reference
+    # the single-structure branch of calculate_batch hands the stress out like the reference's (:626-633)
+    one = calc.calculate_batch([box], properties=["energy", "forces", "stress"])
+    assert np.max(np.abs(one[0]["stress"] - voigt)) <= 2e-5 * max(1.0, np.abs(voigt).max())
+    # no cell -> zeros, like the reference (:548-550); a cell without a periodic axis -> zeros as well
     mol = synthetic.water()
     calc.calculate(mol, properties=["energy", "forces", "stress"])
     assert np.array_equal(calc.results["stress"], np.zeros(6))
+    open_box = synthetic.Structure(numbers, positions, cell=cell, pbc=np.zeros(3, dtype=bool))
+    calc.calculate(open_box, properties=["energy", "forces", "stress"])
+    assert np.array_equal(calc.results["stress"], np.zeros(6))
+    # pbc_mode='ignore' reproduces the reference, whose model never reads the cell: its stress is zeros
+    ref_mode = StudentForceFieldCalculator(GOLDEN / "weights_ultra_tiny.npz", device="cuda", enable_stress=True)
+    ref_mode.calculate(box, properties=["energy", "forces", "stress"])
+    assert np.array_equal(ref_mode.results["stress"], np.zeros(6))
