@@ -53,15 +53,19 @@ def chunk_by_budget(counts: Sequence[int], max_atoms: int, max_structs: int) -> 
     return out
 
 
-_PINNED = {}   # (rows, width) -> pinned host tensor reused by the root of gather_in_order
+_PINNED = {}   # width -> [two pinned host tensors, index of the one handed out last]
 
 
 def _pinned(rows: int, width: int):
+    """Page-locked staging buffer for the root of gather_in_order.  Page-locking 60 MB costs ~10 ms, so the
+    buffers are kept; two per row width are handed out alternately, so the arrays a gather returns stay
+    valid until the second-next gather of the same width (copy them to keep them longer)."""
     import torch
-    key = (width,)
-    buf = _PINNED.get(key)
+    slot = _PINNED.setdefault(width, [[None, None], 1])
+    i = slot[1] = 1 - slot[1]
+    buf = slot[0][i]
     if buf is None or buf.shape[0] < rows:
-        buf = _PINNED[key] = torch.empty((max(rows, 1), width), dtype=torch.float32).pin_memory()
+        buf = slot[0][i] = torch.empty((max(rows, 1), width), dtype=torch.float32).pin_memory()
     return buf[:rows]
 
 
@@ -77,7 +81,8 @@ def gather_in_order(local_energies: np.ndarray, local_forces: np.ndarray, counts
     ``root=None``: every rank receives everything (two padded ``all_gather_into_tensor`` calls).
     ``root=r``: shards are contiguous in input order, so every other rank sends its slab point-to-point
     straight into its slice of ONE output tensor on rank r (no padding, no concatenation; one
-    device-to-pinned-host copy); rank r returns ``(energies, forces)``, the others ``(None, None)``."""
+    device-to-pinned-host copy); rank r returns ``(energies, forces)``, the others ``(None, None)``.  On CUDA
+    the returned arrays are views of cached pinned buffers: valid until the second-next gather."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
@@ -109,9 +114,9 @@ def gather_in_order(local_energies: np.ndarray, local_forces: np.ndarray, counts
                 if r != root and sizes[r]:
                     dist.recv(out[int(starts[r]):int(starts[r + 1])], src=r, group=group)
             if device.type == "cuda":
-                host = _pinned(out.shape[0], width)      # page-locked once, reused by every later gather
+                host = _pinned(out.shape[0], width)      # page-locked once, reused (alternating) by later gathers
                 host.copy_(out, non_blocking=False)
-                return host.numpy().copy()
+                return host.numpy()
             return out.numpy()
 
         energies = to_root(local_energies, n_structs, 1)
