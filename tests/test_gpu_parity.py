@@ -270,6 +270,42 @@ def test_batch_of_druglike_structures_matches_oracle(model_bundle):
     assert np.max(np.abs(f - f_ref)) <= F_TOL
 
 
+def test_c2_full_size_batch_properties(model_bundle, variant):
+    """BASELINE config C2 at its full size (1024 x 50 atoms) through size-independent properties, where the
+    CPU oracle would take minutes: (1) the order of the structures in the batch is irrelevant -- bit for bit,
+    every row is accumulated by one lane group in CSR order whatever CTA it lands in; (2) a structure has
+    the same result in the full batch and in a half batch; (3) the forces of every structure sum to zero
+    (translation invariance of the energy) up to FP32 rounding; (4) a spot sample of structures against the
+    FP64 oracle."""
+    from mlff_distiller_b200 import synthetic
+    model, state, cfg = model_bundle
+    structs = synthetic.druglike_batch(1024, first=0, n=50)
+    z, pos, off = synthetic.concatenate(structs)
+    pos = pos.astype(np.float32)
+    e, f = _run(model, z, pos, off)
+    assert np.isfinite(e).all() and np.isfinite(f).all()
+    # (1) reversed structure order
+    zr, posr, offr = synthetic.concatenate(structs[::-1])
+    er, fr = _run(model, zr, posr.astype(np.float32), offr)
+    assert np.array_equal(er[::-1], e)
+    assert np.array_equal(fr.reshape(1024, 50, 3)[::-1].reshape(-1, 3), f)
+    # (2) first half alone
+    n_half = int(off[512])
+    eh, fh = _run(model, z[:n_half], pos[:n_half], off[:513])
+    assert np.array_equal(eh, e[:512]) and np.array_equal(fh, f[:n_half])
+    # (3) net force per structure
+    net = np.abs(f.reshape(1024, 50, 3).sum(axis=1)).max()
+    assert net <= 2e-4, net
+    # (4) spot sample against the oracle
+    pick = [0, 511, 1023]
+    zs, ps, os_ = synthetic.concatenate([structs[i] for i in pick])
+    e_ref, f_ref = po.evaluate(state, cfg["cutoff"], zs, ps.astype(np.float32), os_, dtype=torch.float64,
+                               dense_graph=False)
+    for k, i in enumerate(pick):
+        assert abs(e[i] - e_ref[k]) / 50 <= E_TOL
+        assert np.max(np.abs(f[50 * i:50 * i + 50] - f_ref[50 * k:50 * k + 50])) <= F_TOL
+
+
 def test_periodic_water_box_matches_oracle(model_bundle):
     from mlff_distiller_b200 import synthetic
     model, state, cfg = model_bundle
