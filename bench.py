@@ -58,6 +58,8 @@ def parse_args():
                          "sweep = BASELINE config 5: ONE host-side list of ragged structures (n ~ U{20..80}) partitioned "
                          "over the ranks, staged, evaluated and gathered back in input order (strong scaling)")
     ap.add_argument("--sweep-structures", type=int, default=100000)
+    ap.add_argument("--sweep-gather", choices=["shm", "p2p"], default="shm",
+                    help="ordered gather of the sweep: shared-memory output on one node | NCCL point-to-point into rank 0")
     ap.add_argument("--sweep-cache", default="",
                     help="npz written by tools/make_sweep_cache.py (numbers, positions, counts of the whole list): "
                          "ranks slice their shard from it instead of generating it")
@@ -447,8 +449,12 @@ def run_sweep(args):
     warm = max(1, min(int(np.searchsorted(offs, calc.max_atoms_per_call, side="right")) - 1, len(counts)))
     for _ in range(2):   # sizes the workspace, the pinned staging and (N > 1) the gather buffers
         calc.evaluate_arrays(numbers[: offs[warm]], pos[: offs[warm]], counts[:warm])
+    shared = None
     if world > 1:
-        sharding.gather_in_order(np.zeros(b - a, np.float32), np.zeros((int(counts.sum()), 3), np.float32), sizes, device=dev, root=0)
+        if args.sweep_gather == "shm":   # one node: every rank writes its host results into its slice of a shared segment
+            shared = sharding.SharedResults(sizes, root=0)
+        else:
+            sharding.gather_in_order(np.zeros(b - a, np.float32), np.zeros((int(counts.sum()), 3), np.float32), sizes, device=dev, root=0)
         dist.barrier()
     torch.cuda.synchronize(dev)
     sampler = ClockSampler(local)
@@ -463,10 +469,16 @@ def run_sweep(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        e, f = calc.evaluate_arrays(numbers, pos, counts)           # H2D, steps and D2H of every micro-batch
+        if shared is not None:   # micro-batch results go straight to this rank's place in the ordered output
+            e, f = calc.evaluate_arrays(numbers, pos, counts,
+                                        out=(shared.energies[shared.a:shared.b], shared.forces[shared.atom0:shared.atom1]))
+        else:
+            e, f = calc.evaluate_arrays(numbers, pos, counts)       # H2D, steps and D2H of every micro-batch
         t1 = time.perf_counter()
-        if world > 1:
-            e_all, f_all = sharding.gather_in_order(e, f, sizes, device=dev, root=0)   # ordered gather of energies and forces on rank 0
+        if shared is not None:
+            e_all, f_all = shared.collect()                         # a barrier: the output is complete on rank 0
+        elif world > 1:
+            e_all, f_all = sharding.gather_in_order(e, f, sizes, device=dev, root=0)   # point-to-point into rank 0's output
         else:
             e_all, f_all = e, f
         torch.cuda.synchronize(dev)
@@ -488,17 +500,23 @@ def run_sweep(args):
                                       f"{int(sizes.sum())} atoms), energy+forces, PaiNN student '{args.variant}', ONE host-side "
                                       "list partitioned over the ranks by atom count, results gathered in input order",
                           "variant": args.variant, "precision": args.precision, "filter_mode": args.filter_mode,
-                          "parallelism": f"structure-sharded x{world}; data path without collective; at the end every rank sends its "
-                                         "energies + forces point-to-point into its slice of rank 0's output",
+                          "parallelism": f"structure-sharded x{world}; data path without collective; ordered gather: "
+                                         + ("every rank's micro-batch results are written to its slice of one shared-memory "
+                                            "output (single node), then one barrier" if shared is not None else
+                                            "every rank sends its energies + forces point-to-point into its slice of rank 0's output"),
                           "l2_policy": "every micro-batch is new data (>100 MB of inputs and results per pass)"},
                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(16 * sizes.sum() + 4 * total),
                        "d2h_bytes_per_step": int(12 * sizes.sum() + 4 * total),
-                       "api": "StudentForceFieldCalculator.evaluate_arrays(host arrays) per rank + sharding.gather_in_order"},
+                       "api": "StudentForceFieldCalculator.evaluate_arrays(host arrays) per rank + "
+                              + ("sharding.SharedResults" if shared is not None else "sharding.gather_in_order")},
                "gpu_launches": launches, "clocks": clocks,
                "phases_s": {"evaluate_max_over_ranks": t_eval[best], "ordered_gather": times[best] - t_eval[best]},
                "all_pass_seconds": times,
                "energy_checksum": float(np.asarray(e_all, dtype=np.float64).sum())}
         print(json.dumps(out))
+    if shared is not None:
+        e = f = e_all = f_all = None
+        shared.close()
     if world > 1:
         dist.destroy_process_group()
 

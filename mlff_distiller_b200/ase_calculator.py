@@ -383,9 +383,26 @@ class StudentForceFieldCalculator(_AseCalculator):
         return results
 
     def evaluate_arrays(self, numbers: np.ndarray, positions: np.ndarray, counts: np.ndarray,
-                        cells: Optional[np.ndarray] = None, pbcs: Optional[np.ndarray] = None):
+                        cells: Optional[np.ndarray] = None, pbcs: Optional[np.ndarray] = None,
+                        out: Optional[Tuple[np.ndarray, np.ndarray]] = None):
         """Host arrays in, host arrays out: (energies [B] float32, forces [N,3] float32).  The
-        batched-structure interface underneath ``calculate_batch``; validation included."""
+        batched-structure interface underneath ``calculate_batch``; validation included.
+        ``out = (energies, forces)``: caller-provided float32 arrays of those shapes (e.g. a rank's slice
+        of a shared-memory result, ``sharding.SharedResults``) that receive the results of every
+        micro-batch as it completes; they are also what is returned."""
+        if out is not None:
+            e_out, f_out = out
+            if e_out.shape != (len(counts),) or f_out.shape != (len(numbers), 3) \
+                    or e_out.dtype != np.float32 or f_out.dtype != np.float32:
+                raise ValueError("out must be (float32 [structures], float32 [atoms, 3]) arrays")
+            e, f = self._evaluate_arrays(numbers, positions, counts, cells, pbcs, out)
+            if e is not e_out:   # paths that produce their own arrays
+                e_out[...] = e
+                f_out[...] = f
+            return e_out, f_out
+        return self._evaluate_arrays(numbers, positions, counts, cells, pbcs, None)
+
+    def _evaluate_arrays(self, numbers, positions, counts, cells, pbcs, out):
         numbers = np.asarray(numbers)
         positions = np.asarray(positions)
         counts = np.asarray(counts, dtype=np.int64)
@@ -410,6 +427,11 @@ class StudentForceFieldCalculator(_AseCalculator):
                 # open boundaries: keep the copies of chunk k+1 / k-1 under the kernels of chunk k
                 gen = ((numbers[int(offs[a]):int(offs[b])], positions[int(offs[a]):int(offs[b])], counts[a:b])
                        for a, b in chunks)
+                if out is not None:   # results of chunk k land in the caller's arrays while chunk k+1 runs
+                    for (a, b), (e, f) in zip(chunks, self.evaluate_stream(gen)):
+                        out[0][a:b] = e
+                        out[1][int(offs[a]):int(offs[b])] = f
+                    return out
                 for e, f in self.evaluate_stream(gen):
                     e_parts.append(e)
                     f_parts.append(f)

@@ -393,6 +393,26 @@ def _ragged_batches(num, per, first):
     return out
 
 
+def test_evaluate_arrays_fills_caller_provided_outputs():
+    """``out=`` (a rank's slice of a shared-memory result in the multi-GPU sweep): same values, written in
+    place, for the single-batch and the micro-batched path."""
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+    calc = StudentForceFieldCalculator(GOLDEN / "weights_ultra_tiny.npz", device="cuda")
+    structs = synthetic.druglike_batch(40, first=900, ragged=True)
+    z, pos, off = synthetic.concatenate(structs)
+    counts = np.diff(off)
+    e_ref, f_ref = calc.evaluate_arrays(z, pos, counts)
+    for budget in (calc.max_atoms_per_call, 400):
+        calc.max_atoms_per_call = budget
+        e_out = np.full(len(counts), np.nan, dtype=np.float32)
+        f_out = np.full((len(z), 3), np.nan, dtype=np.float32)
+        e, f = calc.evaluate_arrays(z, pos, counts, out=(e_out, f_out))
+        assert e is e_out and f is f_out
+        assert np.allclose(e_out, e_ref, rtol=0, atol=2e-5) and np.allclose(f_out, f_ref, rtol=0, atol=2e-5)
+    with pytest.raises(ValueError):
+        calc.evaluate_arrays(z, pos, counts, out=(np.zeros(3, np.float32), f_out))
+
+
 def test_evaluate_stream_matches_blocking_interface(calc):
     """The pipelined sweep interface (two batches in flight, copies under the kernels) returns
     exactly what the blocking call returns, batch by batch and in order."""

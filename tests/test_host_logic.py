@@ -90,6 +90,16 @@ if rank == 0:
     assert np.array_equal(e3, e) and np.array_equal(f3, f)
 else:
     assert e3 is None and f3 is None
+shared = sharding.SharedResults(counts, root=0)                            # one node: shared-memory gather of host results
+for rep in range(2):
+    shared.write(e_local + rep, f_local)
+    e4, f4 = shared.collect()
+    if rank == 0:
+        assert np.allclose(e4, e + rep, rtol=1e-6) and np.array_equal(f4, f)
+    else:
+        assert e4 is None and f4 is None
+    dist.barrier()
+shared.close()
 if rank == 0:
     print('GATHER_OK', a, b)
 dist.destroy_process_group()
