@@ -193,6 +193,8 @@ class SharedResults:
         return None, None
 
     def close(self):
+        if self._shm is None:
+            return
         if self._dist.is_initialized() and self._dist.get_world_size(self.group) > 1:
             self._dist.barrier(group=self.group)   # nobody is still writing
         self.energies = self.forces = None
@@ -202,4 +204,12 @@ class SharedResults:
             pass
         if self.rank == self.root:
             self._shm.unlink()
+        self._shm = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 

@@ -112,6 +112,19 @@ dist.destroy_process_group()
     assert "GATHER_OK" in proc.stdout
 
 
+def test_shared_results_single_process():
+    """Without a process group SharedResults degenerates to one rank owning the whole list."""
+    from mlff_distiller_b200 import sharding
+    counts = [3, 5, 2]
+    with sharding.SharedResults(counts) as shared:
+        assert (shared.a, shared.b, shared.atom0, shared.atom1) == (0, 3, 0, 10)
+        shared.write(np.arange(3), np.arange(30).reshape(10, 3))
+        e, f = shared.collect()
+        assert e.dtype == np.float32 and np.array_equal(e, [0, 1, 2]) and np.array_equal(f, np.arange(30).reshape(10, 3))
+        del e, f
+    shared.close()   # idempotent
+
+
 def test_calculator_validation_messages_without_gpu():
     from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
 
