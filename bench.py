@@ -223,28 +223,52 @@ class ClockSampler:
 # CPU arm: the oracle restatement of the reference path, all host threads
 # ------------------------------------------------------------------------------------------
 def cpu_chunk_runner(args):
+    """One chunk of the workload on the host cores.  With the reference's own files at hand (the tree in
+    the build container, else ``oracle/_ref/reference_path.zip`` packed from it by ``oracle/build_ref.py``)
+    this is the REFERENCE: its ``StudentForceField.forward`` on a stacked batch + one autograd call, the
+    way ``inference/ase_calculator.py:708-763`` (_batch_forward) drives it -- kind "reference".  Without
+    them: the restatement in oracle/painn_oracle.py (same ATen ops in the same order) -- kind "port"."""
     import torch
     from mlff_distiller_b200 import synthetic
     from oracle import painn_oracle as po
+    from oracle import reference_loader
     torch.set_num_threads(os.cpu_count() or 1)
     state, cfg = load_state(args.variant)
-    w = po.to_torch_weights(state)
+    kind = "port"
+    if reference_loader.source() is not None and not os.environ.get("MLFFD_BENCH_FORCE_PORT"):
+        from types import SimpleNamespace
+        model = reference_loader.build_reference_model(state, SimpleNamespace(**cfg))
+        kind = "reference"
+    else:
+        w = po.to_torch_weights(state)
 
-    def run_chunk(first):
+    def inputs(first):
         structs = synthetic.druglike_batch(REFERENCE_CHUNK, first=first, n=args.atoms)
         z, pos, off = synthetic.concatenate(structs)
-        e, f = po.energy_and_forces(w, torch.from_numpy(z), torch.from_numpy(pos.astype(np.float32)),
-                                    cfg["cutoff"], po.batch_from_offsets(off))
+        return torch.from_numpy(z), torch.from_numpy(pos.astype(np.float32)), po.batch_from_offsets(off)
+
+    def run_chunk(first):
+        z, pos, batch = inputs(first)
+        if kind == "reference":
+            pos.requires_grad_(True)
+            e = model(atomic_numbers=z, positions=pos, cell=None, pbc=None, batch=batch)
+            f = -torch.autograd.grad(e, pos, grad_outputs=torch.ones_like(e), create_graph=False, retain_graph=False)[0]
+            e = e.detach()
+        else:
+            e, f = po.energy_and_forces(w, z, pos, cfg["cutoff"], batch)
         return e.numpy().astype(np.float64), f.numpy().astype(np.float64)
 
-    return run_chunk, torch.get_num_threads()
+    described = {"reference": f"the reference's own student_model.py ({reference_loader.source()}: forward on the stacked chunk + autograd "
+                              "forces, as inference/ase_calculator.py:_batch_forward)",
+                 "port": "oracle/painn_oracle.py = torch CPU restatement of the reference, autograd forces"}[kind]
+    return run_chunk, torch.get_num_threads(), kind, described
 
 
 def cpu_baseline(args, gpu_reference=None):
     """Times the CPU restatement of the reference on a bounded sample of the workload and -- with the
     GPU energies / forces of the same (unperturbed) structures in ``gpu_reference`` -- turns the outputs it
     computes anyway into the ``parity`` record of the JSON line."""
-    run_chunk, threads = cpu_chunk_runner(args)
+    run_chunk, threads, kind, described = cpu_chunk_runner(args)
     run_chunk(0)  # warm-up
     done, t0 = 0, time.perf_counter()
     max_de = max_df = 0.0
@@ -257,14 +281,13 @@ def cpu_baseline(args, gpu_reference=None):
             max_df = max(max_df, float(np.max(np.abs(f - f_gpu[a0:a0 + f.shape[0]]))))
         done += REFERENCE_CHUNK
     dt = time.perf_counter() - t0
-    base = {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"first {done} structures of the workload in chunks of {REFERENCE_CHUNK} "
-                      f"(oracle/painn_oracle.py = torch CPU restatement of the reference, autograd forces), {dt:.1f} s"}
+    base = {"value": done / dt, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"first {done} structures of the workload in chunks of {REFERENCE_CHUNK} ({described}), {dt:.1f} s"}
     parity = None
     if gpu_reference is not None:
         parity = {"structures": done, "max_dE_per_atom_eV": max_de, "max_dF_eV_per_A": max_df,
                   "tol_dE_per_atom_eV": 1e-5, "tol_dF_eV_per_A": 1e-4, "ok": bool(max_de <= 1e-5 and max_df <= 1e-4),
-                  "against": "CPU restatement of the reference (FP32) on the first structures of the C2 batch, unperturbed inputs"}
+                  "against": f"{described} (FP32) on the first structures of the C2 batch, unperturbed inputs"}
     return base, parity
 
 
@@ -272,7 +295,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    run_chunk, threads = cpu_chunk_runner(args)
+    run_chunk, threads, kind, described = cpu_chunk_runner(args)
     for i in range(max(args.warmup, 1)):
         run_chunk(i * REFERENCE_CHUNK)
     t0 = time.perf_counter()
@@ -280,14 +303,14 @@ def run_reference(args):
         run_chunk((i % (max(args.batch // REFERENCE_CHUNK, 1))) * REFERENCE_CHUNK)
     dt = time.perf_counter() - t0
     value = args.steps * REFERENCE_CHUNK / dt
-    sample = (f"each step = {REFERENCE_CHUNK} structures of the workload through the torch CPU "
-              f"restatement of the reference path (the reference cannot batch 1024: 31 GB dense mask)")
+    sample = (f"each step = {REFERENCE_CHUNK} structures of the workload through {described} "
+              f"(the reference cannot batch 1024: 31 GB dense mask)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 

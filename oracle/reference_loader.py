@@ -7,8 +7,10 @@ parent-package stubs make them importable under their real dotted names, which
 ``forward_with_analytical_forces`` needs (student_model.py:853, :975).
 
 ``/root/reference`` does not exist on the GPU box: this module is used by
-``tests/golden/make_golden.py`` (run here, output committed) and by CPU tests that skip when the
-reference tree is absent.
+``tests/golden/make_golden.py`` (run here, output committed), by CPU tests that skip when the
+reference tree is absent, and by ``bench.py``'s CPU legs, which fall back from the tree to the
+archive ``oracle/build_ref.py`` packed from it (``oracle/_ref/reference_path.zip``: the same two
+files, unmodified, imported with zipimport).
 """
 from __future__ import annotations
 
@@ -18,24 +20,48 @@ import types
 from pathlib import Path
 
 REFERENCE_ROOT = Path("/root/reference")
+ARCHIVE = Path(__file__).resolve().parent / "_ref" / "reference_path.zip"
 
 
 def available() -> bool:
+    """The reference TREE is present (this container)."""
     return (REFERENCE_ROOT / "src/mlff_distiller/models/student_model.py").exists()
 
 
+def archive_available() -> bool:
+    """The archive packed by ``oracle/build_ref.py`` is present (it travels to the GPU box)."""
+    return ARCHIVE.exists()
+
+
+def source() -> str | None:
+    """Where :func:`load_reference_module` imports from: 'tree', 'archive' or None.
+    ``MLFFD_REFERENCE_SOURCE=archive`` forces the archive (CPU test of the GPU-box situation)."""
+    import os
+    forced = os.environ.get("MLFFD_REFERENCE_SOURCE", "")
+    if forced == "archive":
+        return "archive" if archive_available() else None
+    if available():
+        return "tree"
+    return "archive" if archive_available() else None
+
+
 def load_reference_module(name: str = "student_model"):
-    """Return ``mlff_distiller.models.<name>`` from the reference tree."""
-    if not available():
-        raise FileNotFoundError("reference tree not present")
-    src = REFERENCE_ROOT / "src" / "mlff_distiller"
-    if "mlff_distiller" not in sys.modules or not hasattr(sys.modules["mlff_distiller"], "__path__"):
+    """Return ``mlff_distiller.models.<name>`` from the reference tree, else from the archive."""
+    src_kind = source()
+    if src_kind is None:
+        raise FileNotFoundError("neither the reference tree nor oracle/_ref/reference_path.zip is present")
+    # directory or zip sub-path: both are valid package __path__ entries (zipimport handles the second)
+    src = str(REFERENCE_ROOT / "src" / "mlff_distiller") if src_kind == "tree" else f"{ARCHIVE}/mlff_distiller"
+    pkg = sys.modules.get("mlff_distiller")
+    if pkg is None or getattr(pkg, "__path__", None) != [src]:
+        for key in [k for k in sys.modules if k == "mlff_distiller" or k.startswith("mlff_distiller.")]:
+            del sys.modules[key]
         pkg = types.ModuleType("mlff_distiller")
-        pkg.__path__ = [str(src)]
+        pkg.__path__ = [src]
         sys.modules["mlff_distiller"] = pkg
     if "mlff_distiller.models" not in sys.modules:
         sub = types.ModuleType("mlff_distiller.models")
-        sub.__path__ = [str(src / "models")]
+        sub.__path__ = [src + "/models"]
         sys.modules["mlff_distiller.models"] = sub
     return importlib.import_module(f"mlff_distiller.models.{name}")
 

@@ -179,19 +179,77 @@ def test_validate_arrays_messages_without_gpu():
         calc._validate_arrays(z, np.full((4, 3), np.inf), np.array([4]))
 
 
-def test_bench_reference_arm_prints_exactly_one_json_line():
-    """The driver parses stdout of bench.py: one JSON line, nothing else (library banners go to stderr)."""
+def _reference_arm(env_extra):
     import json
+    import os
     import subprocess
     import sys
     from conftest import ROOT
     proc = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                          capture_output=True, text=True, timeout=600)
+                          capture_output=True, text=True, timeout=600, env={**os.environ, **env_extra})
     assert proc.returncode == 0, proc.stderr[-2000:]
     lines = [l for l in proc.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
-    d = json.loads(lines[0])
+    return json.loads(lines[0])
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver parses stdout of bench.py: one JSON line, nothing else (library banners go to stderr).
+    With neither the reference tree nor the packed archive the arm is the restatement (kind "port")."""
+    d = _reference_arm({"MLFFD_BENCH_FORCE_PORT": "1"})
     assert d["impl"] == "reference" and d["metric"] == "structures_per_second_energy_forces"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"].startswith("C2") and d["higher_is_better"] is True
+
+
+def test_reference_archive_is_the_reference_and_the_arm_runs_it():
+    """oracle/build_ref.py packs the reference's two files, unmodified, into oracle/_ref/reference_path.zip (what
+    travels to the GPU box); imported from there with zipimport the model gives the outputs of the restatement
+    bit for bit, and bench.py --impl reference then reports kind "reference"."""
+    import hashlib
+    import json
+    import zipfile
+    import torch
+    from conftest import load_weights
+    from mlff_distiller_b200 import synthetic
+    from oracle import build_ref, reference_loader
+    import oracle.painn_oracle as po
+    path = build_ref.build()
+    if path is None:
+        pytest.skip("neither the reference tree nor a prebuilt archive is present")
+    with zipfile.ZipFile(path) as z:
+        manifest = json.loads(z.read("MANIFEST.json"))["sha256"]
+        for member, digest in manifest.items():
+            assert hashlib.sha256(z.read(member[len("src/"):])).hexdigest() == digest
+            if reference_loader.available():
+                assert (reference_loader.REFERENCE_ROOT / member).read_bytes() == z.read(member[len("src/"):])
+        assert z.read("mlff_distiller/__init__.py") == b"" and z.read("mlff_distiller/models/__init__.py") == b""
+    d = _reference_arm({"MLFFD_REFERENCE_SOURCE": "archive"})
+    assert d["cpu_baseline"]["kind"] == "reference" and "archive" in d["cpu_baseline"]["sample"]
+    assert d["gpu_launches"] == 0 and d["value"] > 0
+
+    # same outputs as the restatement, in a subprocess so that this process keeps whatever it imported before
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import sys, json, numpy as np, torch; sys.path.insert(0, %r)\n"
+        "from types import SimpleNamespace\n"
+        "from oracle import reference_loader as rl, painn_oracle as po\n"
+        "from mlff_distiller_b200 import synthetic\n"
+        "z = np.load(%r); state = {k: z[k] for k in z.files if not k.startswith('__')}; cfg = json.loads(str(z['__config__']))\n"
+        "assert rl.source() == 'archive'\n"
+        "model = rl.build_reference_model(state, SimpleNamespace(**cfg))\n"
+        "assert '.zip' in sys.modules['mlff_distiller.models.student_model'].__file__\n"
+        "zz, pos, off = synthetic.concatenate(synthetic.druglike_batch(3, first=99, ragged=True))\n"
+        "p = torch.from_numpy(pos.astype(np.float32)).requires_grad_(True); b = po.batch_from_offsets(off)\n"
+        "e = model(atomic_numbers=torch.from_numpy(zz), positions=p, cell=None, pbc=None, batch=b)\n"
+        "f = -torch.autograd.grad(e, p, grad_outputs=torch.ones_like(e))[0]\n"
+        "e2, f2 = po.energy_and_forces(po.to_torch_weights(state), torch.from_numpy(zz), torch.from_numpy(pos.astype(np.float32)), cfg['cutoff'], b)\n"
+        "assert torch.equal(e.detach(), e2) and torch.equal(f, f2), (float((e.detach()-e2).abs().max()), float((f-f2).abs().max()))\n"
+        "print('identical')\n") % (str(ROOT), str(ROOT / "tests" / "golden" / "weights_ultra_tiny.npz"))
+    import os
+    proc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                          env={**os.environ, "MLFFD_REFERENCE_SOURCE": "archive"})
+    assert proc.returncode == 0 and "identical" in proc.stdout, proc.stderr[-2000:]
