@@ -174,6 +174,14 @@ class SharedResults:
             dist.broadcast_object_list(name, src=root, group=group)   # once, outside any timed region
         if self.rank != root:
             self._shm = shared_memory.SharedMemory(name=name[0])
+            # Python < 3.13 registers an ATTACHED segment with this process's resource tracker too, which would
+            # unlink it when this rank exits (possibly before the root has read it) and warn about a leak; the
+            # root created the segment and is the one that unlinks it
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
         self.energies = np.ndarray((nb,), dtype=np.float32, buffer=self._shm.buf, offset=0)
         self.forces = np.ndarray((na, 3), dtype=np.float32, buffer=self._shm.buf, offset=4 * nb)
 

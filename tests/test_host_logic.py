@@ -110,6 +110,8 @@ dist.destroy_process_group()
                            str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert proc.returncode == 0, proc.stderr[-2000:]
     assert "GATHER_OK" in proc.stdout
+    # only the root owns (and unlinks) the shared-memory segment: no second unlink by an attached rank's tracker
+    assert "resource_tracker" not in proc.stderr, proc.stderr[-2000:]
 
 
 def test_shared_results_single_process():
