@@ -359,27 +359,37 @@ class StudentForceFieldCalculator(_AseCalculator):
                 "forces": self.get_forces(atoms) if "forces" in properties else None,
                 "stress": self.get_stress(atoms) if "stress" in properties and self.enable_stress else None,
             }]
-        counts = np.array([len(a) for a in atoms_list], dtype=np.int64)
+        counts = np.fromiter(map(len, atoms_list), dtype=np.int64, count=len(atoms_list))
         if np.any(counts == 0):
             raise ValueError("Cannot calculate properties for empty structure")
-        numbers = np.concatenate([a.get_atomic_numbers() for a in atoms_list])
-        positions = np.concatenate([a.get_positions() for a in atoms_list])
+        # marshalling (ase_calculator.py:647-706 stacks the same two arrays): ASE's `numbers` / `positions`
+        # attributes are the stored arrays, the getters copy each of them first -- 1024 small copies per call
+        try:
+            numbers = np.concatenate([a.numbers for a in atoms_list])
+            positions = np.concatenate([a.positions for a in atoms_list])
+        except AttributeError:   # Atoms-like objects that only offer the getters
+            numbers = np.concatenate([a.get_atomic_numbers() for a in atoms_list])
+            positions = np.concatenate([a.get_positions() for a in atoms_list])
         cells = pbcs = None
         if self.pbc_mode == "minimum_image" and any(np.any(a.get_pbc()) for a in atoms_list):
             cells = np.stack([np.asarray(a.get_cell(), dtype=np.float64) for a in atoms_list])
             pbcs = np.stack([np.asarray(a.get_pbc(), dtype=bool) for a in atoms_list])
         energies, forces = self.evaluate_arrays(numbers, positions, counts, cells, pbcs)
-        results, off = [], 0
-        for i, c in enumerate(counts):
+        # per-structure result dicts (ase_calculator.py:765-817): same keys, forces are views of one array
+        want_e, want_f = "energy" in properties, "forces" in properties
+        want_s = "stress" in properties and self.enable_stress   # "not supported in batch mode yet" (:810-812)
+        e_list = energies.tolist()
+        offs = np.concatenate([[0], np.cumsum(counts)]).tolist()
+        results = []
+        for i in range(len(counts)):
             r: Dict[str, Any] = {}
-            if "energy" in properties:
-                r["energy"] = float(energies[i])
-            if "forces" in properties:
-                r["forces"] = forces[off:off + c]
-            if "stress" in properties and self.enable_stress:
+            if want_e:
+                r["energy"] = e_list[i]
+            if want_f:
+                r["forces"] = forces[offs[i]:offs[i + 1]]
+            if want_s:
                 r["stress"] = None
             results.append(r)
-            off += c
         return results
 
     def evaluate_arrays(self, numbers: np.ndarray, positions: np.ndarray, counts: np.ndarray,

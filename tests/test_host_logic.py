@@ -256,3 +256,64 @@ def test_reference_archive_is_the_reference_and_the_arm_runs_it():
     proc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
                           env={**os.environ, "MLFFD_REFERENCE_SOURCE": "archive"})
     assert proc.returncode == 0 and "identical" in proc.stdout, proc.stderr[-2000:]
+
+
+def test_calculate_batch_marshalling_without_gpu():
+    """List of structure objects -> stacked arrays -> list of result dicts (ase_calculator.py:647-706, :765-817),
+    with a stand-in for the device evaluation: atoms-like objects with ASE's `numbers` / `positions`
+    attributes and ones that only offer the getters give the same stacked inputs; results are cut back per
+    structure in input order with the reference's keys."""
+    from mlff_distiller_b200 import synthetic
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+
+    class GettersOnly:
+        def __init__(self, s):
+            self._s = s
+
+        def __len__(self):
+            return len(self._s)
+
+        def get_atomic_numbers(self):
+            return self._s.get_atomic_numbers()
+
+        def get_positions(self):
+            return self._s.get_positions()
+
+        def get_pbc(self):
+            return self._s.get_pbc()
+
+        def get_cell(self):
+            return self._s.get_cell()
+
+    calc = object.__new__(StudentForceFieldCalculator)
+    calc.pbc_mode, calc.enable_stress = "ignore", True
+    seen = []
+
+    def fake_evaluate(numbers, positions, counts, cells=None, pbcs=None, out=None):
+        seen.append((numbers.copy(), positions.copy(), counts.copy(), cells, pbcs))
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        e = np.array([positions[offs[i]:offs[i + 1]].sum() for i in range(len(counts))], dtype=np.float32)
+        return e, (positions * 2.0).astype(np.float32)
+
+    calc.evaluate_arrays = fake_evaluate
+    structs = synthetic.druglike_batch(7, first=3, ragged=True)
+    res_a = calc.calculate_batch(structs)
+    res_g = calc.calculate_batch([GettersOnly(s) for s in structs])
+    for a, b in zip(seen[0][:3], seen[1][:3]):
+        assert np.array_equal(a, b)
+    z, pos, off = synthetic.concatenate(structs)
+    assert np.array_equal(seen[0][0], z) and np.array_equal(seen[0][1], pos) and seen[0][3] is None
+    assert np.array_equal(seen[0][2], np.diff(off))
+    for res in (res_a, res_g):
+        assert len(res) == len(structs)
+        for i, (r, s) in enumerate(zip(res, structs)):
+            assert set(r) == {"energy", "forces"} and isinstance(r["energy"], float)
+            assert r["energy"] == float(np.float32(s.positions.sum()))
+            assert r["forces"].shape == (len(s), 3) and np.array_equal(r["forces"], (s.positions * 2.0).astype(np.float32))
+    only_e = calc.calculate_batch(structs[:2], properties=["energy"])
+    assert [set(r) for r in only_e] == [{"energy"}, {"energy"}]
+    with_s = calc.calculate_batch(structs[:2], properties=["energy", "forces", "stress"])
+    assert all(r["stress"] is None for r in with_s)      # "not supported in batch mode yet", like the reference
+    assert calc.calculate_batch([]) == []
+    with pytest.raises(ValueError, match="empty structure"):
+        calc.calculate_batch([structs[0], synthetic.Structure([], np.zeros((0, 3)))])
