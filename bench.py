@@ -784,6 +784,7 @@ def main():
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     buf = io.StringIO()
+    failed = None
     try:
         with contextlib.redirect_stdout(buf):
             if args.impl == "reference":
@@ -792,6 +793,8 @@ def main():
                 run_sweep(args)
             else:
                 run_b200(args)
+    except SystemExit as e:   # a failed parity record: the line (with parity.ok = false) is still printed, then exit non-zero
+        failed = e
     finally:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
@@ -799,6 +802,8 @@ def main():
     lines = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
     if lines:
         print(lines[-1], flush=True)
+    if failed is not None:
+        raise failed
 
 
 if __name__ == "__main__":

@@ -23,7 +23,7 @@ from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Tupl
 import numpy as np
 import torch
 
-from .student_model import StudentForceField
+from .student_model import StudentForceField, check_minimum_image
 
 logger = logging.getLogger(__name__)
 
@@ -234,20 +234,8 @@ class StudentForceFieldCalculator(_AseCalculator):
                 self._check_minimum_image(cell, pbc)
 
     def _check_minimum_image(self, cell, pbc):
-        """Minimum image is unique only if every periodic cell height is >= 2 r_c."""
-        vol = abs(np.linalg.det(cell))
-        for k in range(3):
-            if pbc[k]:
-                a, b = cell[(k + 1) % 3], cell[(k + 2) % 3]
-                height = vol / np.linalg.norm(np.cross(a, b))
-                if height < 2.0 * self.model.cutoff:
-                    raise ValueError(
-                        f"pbc_mode='minimum_image' needs cell heights >= 2*cutoff "
-                        f"({2 * self.model.cutoff:.2f} Å); axis {k} has {height:.3f} Å")
-                if height < 2.0 * (self.model.cutoff + self.skin):
-                    raise ValueError(
-                        f"skin={self.skin} needs periodic cell heights >= 2*(cutoff + skin) "
-                        f"({2 * (self.model.cutoff + self.skin):.2f} Å); axis {k} has {height:.3f} Å")
+        """Minimum image is unique only if every periodic cell height is >= 2 (r_c + skin)."""
+        check_minimum_image(cell, pbc, float(self.model.cutoff), getattr(self, "skin", 0.0))
 
     def _evaluate_single(self, positions, numbers, cell, pbc, want_virial: bool = False):
         """One structure.  The first calls for a system run eagerly (size the workspace, grow it
@@ -421,10 +409,8 @@ class StudentForceFieldCalculator(_AseCalculator):
         if periodic:
             if not np.isfinite(np.asarray(cells)).all():
                 raise ValueError("Cell contains NaN or Inf values")
-            cells_a, pbcs_a = np.asarray(cells, dtype=np.float64).reshape(-1, 3, 3), np.asarray(pbcs, dtype=bool).reshape(-1, 3)
-            for b in range(len(counts)):   # a cell too small for the minimum image would silently drop periodic images
-                if pbcs_a[min(b, len(pbcs_a) - 1)].any():
-                    self._check_minimum_image(cells_a[min(b, len(cells_a) - 1)], pbcs_a[min(b, len(pbcs_a) - 1)])
+            # a cell too small for the minimum image would silently drop periodic images
+            self._check_minimum_image(np.asarray(cells, dtype=np.float64), np.asarray(pbcs, dtype=bool))
         if self._replicas is not None and not periodic and len(counts) >= 2 * len(self._replicas):
             return self._evaluate_on_all_devices(numbers, positions, counts)
         if len(numbers) > self.max_atoms_per_call and len(counts) > 1:

@@ -139,6 +139,8 @@ class DeviceMD:
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.cells = self.pbc = None
         if cell is not None and pbc is not None and bool(np.any(pbc)):
+            from .student_model import check_minimum_image
+            check_minimum_image(np.asarray(cell), np.asarray(pbc), float(model.cutoff), float(getattr(model, "skin", 0.0)))
             self.cells, self.pbc = model.pack_cells(torch.as_tensor(np.asarray(cell)), torch.as_tensor(np.asarray(pbc)),
                                                     self.nb, dev)
         self.use_graph, self.graph, self._graph_caps = use_graph, None, None

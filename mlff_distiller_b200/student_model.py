@@ -80,6 +80,33 @@ class _InteractionParams(nn.Module):
         self.update = _UpdateParams(h)
 
 
+def check_minimum_image(cell, pbc, cutoff: float, skin: float = 0.0) -> None:
+    """The one-image neighbour kernels are exact only if every PERIODIC cell height is >= 2 (r_c + skin);
+    a smaller cell would silently lose periodic images.  ``cell`` [3,3] or [B,3,3], ``pbc`` [3] or [B,3]
+    (arrays or tensors, any device); raises ``ValueError`` naming the first offending structure and axis.
+    Shared by every entry point that accepts a cell: the calculator, ``StudentForceField`` (forward,
+    analytical forces, stress), ``radius_graph`` and ``md.DeviceMD``."""
+    c = np.asarray(torch.as_tensor(cell).detach().cpu().numpy(), dtype=np.float64).reshape(-1, 3, 3)
+    p = np.asarray(torch.as_tensor(pbc).detach().cpu().numpy()).astype(bool).reshape(-1, 3)
+    for b in range(max(len(c), len(p))):
+        cb, pb = c[min(b, len(c) - 1)], p[min(b, len(p) - 1)]
+        if not pb.any():
+            continue
+        vol = abs(np.linalg.det(cb))
+        for k in range(3):
+            if not pb[k]:
+                continue
+            area = np.linalg.norm(np.cross(cb[(k + 1) % 3], cb[(k + 2) % 3]))
+            height = vol / area if area > 0 else 0.0
+            where = f"axis {k}" if max(len(c), len(p)) == 1 else f"structure {b}, axis {k}"
+            if height < 2.0 * cutoff:
+                raise ValueError(f"pbc_mode='minimum_image' needs cell heights >= 2*cutoff "
+                                 f"({2 * cutoff:.2f} Å); {where} has {height:.3f} Å")
+            if height < 2.0 * (cutoff + skin):
+                raise ValueError(f"skin={skin} needs periodic cell heights >= 2*(cutoff + skin) "
+                                 f"({2 * (cutoff + skin):.2f} Å); {where} has {height:.3f} Å")
+
+
 def _offsets_from_batch(batch: torch.Tensor) -> Tuple[torch.Tensor, int]:
     """offsets [B+1] int32 from a sorted batch vector (one device sync, like the reference's
     ``batch.max()`` at student_model.py:739-745)."""
@@ -265,6 +292,7 @@ class StudentForceField(nn.Module):
         cells_d = pbc_d = None
         if self.pbc_mode == "minimum_image" and cell is not None and pbc is not None \
                 and bool(torch.as_tensor(pbc).any()):
+            check_minimum_image(cell, pbc, float(self.cutoff), self.skin)
             cells_d, pbc_d = self.pack_cells(cell, pbc, nb, dev)
         return z, pos, offsets, nb, cells_d, pbc_d
 
@@ -429,6 +457,7 @@ def radius_graph(positions: torch.Tensor, r: float, batch: Optional[torch.Tensor
         offsets, nb = _offsets_from_batch(batch.to(dev))
     cells_d = pbc_d = None
     if cell is not None and pbc is not None and bool(torch.as_tensor(pbc).any()):
+        check_minimum_image(cell, pbc, float(r), getattr(engine, "skin", 0.0))
         cells_d, pbc_d = StudentForceField.pack_cells(cell, pbc, nb, dev)
     eng = engine
     eng.ensure(n, nb)
@@ -446,4 +475,4 @@ def radius_graph(positions: torch.Tensor, r: float, batch: Optional[torch.Tensor
     raise RuntimeError("edge workspace overflow persisted after growing")
 
 
-__all__ = ["StudentForceField", "EnergyOnlyWrapper", "radius_graph"]
+__all__ = ["StudentForceField", "EnergyOnlyWrapper", "radius_graph", "check_minimum_image"]

@@ -317,3 +317,44 @@ def test_calculate_batch_marshalling_without_gpu():
     assert calc.calculate_batch([]) == []
     with pytest.raises(ValueError, match="empty structure"):
         calc.calculate_batch([structs[0], synthetic.Structure([], np.zeros((0, 3)))])
+
+
+def test_minimum_image_check_is_shared_by_every_entry_point_that_takes_a_cell():
+    """A periodic cell height below 2 (r_c + skin) would silently lose images in the one-image kernels: the
+    calculator (single and batched), StudentForceField._prepare (forward / analytical forces / stress) and
+    md.DeviceMD all run the same host-side check before anything reaches the device."""
+    import torch
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+    from mlff_distiller_b200.student_model import StudentForceField, check_minimum_image
+    sheared = np.eye(3) * 10.6
+    sheared[1, 0], sheared[2, 1] = 0.7, -0.5
+    check_minimum_image(sheared, [True] * 3, 5.0)                                   # heights 10.58 .. 10.6
+    check_minimum_image(torch.from_numpy(sheared)[None], torch.tensor([[True] * 3]), 5.0)
+    check_minimum_image(np.diag([20.0, 3.0, 20.0]), [True, False, True], 5.0)       # the short axis is not periodic
+    check_minimum_image(np.eye(3) * 3, [False] * 3, 5.0)
+    with pytest.raises(ValueError, match=r"2\*cutoff.*axis 0 has 9\.900"):
+        check_minimum_image(np.eye(3) * 9.9, [True, False, False], 5.0)
+    with pytest.raises(ValueError, match="structure 1, axis 2"):
+        check_minimum_image(np.stack([np.eye(3) * 20, np.eye(3) * 8]), np.array([[True] * 3, [False, False, True]]), 5.0)
+    with pytest.raises(ValueError, match=r"skin=1\.0 needs"):
+        check_minimum_image(np.eye(3) * 11, [True] * 3, 5.0, 1.0)
+    # a sheared cell whose edge lengths pass but whose height does not
+    thin = np.array([[10.5, 0, 0], [9.0, 5.4, 0], [0, 0, 12.0]])
+    assert np.linalg.norm(thin[1]) > 10.0
+    with pytest.raises(ValueError, match=r"axis 0 has 5\.40"):
+        check_minimum_image(thin, [True] * 3, 5.0)
+
+    model = StudentForceField(hidden_dim=32, num_interactions=1, num_rbf=4, cutoff=5.0, max_z=10, pbc_mode="minimum_image")
+    with pytest.raises(ValueError, match=r"2\*cutoff"):
+        model._prepare(torch.tensor([1, 8]), torch.zeros(2, 3), torch.eye(3) * 6, torch.tensor([True] * 3), None)
+    ignore = StudentForceField(hidden_dim=32, num_interactions=1, num_rbf=4, cutoff=5.0, max_z=10)
+    ignore._prepare(torch.tensor([1, 8]), torch.zeros(2, 3), torch.eye(3) * 6, torch.tensor([True] * 3), None)   # pbc_mode='ignore'
+
+    class Fake:
+        max_z, cutoff = 100, 5.0
+
+    calc = object.__new__(StudentForceFieldCalculator)
+    calc.model, calc.pbc_mode, calc.skin, calc._replicas = Fake(), "minimum_image", 0.0, None
+    z, pos, counts = np.array([1, 8, 1, 8]), np.zeros((4, 3)), np.array([2, 2])
+    with pytest.raises(ValueError, match="structure 1, axis 0"):
+        calc._evaluate_arrays(z, pos, counts, np.stack([np.eye(3) * 20, np.eye(3) * 7]), np.ones((2, 3), dtype=bool), None)
