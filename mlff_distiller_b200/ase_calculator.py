@@ -182,7 +182,7 @@ class StudentForceFieldCalculator(_AseCalculator):
             pbc = np.asarray(atoms.get_pbc(), dtype=bool)
             self._validate_inputs(positions, numbers, cell, pbc)
             want_stress = "stress" in properties and self.enable_stress
-            volume = abs(float(np.linalg.det(cell)))
+            volume = abs(float(np.linalg.det(cell))) if want_stress else 0.0   # an MD loop asks for energy + forces only
             # Stress semantics.  The reference returns zeros without a cell or without a periodic axis
             # (ase_calculator.py:548-550) and, because its model never reads `cell`, zeros for periodic
             # input as well (the autograd call at :566 fails and :586-588 falls back).  pbc_mode='ignore' is
@@ -217,9 +217,10 @@ class StudentForceFieldCalculator(_AseCalculator):
         embedding size (the reference checks 1-118 although trained tables stop at max_z)."""
         if len(positions) == 0:
             raise ValueError("Cannot calculate properties for empty structure")
-        if np.any(numbers < 1) or np.any(numbers > 118):
+        z_min, z_max = int(numbers.min()), int(numbers.max())   # two reductions instead of three masks: this runs every MD step
+        if z_min < 1 or z_max > 118:
             raise ValueError(f"Invalid atomic numbers: must be 1-118, got {numbers}")
-        if np.any(numbers > self.model.max_z):
+        if z_max > self.model.max_z:
             raise ValueError(f"Invalid atomic numbers: model supports Z <= {self.model.max_z}, got {numbers}")
         if not np.isfinite(positions).all():
             raise ValueError("Positions contain NaN or Inf values")
