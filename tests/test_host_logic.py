@@ -25,6 +25,44 @@ def test_partition_covers_everything_once():
     assert all(counts[a:b].sum() <= 4096 and b - a <= 64 for a, b in chunks)
 
 
+def test_partition_and_chunking_properties():
+    """Property tests (hypothesis): for ANY list of structure sizes and ANY shard count the shards are
+    contiguous, disjoint and cover the list (empty shards allowed when there are more ranks than
+    structures), no shard exceeds the ideal load by more than the largest structure, and micro-batches
+    respect both budgets except for a single structure that is larger than the atom budget by itself."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.integers(1, 400), min_size=0, max_size=200), st.integers(1, 16))
+    def check_partition(counts, shards):
+        parts = sharding.partition_by_atoms(counts, shards)
+        assert len(parts) == shards and parts[0][0] == 0 and parts[-1][1] == len(counts)
+        assert all(a <= b for a, b in parts)
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(shards - 1))
+        if counts:
+            loads = [sum(counts[a:b]) for a, b in parts]
+            assert sum(loads) == sum(counts)
+            assert max(loads) <= sum(counts) / shards + max(counts)
+        for r in range(shards):
+            assert sharding.shard_slice(counts, r, shards) == parts[r]
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.integers(1, 400), min_size=0, max_size=200), st.integers(1, 2000), st.integers(1, 50))
+    def check_chunks(counts, max_atoms, max_structs):
+        chunks = sharding.chunk_by_budget(counts, max_atoms, max_structs)
+        if not counts:
+            assert chunks == []
+            return
+        assert chunks[0][0] == 0 and chunks[-1][1] == len(counts)
+        assert all(chunks[i][1] == chunks[i + 1][0] for i in range(len(chunks) - 1))
+        for a, b in chunks:
+            assert 1 <= b - a <= max_structs
+            assert sum(counts[a:b]) <= max_atoms or b - a == 1
+
+    check_partition()
+    check_chunks()
+
+
 def test_synthetic_workloads_are_seeded_and_sane():
     a = synthetic.druglike_batch(3)
     b = synthetic.druglike_batch(3)
