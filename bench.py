@@ -66,7 +66,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the records measured outside the C2 timed region (md: C1/C3/C4 single-trajectory latency, "
-                         "variants: Tiny / Ultra-tiny on C2 shapes)")
+                         "variants: Tiny / Ultra-tiny on C2 shapes, sweep_1gpu: a C5 sample on one GPU)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -409,6 +409,53 @@ def variants_record(args, dev, steps=20):
         out[variant] = {"structures_per_s": B / (ms * 1e-3), "ms_per_step": ms, "steps": steps}
     return out
 
+
+
+def sweep_record(args, dev, distinct=4096, repeat=6, passes=3):
+    """BASELINE config 5 at ONE GPU inside the default run (the 2 / 4 / 8-GPU form is ``--mode sweep``): a ragged
+    screening list (20 - 80 atoms per structure) as host arrays through ``evaluate_arrays`` -- validation,
+    FP64 -> FP32 staging, micro-batches of <= 262 144 atoms with the copies of batch k+1 / k-1 under the kernels of
+    batch k, results back as host arrays -- for Original, Tiny and Ultra-tiny; wall clock, best of ``passes``.
+    The list is ``distinct`` generated structures repeated ``repeat`` times (generating 100 000 structures in this
+    process would take minutes; the device does not cache anything between structures)."""
+    import gc
+    import torch
+    from mlff_distiller_b200.ase_calculator import StudentForceFieldCalculator
+    numbers, pos, counts = sweep_shard(0, distinct, 1)
+    numbers, pos, counts = np.tile(numbers, repeat), np.tile(pos, (repeat, 1)), np.tile(counts, repeat)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    rec = {"structures": int(len(counts)), "atoms": int(len(numbers)), "distinct_structures": int(distinct),
+           "api": "StudentForceFieldCalculator.evaluate_arrays (host arrays in, host arrays out), 1 GPU",
+           "timing": f"wall clock around the call, best of {passes} passes"}
+    for variant in ("original", "tiny", "ultra_tiny"):
+        calc = StudentForceFieldCalculator(ROOT / "tests" / "golden" / VARIANT_FILES[variant], device=str(dev),
+                                          precision=args.precision, filter_mode=args.filter_mode)
+        warm = max(1, min(int(np.searchsorted(offs, calc.max_atoms_per_call, side="right")) - 1, len(counts)))
+        for _ in range(2):   # sizes the workspace and the pinned staging
+            calc.evaluate_arrays(numbers[: offs[warm]], pos[: offs[warm]], counts[:warm])
+        times = []
+        for _ in range(passes):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            e, f = calc.evaluate_arrays(numbers, pos, counts)
+            torch.cuda.synchronize(dev)
+            times.append(time.perf_counter() - t0)
+        if len(e) != len(counts) or f.shape != (len(numbers), 3) or not (np.isfinite(e).all() and np.isfinite(f).all()):
+            raise RuntimeError(f"sweep record: bad results for {variant}")
+        per_copy = np.asarray(e, dtype=np.float64).reshape(repeat, distinct)
+        rec[variant] = {"structures_per_s": len(counts) / min(times), "seconds": min(times),
+                        "max_energy_spread_between_repeats_eV": float(np.abs(per_copy - per_copy[0]).max())}
+        del calc
+        gc.collect()
+    return rec
+
+
+def guarded(record, *a, **k):
+    """The records measured outside the timed region must never cost the headline line: a failure is reported in place."""
+    try:
+        return record(*a, **k)
+    except Exception as e:   # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:500]}
 
 
 # ------------------------------------------------------------------------------------------
@@ -766,9 +813,10 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"], out["parity"] = cpu_baseline(args, gpu_reference if args.atoms * B == N else None)
     if world == 1 and not args.no_extras:
-        out["md"] = md_record(args, dev)
+        out["md"] = guarded(md_record, args, dev)
         if args.variant == "original":
-            out["variants"] = variants_record(args, dev)
+            out["variants"] = guarded(variants_record, args, dev)
+            out["sweep_1gpu"] = guarded(sweep_record, args, dev)
     print(json.dumps(out))
     if out.get("parity") is not None and not out["parity"]["ok"]:
         raise SystemExit(f"parity check failed at the benchmarked size: {out['parity']}")

@@ -396,3 +396,44 @@ def test_minimum_image_check_is_shared_by_every_entry_point_that_takes_a_cell():
     z, pos, counts = np.array([1, 8, 1, 8]), np.zeros((4, 3)), np.array([2, 2])
     with pytest.raises(ValueError, match="structure 1, axis 0"):
         calc._evaluate_arrays(z, pos, counts, np.stack([np.eye(3) * 20, np.eye(3) * 7]), np.ones((2, 3), dtype=bool), None)
+
+
+def test_bench_sweep_record_glue_with_a_stand_in_calculator(monkeypatch):
+    """bench.py's one-GPU C5 record (ragged list -> evaluate_arrays -> structures/s per variant) and the guard that
+    keeps a failing extra record from costing the headline line, exercised without a GPU."""
+    import importlib.util
+    import types
+    import torch
+    spec = importlib.util.spec_from_file_location("bench_under_test", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    import mlff_distiller_b200.ase_calculator as ac
+    calls = []
+
+    class FakeCalc:
+        max_atoms_per_call = 1500
+
+        def __init__(self, path, device, precision, filter_mode):
+            assert path.exists()
+            calls.append(path.name)
+
+        def evaluate_arrays(self, numbers, positions, counts):
+            assert numbers.dtype == np.int64 and positions.dtype == np.float64 and int(counts.sum()) == len(numbers)
+            offs = np.concatenate([[0], np.cumsum(counts)])
+            e = np.add.reduceat(positions.sum(1), offs[:-1]).astype(np.float32)
+            return e, (positions * 0.5).astype(np.float32)
+
+    monkeypatch.setattr(ac, "StudentForceFieldCalculator", FakeCalc)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    args = types.SimpleNamespace(precision="tc", filter_mode="spline")
+    rec = bench.sweep_record(args, "cpu", distinct=40, repeat=3, passes=2)
+    assert rec["structures"] == 120 and rec["distinct_structures"] == 40 and rec["atoms"] % 3 == 0
+    assert calls == ["weights_original.npz", "weights_tiny.npz", "weights_ultra_tiny.npz"]
+    for v in ("original", "tiny", "ultra_tiny"):
+        assert rec[v]["structures_per_s"] > 0 and rec[v]["max_energy_spread_between_repeats_eV"] == 0.0
+
+    def boom():
+        raise RuntimeError("no device")
+
+    assert bench.guarded(boom) == {"error": "RuntimeError: no device"}
+    assert bench.guarded(lambda x: x + 1, 1) == 2
