@@ -252,7 +252,12 @@ def load_any(path: Union[str, Path]) -> Tuple[Dict[str, np.ndarray], ModelConfig
         if is_torchscript_archive(path):
             ckpt = torch.jit.load(str(path), map_location="cpu")
         else:
-            ckpt = torch.load(path, map_location="cpu", weights_only=False)
+            try:   # tensors, containers and primitives only: nothing in the file gets to run code
+                ckpt = torch.load(path, map_location="cpu", weights_only=True)
+            except Exception:
+                # like the reference (student_model.py:1116): trainer checkpoints may carry arbitrary
+                # pickled objects (configs, optimizer / scheduler state); only for files the caller trusts
+                ckpt = torch.load(path, map_location="cpu", weights_only=False)
         if isinstance(ckpt, torch.jit.ScriptModule):
             # TorchScript export of the (Z, R) -> E wrapper (scripts/export_to_torchscript.py:77-104):
             # the parameters live under the wrapper's ``model.`` attribute
