@@ -84,3 +84,27 @@ def test_no_cpu_fallback():
     rc = lib.mlffd_model_create(ctypes.byref(h), 0, ctypes.byref(mc),
                                 blob.ctypes.data_as(ctypes.c_void_p), blob.size)
     assert rc == _lib.MLFFD_ECUDA
+
+
+def test_header_is_plain_c99():
+    """The drop-in boundary is a C ABI: include/mlffd.h must compile as C99 (no C++ or torch types), warning-free,
+    and a C translation unit that takes the address of every declared entry point must compile against it."""
+    import shutil
+    import subprocess
+    import tempfile
+    from pathlib import Path
+    from mlff_distiller_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    header = Path(__file__).resolve().parents[1] / "include" / "mlffd.h"
+    proc = subprocess.run([gcc, "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", str(header)],
+                          capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    with tempfile.TemporaryDirectory() as tmp:
+        src = Path(tmp) / "use_all.c"
+        body = "\n".join(f"    p[{i}] = (const void*)(size_t)&{name};" for i, name in enumerate(_lib.EXPORTS))
+        src.write_text(f'#include <stddef.h>\n#include "mlffd.h"\nconst void* p[{len(_lib.EXPORTS)}];\nvoid take(void) {{\n{body}\n}}\n')
+        proc = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", str(header.parent), "-c", str(src), "-o", str(Path(tmp) / "use_all.o")],
+                              capture_output=True, text=True)
+        assert proc.returncode == 0, proc.stderr
